@@ -1,0 +1,231 @@
+/*
+ * soundgen_b200.h -- C ABI of libsoundgen_b200.so
+ *
+ * B200 (sm_100a) implementation of soundgen's per-frame source-filter synthesis
+ * path.  The reference (nemochina2008/soundgen_beta) is pure R and has no FFI for
+ * this path, so each entry point below replaces an R function (file:line under
+ * the reference tree) and is what the package's `.Call` shim binds
+ * (r/src/rshim.c).
+ *
+ * Conventions
+ *   - plain C, POD structs, pointers + sizes; no C++ / torch types.
+ *   - all host buffers are caller-owned and read-only unless named `out_*`.
+ *   - matrices are column-major (R layout); indices returned as artefacts are
+ *     1-based like R's.
+ *   - every function returns SGB_OK (0) or a negative error code; the message is
+ *     available from sgb_last_error() (thread-local).
+ *   - there is NO CPU fallback: without a usable CUDA device every compute
+ *     entry point fails with SGB_ERR_CUDA.
+ *   - random draws are never made inside the library: normals / uniforms are
+ *     drawn by the caller from R's set.seed stream in the reference's order and
+ *     passed in as buffers ("z" = standard normals, "u" = uniforms).
+ */
+#ifndef SOUNDGEN_B200_H
+#define SOUNDGEN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGB_OK                 0
+#define SGB_ERR_INVALID       -1   /* bad argument                                   */
+#define SGB_ERR_CUDA          -2   /* CUDA runtime failure / no device               */
+#define SGB_ERR_UNSUPPORTED   -3   /* valid in the reference, not in this library     */
+#define SGB_ERR_SYNTH         -4   /* the reference would stop() ("Failed to generate
+                                      the new syllable!", soundgen.R:624-626)          */
+#define SGB_ERR_STREAM        -5   /* a z/u stream was shorter than the draws needed  */
+#define SGB_ERR_STATE         -6   /* call sequence error on a batch handle           */
+
+#define SGB_VERSION 100
+
+int         sgb_version(void);
+const char *sgb_last_error(void);
+int         sgb_device_count(void);
+int         sgb_set_device(int device);
+
+/* ------------------------------------------------------------------------- */
+/* Batched whole-path interface: replaces the bout loop of soundgen()         */
+/* (R/soundgen.R:482-849) for many calls at once.                             */
+/* ------------------------------------------------------------------------- */
+
+/* Anchors are (time, value) pairs stored interleaved in the `anchors` pool;
+ * contour evaluation follows getSmoothContour (R/smoothContours.R:53-227) for 1
+ * anchor (flat), 2 anchors (seq) and method = 'spline'; a loess contour (3-10
+ * anchors, host-side in R) must be passed pre-evaluated where the struct has a
+ * `*_pre_off` field. */
+
+/* One voiced syllable = one generateHarmonics() call (R/source.R:173-205). */
+typedef struct sgb_syllable {
+  int32_t kind;          /* 1 = synthesise; 0 = `silent_len` zeros (soundgen.R:608-613);
+                            2 = raw samples given in `pitch` pool (used by sgb_filter)  */
+  int32_t silent_len;
+  int64_t pitch_off;     /* offset into `pitch` pool (doubles)                        */
+  int32_t pitch_len;     /* P = round(dur * pitchSamplingRate / 1000)                 */
+  int32_t pause_after;   /* zeros appended after the syllable (soundgen.R:632-640)    */
+  int64_t z_off;         /* offset into `z` pool: this syllable's normal stream       */
+  int32_t z_cap;         /* normals available                                         */
+  int32_t ampl_n;        /* amplAnchors: number of anchors, 0 = NA                    */
+  int64_t ampl_off;      /* offset (in pairs) into `anchors`                          */
+  double attackLen, nonlinBalance, jitterDep, jitterLen, vibratoFreq, vibratoDep,
+         shimmerDep, rolloff, rolloffOct, rolloffKHz, rolloffParab, rolloffParabHarm,
+         rolloff_perAmpl, temperature, pitchDriftDep, pitchDriftFreq,
+         randomWalk_trendStrength, shortestEpoch, subFreq, subDep, samplingRate,
+         pitchFloor, pitchCeiling, pitchSamplingRate, throwaway;
+} sgb_syllable;
+
+/* One formant filter = one getSpectralEnvelope() call (R/sourceSpectrum.R:261-283). */
+typedef struct sgb_envelope {
+  int32_t n_formants;    /* 0 = formants NA and vocalTract NULL (lip radiation only)  */
+  int32_t tracks_given;  /* 1: `formants` holds nc pre-upsampled rows per formant (the
+                            host ran the stochastic block sourceSpectrum.R:346-415)   */
+  int64_t formant_off;   /* offset into `formant_index` (one {off,n} entry per formant) */
+  int32_t mouth_n;       /* mouthAnchors: number of anchors, 0 = NA                   */
+  int32_t nc_fixed;      /* >0: number of columns; 0: one column per STFT frame       */
+  int64_t mouth_off;     /* offset (pairs) into `anchors`                             */
+  double formantDep, rolloffLip, mouthOpenThres, openMouthBoost,
+         vocalTract /* NaN = NULL */, samplingRate, speedSound, smoothLinearFactor;
+} sgb_envelope;
+
+/* One unvoiced segment = one generateNoise() call (R/source.R:57-68). */
+typedef struct sgb_noise {
+  int32_t len;           /* unvoicedDur_syl                                           */
+  int32_t insertion;     /* syllableStartIdx[s] (1-based, may be < 1)                 */
+  int32_t mix;           /* 0: added before filtering (soundgen.R:708-714);
+                            1: added after filtering (soundgen.R:813-818)             */
+  int32_t wl;            /* windowLength_points                                       */
+  int64_t u_off;         /* offset into `u` pool (nr*nc uniforms, column-major)       */
+  int64_t anchor_off;    /* noise anchors (time ms, value dB), offset in pairs        */
+  int32_t anchor_n;
+  int32_t env_id;        /* index into envelopes[], -1 = no filterNoise               */
+  int64_t strength_pre_off; /* >= 0: pre-evaluated dB contour (len doubles) in `pre`  */
+  double rolloffNoise, attackLen, samplingRate, overlap;
+} sgb_noise;
+
+/* One bout (R/soundgen.R:482-843). */
+typedef struct sgb_bout {
+  int32_t syl_begin, syl_end;       /* [begin, end) in syllables[]                    */
+  int32_t noise_begin, noise_end;   /* [begin, end) in noises[]                       */
+  int32_t env_id;                   /* main vocal-tract filter                        */
+  int32_t moving;                   /* movingFormants (soundgen.R:751-759)            */
+  int32_t wl;                       /* windowLength_points before the clamp at :743   */
+  int32_t lead_silence;             /* zeros before this bout in the call's output    */
+  int32_t tail_silence;             /* zeros after it (addSilence on the last bout)   */
+  int32_t aglobal_n;                /* amplAnchorsGlobal anchors (values already
+                                       2^(dB/10), soundgen.R:724), 0 = NA             */
+  int64_t aglobal_off;
+  double overlap, amDep, amFreq, amShape, samplingRate, throwaway;
+} sgb_bout;
+
+/* One soundgen() call = consecutive bouts. */
+typedef struct sgb_call {
+  int32_t bout_begin, bout_end;
+} sgb_call;
+
+typedef struct sgb_formant_ref { int64_t off; int32_t n; int32_t pad; } sgb_formant_ref;
+
+typedef struct sgb_batch_desc {
+  int32_t n_calls, n_bouts, n_syllables, n_noises, n_envelopes, n_formant_refs;
+  const sgb_call        *calls;
+  const sgb_bout        *bouts;
+  const sgb_syllable    *syllables;
+  const sgb_noise       *noises;
+  const sgb_envelope    *envelopes;
+  const sgb_formant_ref *formant_index;
+  const double *pitch;    int64_t n_pitch;     /* pitch contours                       */
+  const double *anchors;  int64_t n_anchors;   /* (time, value) pairs: 2*n doubles     */
+  const double *formants; int64_t n_formants;  /* rows of (time, freq, amp, width)     */
+  const double *z;        int64_t n_z;         /* standard normals                     */
+  const void   *u;        int64_t n_u;         /* uniforms, double or float            */
+  int32_t       u_is_float;
+  int32_t       reserved;
+  const double *pre;      int64_t n_pre;       /* pre-evaluated contours               */
+} sgb_batch_desc;
+
+typedef struct sgb_batch sgb_batch;   /* opaque */
+
+/* Stage timings of the last sgb_batch_run (CUDA events on the library's stream). */
+enum { SGB_T_H2D = 0, SGB_T_CONTROL, SGB_T_AMPL, SGB_T_SYNTH, SGB_T_COMPOSE,
+       SGB_T_NOISE, SGB_T_ASSEMBLE, SGB_T_ENVELOPE, SGB_T_FILTER, SGB_T_FINALIZE,
+       SGB_T_D2H, SGB_T_TOTAL, SGB_T_COUNT };
+
+typedef struct sgb_run_info {
+  int64_t total_samples;      /* sum of output lengths over calls                     */
+  int64_t synth_partials;     /* sum over epochs of rows * samples (K1 work units)    */
+  int64_t synth_samples;      /* samples produced by K1                               */
+  int64_t filter_samples;     /* samples emitted by K2                                */
+  int64_t filter_frames;      /* STFT frames processed by K2 (incl. warm-up)          */
+  int64_t noise_samples;      /* samples emitted by K5                                */
+  int32_t kernel_launches;    /* kernels launched by this run                         */
+  int32_t n_failed;           /* syllables/bouts whose reference call would stop()    */
+  float   ms[SGB_T_COUNT];
+} sgb_run_info;
+
+int sgb_batch_create(sgb_batch **out);
+void sgb_batch_destroy(sgb_batch *b);
+
+/* Copies the description to the device (pinned staging + cudaMemcpyAsync). */
+int sgb_batch_upload(sgb_batch *b, const sgb_batch_desc *desc);
+/* Runs the whole path on data already resident on the device. */
+int sgb_batch_run(sgb_batch *b, sgb_run_info *info);
+/* Per-call output lengths (valid after run). */
+int sgb_batch_lengths(sgb_batch *b, int64_t *out_len /* n_calls */);
+/* Concatenated outputs of all calls, call c at sum(len[0..c)). */
+int sgb_batch_fetch_f32(sgb_batch *b, float *out, int64_t n);
+int sgb_batch_fetch_f64(sgb_batch *b, double *out, int64_t n);
+/* Per-call failure flags (0 = ok, else an SGB_ERR_* code). */
+int sgb_batch_status(sgb_batch *b, int32_t *out_status /* n_calls */);
+
+/* Intermediate results (valid after run).  Sizes via the *_len calls. */
+int sgb_batch_syllable_len(sgb_batch *b, int32_t syl, int64_t *out_len);
+int sgb_batch_syllable_fetch(sgb_batch *b, int32_t syl, double *out, int64_t n);
+int sgb_batch_noise_fetch(sgb_batch *b, int32_t noise, double *out, int64_t n);
+
+/* Integer artefacts of one voiced syllable (bit-exact contract). */
+typedef struct sgb_syl_artefacts {
+  int32_t nGC, nHarmonics, rows_kept, nEpochs, n_upsampled, n_jitter_idx, z_used, status;
+  double  raw_max;
+} sgb_syl_artefacts;
+int sgb_batch_artefacts(sgb_batch *b, int32_t syl, sgb_syl_artefacts *out);
+/* which: 0 gc (nGC), 1 gc_upsampled (nGC+1), 2 nSubharm (nGC), 3 rw_bin (nGC),
+ *        4 jitter idx, 5 epochs (2*nEpochs: start,end), 6 zero crossings
+ *        (2*nEpochs: zc1, zc2; 0 = NA) */
+int sgb_batch_artefact_ints(sgb_batch *b, int32_t syl, int which, int32_t *out, int32_t cap);
+int sgb_batch_pitch_per_gc(sgb_batch *b, int32_t syl, double *out, int32_t cap);
+
+/* ------------------------------------------------------------------------- */
+/* Single-call interfaces                                                     */
+/* ------------------------------------------------------------------------- */
+
+/* getRolloff (R/sourceSpectrum.R:71-186).  rolloff / rolloffOct / rolloffKHz are
+ * vectors of length 1 or nGC (n_* gives which).  out: nHarmonics x nGC doubles,
+ * column-major, of which the first *out_rows rows per column are valid after
+ * compaction (leading dimension stays nHarmonics); rownames are 1..*out_rows.
+ * rolloffParabCeiling < 0 means NULL. */
+int sgb_get_rolloff(const double *pitch_per_gc, int32_t nGC, int32_t nHarmonics,
+                    const double *rolloff, int32_t n_rolloff,
+                    const double *rolloffOct, int32_t n_rolloffOct,
+                    const double *rolloffKHz, int32_t n_rolloffKHz,
+                    double rolloffParab, double rolloffParabHarm,
+                    double rolloffParabCeiling, double baseline, double throwaway,
+                    double samplingRate, double *out, int32_t *out_rows);
+
+/* getSpectralEnvelope (R/sourceSpectrum.R:261-566), deterministic part.
+ * formants: n_formants blocks, block f has formant_n[f] rows of
+ * (time, freq, amp, width).  out: nr x nc doubles, column-major. */
+int sgb_get_spectral_envelope(int32_t nr, int32_t nc, const sgb_envelope *env,
+                              const double *formants, const int32_t *formant_n,
+                              const double *mouth_anchors, double *out);
+
+/* STFT -> envelope multiply -> ISTFT -> /max (R/soundgen.R:743-807 with
+ * seewave::stft / istft, seewave.r:7782-7818, :3447-3487).  envelope: nr x nInt,
+ * nInt in {1, nc}.  out must hold sgb_filter_len() doubles. */
+int64_t sgb_filter_len(int64_t len, int32_t wl, double overlap);
+int sgb_filter(const double *sound, int64_t len, const double *envelope, int32_t nInt,
+               int32_t wl, double overlap, double *out, int64_t out_cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOUNDGEN_B200_H */

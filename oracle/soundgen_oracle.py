@@ -530,6 +530,9 @@ class HarmonicsArtefacts:
     n_upsampled: int = 0
     z_used: int = 0
     raw_max: float = 0.0               # max(waveform) before normalisation
+    mats: list = None                  # per-epoch (matrix, rownames)
+    integr: np.ndarray = None          # cumsum(pitch_upsampled) / samplingRate
+    epoch_waves: list = field(default_factory=list)
 
 
 def generateHarmonics(pitch, attackLen=50, nonlinBalance=0, nonlinDep=0, jitterDep=0,
@@ -634,11 +637,13 @@ def generateHarmonics(pitch, attackLen=50, nonlinBalance=0, nonlinDep=0, jitterD
         epochs = np.array([[1, nGC]])
     art.epochs = epochs
     art.epoch_rows = [m[1] for m in mats]
+    art.mats = mats
 
     pitch_upsampled, gc_upsampled = upsample(pitch_per_gc, samplingRate)  # :382
     art.gc_upsampled = gc_upsampled
     art.n_upsampled = pitch_upsampled.size
     integr = r_cumsum(pitch_upsampled) / samplingRate  # :385
+    art.integr = integr
     waveform = np.zeros(1)  # `waveform = 0`
 
     for e in range(epochs.shape[0]):  # :389-427
@@ -653,6 +658,8 @@ def generateHarmonics(pitch, attackLen=50, nonlinBalance=0, nonlinDep=0, jitterD
         for h in range(mat.shape[0]):
             am_upsampled = r_approx(mat[h, :], n_e, x=xk)
             waveform_epoch = waveform_epoch + np.sin(two_pi_integr * nm[h]) * am_upsampled
+        if want_artefacts:
+            art.epoch_waves.append(waveform_epoch)
         waveform, zc1, zc2 = crossFade(waveform, waveform_epoch, samplingRate, crossLen=15)
         art.zc.append((zc1, zc2))
 
