@@ -1,0 +1,700 @@
+"""Python mirror of soundgen's R shells over the C ABI (libsoundgen_b200.so).
+
+Same function names and argument meaning as the reference
+(R/soundgen.R:208-277, R/source.R:57-68, :173-205, R/sourceSpectrum.R:71-82, :261-283);
+all sample-rate work is done by the CUDA library -- there is no CPU path here.
+R is absent from the build image, so this mirror stands in for the R shells of `r/R/`
+(which call the same entry points through `.Call`).
+
+Random draws: the library never draws.  `z` = standard normals (R `rnorm` stream) per
+voiced syllable, `u` = uniforms (`runif`) per noise segment, drawn by the caller in the
+reference's order.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _abi, host
+from ._abi import (BatchDesc, Bout, Call, Envelope, FormantRef, Noise, RunInfo, SylArtefacts,
+                   Syllable)
+
+
+class SoundgenError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__('%s (code %d)' % (msg, code))
+        self.code = code
+
+
+def _check(rc):
+    if rc < 0:
+        raise SoundgenError(rc, _abi.load().sgb_last_error().decode())
+    return rc
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
+
+
+DEFAULT_FORMANTS = [dict(time=0, freq=860, amp=30, width=120),
+                    dict(time=0, freq=1280, amp=40, width=120),
+                    dict(time=0, freq=2900, amp=25, width=200)]
+
+
+def _formant_rows(f):
+    """one formant (dict/list/array) -> (k,4) array time, freq, amp, width"""
+    if isinstance(f, dict):
+        cols = [np.atleast_1d(np.asarray(f[k], dtype=np.float64)) for k in ('time', 'freq', 'amp', 'width')]
+        n = max(c.size for c in cols)
+        return np.stack([np.resize(c, n) for c in cols], axis=1)
+    a = np.asarray(f, dtype=np.float64)
+    return a.reshape(-1, 4)
+
+
+def _formant_list(formants):
+    if formants is None:
+        return None
+    if isinstance(formants, str):
+        raise NotImplementedError('phoneme strings need the presets dictionary (convertStringToFormants, '
+                                  'R/utilities_soundgen.R:135-222): pass a list of formants')
+    if isinstance(formants, dict):
+        formants = list(formants.values())
+    return [_formant_rows(f) for f in formants]
+
+
+class BatchBuilder:
+    """Accumulates soundgen() calls into the flat pools of an sgb_batch_desc."""
+
+    def __init__(self, u_dtype=np.float64):
+        self.calls, self.bouts, self.syls, self.noises, self.envs, self.frefs = [], [], [], [], [], []
+        self.pitch, self.anchors, self.formants, self.z, self.u, self.pre = [], [], [], [], [], []
+        self.n_pitch = self.n_anchors = self.n_formants = self.n_z = self.n_u = self.n_pre = 0
+        self.u_dtype = np.dtype(u_dtype)
+        self._keep = []
+
+    # ---- pools ----
+    def _add_pitch(self, p):
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        off = self.n_pitch
+        self.pitch.append(p)
+        self.n_pitch += p.size
+        return off
+
+    def _add_anchors(self, an):
+        t, v = an
+        a = np.stack([np.asarray(t, dtype=np.float64), np.asarray(v, dtype=np.float64)], axis=1)
+        off = self.n_anchors
+        self.anchors.append(a.ravel())
+        self.n_anchors += a.shape[0]
+        return off, a.shape[0]
+
+    def _add_z(self, z):
+        z = np.zeros(0) if z is None else np.ascontiguousarray(z, dtype=np.float64)
+        off = self.n_z
+        self.z.append(z)
+        self.n_z += z.size
+        return off, z.size
+
+    def _add_u(self, u):
+        u = np.ascontiguousarray(u, dtype=self.u_dtype)
+        off = self.n_u
+        self.u.append(u)
+        self.n_u += u.size
+        return off
+
+    def _add_pre(self, c):
+        c = np.ascontiguousarray(c, dtype=np.float64)
+        off = self.n_pre
+        self.pre.append(c)
+        self.n_pre += c.size
+        return off
+
+    def add_envelope(self, formants, formantDep=1, rolloffLip=6, mouthAnchors=None, mouthOpenThres=0,
+                     openMouthBoost=0, vocalTract=None, samplingRate=16000, speedSound=35400,
+                     smoothLinearFactor=1, nc_fixed=0, tracks=None):
+        """Registers one getSpectralEnvelope() specification; resolves the vocalTract /
+        schwa defaults of R/sourceSpectrum.R:294-315 (argument munging, host side)."""
+        fl = _formant_list(formants)
+        if fl is not None and vocalTract is None and fl[0].shape[1] > 2:
+            freqs = np.concatenate([f[:, 1] for f in fl])
+            if freqs.size > 1:
+                vocalTract = speedSound / 2 / float(np.mean(np.diff(freqs)))
+            else:
+                vocalTract = speedSound / 4 / float(fl[0][0, 1])
+        if fl is None and vocalTract is not None:
+            freq = speedSound / 4 / vocalTract
+            fl = [np.array([[0, freq, 30, 50 * (1 + freq ** 2 / 6 / 10 ** 6)]])]
+        e = Envelope()
+        e.n_formants = 0 if fl is None else len(fl)
+        e.tracks_given = 0
+        e.formant_off = len(self.frefs)
+        if tracks is not None:
+            fl = [np.asarray(t, dtype=np.float64).reshape(-1, 4) for t in tracks]
+            e.n_formants = len(fl)
+            e.tracks_given = 1
+        if fl is not None:
+            for f in fl:
+                r = FormantRef()
+                r.off = self.n_formants
+                r.n = f.shape[0]
+                self.frefs.append(r)
+                self.formants.append(np.ascontiguousarray(f, dtype=np.float64).ravel())
+                self.n_formants += f.shape[0]
+        ma = host.as_anchors(mouthAnchors)
+        if ma is not None and not np.any(np.isnan(ma[1])):
+            if 3 <= ma[0].size <= 10:
+                raise NotImplementedError('mouthAnchors with 3-10 anchors use loess in the reference')
+            e.mouth_off, e.mouth_n = self._add_anchors(ma)
+        else:
+            e.mouth_n = 0
+        e.nc_fixed = int(nc_fixed)
+        e.formantDep, e.rolloffLip = float(formantDep), float(rolloffLip)
+        e.mouthOpenThres, e.openMouthBoost = float(mouthOpenThres), float(openMouthBoost)
+        e.vocalTract = float('nan') if vocalTract is None else float(vocalTract)
+        e.samplingRate, e.speedSound = float(samplingRate), float(speedSound)
+        e.smoothLinearFactor = float(smoothLinearFactor)
+        self.envs.append(e)
+        return len(self.envs) - 1
+
+    def add_syllable(self, pitch, z=None, amplAnchors=None, pause_after=0, contour_method='loess', **pars):
+        s = Syllable()
+        s.kind = 1
+        s.pitch_off = self._add_pitch(pitch)
+        s.pitch_len = int(np.size(pitch))
+        s.pause_after = int(pause_after)
+        s.z_off, s.z_cap = self._add_z(z)
+        an = host.as_anchors(amplAnchors)
+        if an is not None:
+            if 3 <= an[0].size <= 10 and contour_method != 'spline':
+                raise NotImplementedError('amplAnchors with 3-10 anchors use loess in the reference '
+                                          "(pass contour_method='spline')")
+            s.ampl_off, s.ampl_n = self._add_anchors(an)
+        d = dict(attackLen=50, nonlinBalance=0, jitterDep=0, jitterLen=1, vibratoFreq=100, vibratoDep=0,
+                 shimmerDep=0, rolloff=-18, rolloffOct=-2, rolloffKHz=-6, rolloffParab=0,
+                 rolloffParabHarm=3, rolloff_perAmpl=12, temperature=0, pitchDriftDep=.5,
+                 pitchDriftFreq=.125, randomWalk_trendStrength=.5, shortestEpoch=300, subFreq=100,
+                 subDep=0, samplingRate=16000, pitchFloor=75, pitchCeiling=3500, pitchSamplingRate=3500,
+                 throwaway=-120)
+        for k, v in pars.items():
+            if k in d:
+                d[k] = v
+        for k in _abi.SYL_DOUBLES:
+            setattr(s, k, float(d[k]))
+        self.syls.append(s)
+        return len(self.syls) - 1
+
+    def add_silent_syllable(self, n, pause_after=0):
+        s = Syllable()
+        s.kind = 0
+        s.silent_len = int(n)
+        s.pause_after = int(pause_after)
+        self.syls.append(s)
+        return len(self.syls) - 1
+
+    def add_noise(self, length, noiseAnchors, u, rolloffNoise=-6, attackLen=10, windowLength_points=1024,
+                  samplingRate=16000, overlap=75, env_id=-1, insertion=1, mix=0, strength=None):
+        n = Noise()
+        n.len = int(length)
+        n.insertion = int(insertion)
+        n.mix = int(mix)
+        n.wl = int(windowLength_points)
+        n.u_off = self._add_u(u)
+        an = host.as_anchors(noiseAnchors)
+        n.strength_pre_off = -1
+        if strength is not None:
+            n.strength_pre_off = self._add_pre(strength)
+            n.anchor_n = 0
+        else:
+            if 3 <= an[0].size <= 10:
+                raise NotImplementedError('noiseAnchors with 3-10 anchors use loess in the reference: '
+                                          'pass a pre-evaluated `strength` contour')
+            n.anchor_off, n.anchor_n = self._add_anchors(an)
+        n.env_id = int(env_id)
+        n.rolloffNoise, n.attackLen = float(rolloffNoise), float(attackLen)
+        n.samplingRate, n.overlap = float(samplingRate), float(overlap)
+        self.noises.append(n)
+        return len(self.noises) - 1
+
+    def add_bout(self, syl_begin, syl_end, noise_begin, noise_end, env_id, moving, wl, overlap=75,
+                 lead_silence=0, tail_silence=0, amplAnchorsGlobal=None, amDep=0, amFreq=30, amShape=0,
+                 samplingRate=16000, throwaway=-120):
+        b = Bout()
+        b.syl_begin, b.syl_end, b.noise_begin, b.noise_end = syl_begin, syl_end, noise_begin, noise_end
+        b.env_id, b.moving, b.wl = int(env_id), int(bool(moving)), int(wl)
+        b.lead_silence, b.tail_silence = int(lead_silence), int(tail_silence)
+        if amplAnchorsGlobal is not None:
+            b.aglobal_off, b.aglobal_n = self._add_anchors(amplAnchorsGlobal)
+        b.overlap, b.amDep, b.amFreq, b.amShape = float(overlap), float(amDep), float(amFreq), float(amShape)
+        b.samplingRate, b.throwaway = float(samplingRate), float(throwaway)
+        self.bouts.append(b)
+        return len(self.bouts) - 1
+
+    def add_call(self, bout_begin, bout_end):
+        c = Call()
+        c.bout_begin, c.bout_end = bout_begin, bout_end
+        self.calls.append(c)
+        return len(self.calls) - 1
+
+    # ---- the bout orchestrator's host-side part (R/soundgen.R:278-699) ----
+    def add_soundgen(self, repeatBout=1, nSyl=1, sylLen=300, pauseLen=200,
+                     pitchAnchors=((0, .1, .9, 1), (100, 150, 135, 100)), pitchAnchorsGlobal=None,
+                     temperature=0.025, maleFemale=0, creakyBreathy=0, nonlinBalance=0, nonlinDep=50,
+                     jitterLen=1, jitterDep=3, vibratoFreq=5, vibratoDep=0, shimmerDep=0, attackLen=50,
+                     rolloff=-12, rolloffOct=-12, rolloffKHz=-6, rolloffParab=0, rolloffParabHarm=3,
+                     rolloffLip=6, formants='default', formantDep=1, formantDepStoch=30, vocalTract=15.5,
+                     subFreq=100, subDep=100, shortestEpoch=300, amDep=0, amFreq=30, amShape=0,
+                     noiseAnchors=((0, 300), (-120, -120)), formantsNoise=None, rolloffNoise=-14,
+                     mouthAnchors=((0, 1), (.5, .5)), amplAnchors=None, amplAnchorsGlobal=None,
+                     samplingRate=16000, windowLength=50, overlap=75, addSilence=100, pitchFloor=50,
+                     pitchCeiling=3500, pitchSamplingRate=3500, throwaway=-120,
+                     invalidArgAction='adjust', z=None, u=None, contour_method='loess',
+                     pitchContours=None, warn=None):
+        """Adds one soundgen() call.  z: list of normal streams (one per voiced syllable, in
+        order); u: list of uniform buffers (one per noise segment).  Returns the call index."""
+        loc = dict(locals())
+        for p, (dflt, lo, hi) in host.PERMITTED.items():   # soundgen.R:279-302
+            v = loc[p]
+            if not isinstance(v, (int, float)) or v < lo or v > hi:
+                if invalidArgAction == 'abort':
+                    raise ValueError('%s must be between %s and %s' % (p, lo, hi))
+                if invalidArgAction == 'ignore':
+                    if warn is not None:
+                        warn.append("%s outside its range in 'permittedValues'" % p)
+                else:
+                    loc[p] = dflt
+                    if warn is not None:
+                        warn.append('%s outside permitted range, reset to %s' % (p, dflt))
+        g = lambda k: loc[k]
+        repeatBout, nSyl, sylLen, pauseLen, temperature = g('repeatBout'), g('nSyl'), g('sylLen'), g('pauseLen'), g('temperature')
+        maleFemale, creakyBreathy, nonlinBalance, nonlinDep = g('maleFemale'), g('creakyBreathy'), g('nonlinBalance'), g('nonlinDep')
+        jitterDep, jitterLen, vibratoFreq, vibratoDep, shimmerDep = g('jitterDep'), g('jitterLen'), g('vibratoFreq'), g('vibratoDep'), g('shimmerDep')
+        attackLen, rolloff, rolloffOct, rolloffParab, rolloffParabHarm = g('attackLen'), g('rolloff'), g('rolloffOct'), g('rolloffParab'), g('rolloffParabHarm')
+        rolloffKHz, rolloffLip, formantDep, vocalTract = g('rolloffKHz'), g('rolloffLip'), g('formantDep'), g('vocalTract')
+        subFreq, subDep, shortestEpoch, amDep, amFreq, amShape = g('subFreq'), g('subDep'), g('shortestEpoch'), g('amDep'), g('amFreq'), g('amShape')
+        samplingRate, windowLength, rolloffNoise = g('samplingRate'), g('windowLength'), g('rolloffNoise')
+        if temperature > 0:
+            raise NotImplementedError('temperature > 0 at the soundgen() level draws rnorm_bounded / '
+                                      'wiggleAnchors / stochastic formants from R\'s RNG on the host '
+                                      '(SURVEY.md 8f-2); use temperature = 0 here')
+        pitchAnchors = host.as_anchors(pitchAnchors)
+        pitchAnchorsGlobal = host.as_anchors(pitchAnchorsGlobal)
+        amplAnchors = host.as_anchors(amplAnchors)
+        amplAnchorsGlobal = host.as_anchors(amplAnchorsGlobal)
+        mouthAnchors = host.as_anchors(mouthAnchors)
+        noiseAnchors = host.as_anchors(noiseAnchors, t_hi=sylLen)
+        if isinstance(formants, str) and formants == 'default':
+            formants = DEFAULT_FORMANTS
+        formants = _formant_list(formants)
+        formantsNoise = _formant_list(formantsNoise)
+        wl_points = int(math.floor(windowLength / 1000 * samplingRate / 2) * 2)   # :317
+        if creakyBreathy < 0:   # :337-351
+            nonlinBalance = min(100, nonlinBalance - creakyBreathy * 50)
+            jitterDep = max(0, jitterDep - creakyBreathy / 2)
+            shimmerDep = max(0, shimmerDep - creakyBreathy * 5)
+            subDep = subDep * 2 ** (-creakyBreathy)
+        elif creakyBreathy > 0:
+            v = np.array([-120., -120.]) + creakyBreathy * 160
+            v[v > host.NOISE_AMPL[1]] = host.NOISE_AMPL[1]
+            noiseAnchors = (np.array([0., sylLen + 100]), v)
+        rolloff = rolloff - creakyBreathy * 10
+        rolloffOct = rolloffOct - creakyBreathy * 5
+        subFreq = 2 * (subFreq - 50) / (1 + math.exp(-.1 * (50 - nonlinDep))) + 50
+        jitterDep = 2 * jitterDep / (1 + math.exp(.1 * (50 - nonlinDep)))
+        if maleFemale != 0:   # :364-379
+            if pitchAnchors is not None:
+                pitchAnchors = (pitchAnchors[0], pitchAnchors[1] * 2 ** maleFemale)
+            if formants is not None:
+                for f in formants:
+                    f[:, 1] = f[:, 1] * 1.25 ** maleFemale
+            vocalTract = vocalTract * (1 - .25 * maleFemale)
+        nSyl, repeatBout = int(math.floor(nSyl)), int(math.floor(repeatBout))
+        pars = dict(attackLen=attackLen, jitterDep=jitterDep, jitterLen=jitterLen, vibratoFreq=vibratoFreq,
+                    vibratoDep=vibratoDep, shimmerDep=shimmerDep, rolloff=rolloff, rolloffOct=rolloffOct,
+                    rolloffKHz=rolloffKHz, rolloffParab=rolloffParab, rolloffParabHarm=rolloffParabHarm,
+                    temperature=temperature, pitchDriftDep=.5, pitchDriftFreq=.125,
+                    shortestEpoch=shortestEpoch, subFreq=subFreq, subDep=subDep,
+                    nonlinBalance=nonlinBalance, pitchFloor=pitchFloor, pitchCeiling=pitchCeiling,
+                    pitchSamplingRate=pitchSamplingRate, throwaway=throwaway, samplingRate=samplingRate)
+        if pitchAnchorsGlobal is not None and np.any(pitchAnchorsGlobal[1] != 0) and nSyl > 1:   # :448-462
+            pitchDeltas = 2 ** (host.smooth_contour(pitchAnchorsGlobal, nSyl, method='spline') / 12)
+        else:
+            pitchDeltas = np.ones(nSyl)
+        if pitchAnchors is not None:   # :465-472
+            t = pitchAnchors[0]
+            if np.min(t) < 0:
+                t = t - np.min(t)
+            if np.max(t) > 1:
+                t = t / np.max(t)
+            pitchAnchors = (t, pitchAnchors[1])
+        has_noise = noiseAnchors is not None and np.sum(noiseAnchors[1] > throwaway) > 0
+        z = list(z) if isinstance(z, (list, tuple)) else ([z] if z is not None else [])
+        u = list(u) if isinstance(u, (list, tuple)) else ([u] if u is not None else [])
+        zi = ui = si = 0
+        # main vocal-tract filter (soundgen.R:751-775)
+        moving = formants is not None and max(f.shape[0] for f in formants) > 1
+        if mouthAnchors is not None and np.sum(mouthAnchors[1] != .5) > 0:
+            moving = True
+        env_main = self.add_envelope(formants, formantDep=formantDep, rolloffLip=rolloffLip,
+                                     mouthAnchors=mouthAnchors, vocalTract=vocalTract,
+                                     samplingRate=samplingRate)
+        ag = None
+        if amplAnchorsGlobal is not None and np.sum(amplAnchorsGlobal[1] < -throwaway) > 0:   # :721-724
+            if 3 <= amplAnchorsGlobal[0].size <= 10:
+                raise NotImplementedError('amplAnchorsGlobal with 3-10 anchors use loess in the reference')
+            ag = amplAnchorsGlobal
+        bout0 = len(self.bouts)
+        n_sil = int(host.rint(samplingRate / 1000 * addSilence)) if addSilence is not None else 0
+        for b in range(repeatBout):   # :482
+            if nSyl == 1:
+                syllables = np.array([[0., float(sylLen)]])
+            else:
+                rows, c = [], 0.
+                while len(rows) < nSyl:
+                    start = 1 + c
+                    end = start + sylLen
+                    rows.append([start, end])
+                    c = end + pauseLen
+                syllables = np.array(rows)
+            startIdx = host.rint(syllables[:, 0] * samplingRate / 1000)   # :517-532
+            startIdx[0] = 1
+            if noiseAnchors is not None and noiseAnchors[0][0] != 0:
+                shift = -host.rint(noiseAnchors[0][0] * samplingRate / 1000)
+                if noiseAnchors[0][0] < 0:
+                    startIdx[0] = (startIdx - shift)[0]
+                else:
+                    startIdx = startIdx - shift
+            syl_begin, noise_begin = len(self.syls), len(self.noises)
+            for s in range(syllables.shape[0]):   # :540
+                dur_syl = float(syllables[s, 1] - syllables[s, 0])
+                pause = 0
+                if s < syllables.shape[0] - 1:
+                    pause = int(math.floor((syllables[s + 1, 0] - syllables[s, 1]) * samplingRate / 1000))
+                silent = (dur_syl < host.SYLLEN_LOW or pitchAnchors is None or
+                          (noiseAnchors is not None and np.min(noiseAnchors[1]) >= 40))
+                if silent:
+                    self.add_silent_syllable(int(host.rint(dur_syl * samplingRate / 1000)), pause_after=pause)
+                else:
+                    if pitchContours is not None:
+                        pc = np.asarray(pitchContours[si], dtype=np.float64)
+                    else:
+                        pc = host.smooth_contour(pitchAnchors, int(host.rint(dur_syl * pitchSamplingRate / 1000)),
+                                                 thisIsPitch=True, method=contour_method,
+                                                 valueFloor=pitchFloor, valueCeiling=pitchCeiling)
+                    pc = pc * pitchDeltas[s]
+                    zs = z[zi] if zi < len(z) else None
+                    zi += 1
+                    self.add_syllable(pc, z=zs, amplAnchors=amplAnchors, pause_after=pause,
+                                      contour_method=contour_method, **pars)
+                si += 1
+                if has_noise:   # :643-698
+                    t = noiseAnchors[0].copy()
+                    t[t > 0] = t[t > 0] * dur_syl / sylLen
+                    rng_t = float(np.max(t) - np.min(t))
+                    ulen = int(host.rint(rng_t * samplingRate / 1000))
+                    env_n = -1
+                    if formantsNoise is not None:
+                        nInt = int(host.rint(rng_t / 10))   # :662-666 (always "moving", see oracle note)
+                        env_n = self.add_envelope(formantsNoise, formantDep=formantDep, rolloffLip=rolloffLip,
+                                                  mouthAnchors=mouthAnchors, vocalTract=vocalTract,
+                                                  samplingRate=samplingRate, nc_fixed=nInt)
+                    if ui >= len(u):
+                        raise ValueError('soundgen(): a uniform buffer `u` is needed for each noise segment')
+                    self.add_noise(ulen, (t, noiseAnchors[1]), u[ui], rolloffNoise=rolloffNoise,
+                                   attackLen=attackLen, windowLength_points=wl_points, samplingRate=samplingRate,
+                                   overlap=overlap, env_id=env_n, insertion=int(startIdx[s]),
+                                   mix=0 if formantsNoise is None else 1)
+                    ui += 1
+            lead = n_sil if b == 0 else int(pauseLen * samplingRate / 1000)   # :836-849
+            tail = n_sil if b == repeatBout - 1 else 0
+            self.add_bout(syl_begin, len(self.syls), noise_begin, len(self.noises), env_main, moving, wl_points,
+                          overlap=overlap, lead_silence=lead, tail_silence=tail, amplAnchorsGlobal=ag,
+                          amDep=amDep, amFreq=amFreq, amShape=amShape, samplingRate=samplingRate,
+                          throwaway=throwaway)
+        return self.add_call(bout0, len(self.bouts))
+
+    def noise_uniform_count(self, length, windowLength_points, overlap=75):
+        """number of runif() draws generateNoise makes (R/source.R:88-111)."""
+        wl = int(windowLength_points)
+        h = wl - (overlap * wl / 100)
+        return (wl // 2) * host.seq_by_count(1.0, float(length) + wl, h)
+
+    # ---- finalise ----
+    def build(self):
+        def arr(T, items):
+            a = (T * max(1, len(items)))()
+            for i, it in enumerate(items):
+                a[i] = it
+            return a
+
+        def cat(parts, dtype):
+            return np.ascontiguousarray(np.concatenate(parts), dtype=dtype) if parts else np.zeros(0, dtype=dtype)
+        d = BatchDesc()
+        keep = dict(calls=arr(Call, self.calls), bouts=arr(Bout, self.bouts), syls=arr(Syllable, self.syls),
+                    noises=arr(Noise, self.noises), envs=arr(Envelope, self.envs),
+                    frefs=arr(FormantRef, self.frefs), pitch=cat(self.pitch, np.float64),
+                    anchors=cat(self.anchors, np.float64), formants=cat(self.formants, np.float64),
+                    z=cat(self.z, np.float64), u=cat(self.u, self.u_dtype), pre=cat(self.pre, np.float64))
+        d.n_calls, d.n_bouts, d.n_syllables = len(self.calls), len(self.bouts), len(self.syls)
+        d.n_noises, d.n_envelopes, d.n_formant_refs = len(self.noises), len(self.envs), len(self.frefs)
+        for k in ('calls', 'bouts', 'noises'):
+            setattr(d, k, C.cast(keep[k], C.c_void_p))
+        d.syllables = C.cast(keep['syls'], C.c_void_p)
+        d.envelopes = C.cast(keep['envs'], C.c_void_p)
+        d.formant_index = C.cast(keep['frefs'], C.c_void_p)
+        d.pitch, d.n_pitch = _ptr(keep['pitch']), self.n_pitch
+        d.anchors, d.n_anchors = _ptr(keep['anchors']), self.n_anchors
+        d.formants, d.n_formants = _ptr(keep['formants']), self.n_formants
+        d.z, d.n_z = _ptr(keep['z']), self.n_z
+        d.u, d.n_u = _ptr(keep['u']), self.n_u
+        d.u_is_float = 1 if self.u_dtype == np.float32 else 0
+        d.pre, d.n_pre = _ptr(keep['pre']), self.n_pre
+        d._keep = keep
+        return d
+
+    def h2d_bytes(self):
+        return (8 * (self.n_pitch + 2 * self.n_anchors + 4 * self.n_formants + self.n_z + self.n_pre) +
+                self.u_dtype.itemsize * self.n_u + C.sizeof(Syllable) * len(self.syls) +
+                C.sizeof(Bout) * len(self.bouts) + C.sizeof(Noise) * len(self.noises) +
+                C.sizeof(Envelope) * len(self.envs) + C.sizeof(FormantRef) * len(self.frefs))
+
+
+class Batch:
+    """Owner of one sgb_batch handle."""
+
+    def __init__(self):
+        self.L = _abi.load()
+        self.h = C.c_void_p()
+        _check(self.L.sgb_batch_create(C.byref(self.h)))
+        self.desc = None
+        self.info = None
+
+    def close(self):
+        if self.h:
+            self.L.sgb_batch_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload(self, desc):
+        self.desc = desc
+        _check(self.L.sgb_batch_upload(self.h, C.byref(desc)))
+
+    def run(self):
+        info = RunInfo()
+        _check(self.L.sgb_batch_run(self.h, C.byref(info)))
+        self.info = info
+        return info
+
+    def lengths(self):
+        n = self.desc.n_calls
+        out = np.zeros(n, dtype=np.int64)
+        _check(self.L.sgb_batch_lengths(self.h, _ptr(out)))
+        return out
+
+    def status(self):
+        out = np.zeros(self.desc.n_calls, dtype=np.int32)
+        _check(self.L.sgb_batch_status(self.h, _ptr(out)))
+        return out
+
+    def fetch(self, dtype=np.float64, out=None):
+        lens = self.lengths()
+        total = int(lens.sum())
+        if out is None:
+            out = np.zeros(max(total, 1), dtype=dtype)
+        if np.dtype(dtype) == np.float32:
+            _check(self.L.sgb_batch_fetch_f32(self.h, _ptr(out), out.size))
+        else:
+            _check(self.L.sgb_batch_fetch_f64(self.h, _ptr(out), out.size))
+        offs = np.concatenate(([0], np.cumsum(lens)))
+        return [out[offs[i]:offs[i + 1]] for i in range(lens.size)]
+
+    def syllable(self, s):
+        n = C.c_int64()
+        _check(self.L.sgb_batch_syllable_len(self.h, s, C.byref(n)))
+        out = np.zeros(max(n.value, 1))
+        _check(self.L.sgb_batch_syllable_fetch(self.h, s, _ptr(out), out.size))
+        return out[:n.value]
+
+    def noise(self, n, length):
+        out = np.zeros(max(int(length), 1))
+        _check(self.L.sgb_batch_noise_fetch(self.h, n, _ptr(out), out.size))
+        return out[:int(length)]
+
+    def artefacts(self, s):
+        a = SylArtefacts()
+        _check(self.L.sgb_batch_artefacts(self.h, s, C.byref(a)))
+        res = dict(nGC=a.nGC, nHarmonics=a.nHarmonics, rows_kept=a.rows_kept, nEpochs=a.nEpochs,
+                   n_upsampled=a.n_upsampled, z_used=a.z_used, status=a.status, raw_max=a.raw_max)
+        cap = max(a.nGC + 2, 2 * a.nEpochs + 2, a.n_jitter_idx + 2)
+        names = ['gc', 'gc_upsampled', 'nSubharm', 'rw_bin', 'jitter_idx', 'epochs', 'zc']
+        for w, nm in enumerate(names):
+            buf = np.zeros(cap, dtype=np.int32)
+            n = _check(self.L.sgb_batch_artefact_ints(self.h, s, w, _ptr(buf), cap))
+            res[nm] = buf[:n].copy()
+        res['epochs'] = res['epochs'].reshape(-1, 2)
+        res['zc'] = res['zc'].reshape(-1, 2)
+        p = np.zeros(max(a.nGC, 1))
+        _check(self.L.sgb_batch_pitch_per_gc(self.h, s, _ptr(p), p.size))
+        res['pitch_per_gc'] = p[:a.nGC]
+        return res
+
+
+# ------------------------------------------------------------------------------
+# R-named entry points
+# ------------------------------------------------------------------------------
+def soundgen(*args, z=None, u=None, contour_method='loess', pitchContours=None, return_batch=False,
+             **kwargs):
+    """soundgen() (R/soundgen.R:208-277): returns the synthesised waveform (float64).
+    Raises SoundgenError('Failed to generate the new syllable!') where the reference stops."""
+    names = ['repeatBout', 'nSyl', 'sylLen', 'pauseLen', 'pitchAnchors', 'pitchAnchorsGlobal', 'temperature']
+    kwargs.update(dict(zip(names, args)))
+    bb = BatchBuilder()
+    bb.add_soundgen(z=z, u=u, contour_method=contour_method, pitchContours=pitchContours, **kwargs)
+    bt = Batch()
+    bt.upload(bb.build())
+    bt.run()
+    st = bt.status()
+    if st[0] == _abi.SGB_ERR_SYNTH:
+        raise SoundgenError(st[0], 'Failed to generate the new syllable!')
+    if st[0] != 0:
+        raise SoundgenError(int(st[0]), 'soundgen failed')
+    y = bt.fetch(np.float64)[0].copy()
+    if return_batch:
+        return y, bt
+    bt.close()
+    return y
+
+
+def soundgen_batch(list_of_kwargs, out_dtype=np.float32, u_dtype=np.float64):
+    """Many soundgen() calls in one pass (the batched entry the reference lacks)."""
+    bb = BatchBuilder(u_dtype=u_dtype)
+    for kw in list_of_kwargs:
+        bb.add_soundgen(**kw)
+    bt = Batch()
+    bt.upload(bb.build())
+    bt.run()
+    out = [a.copy() for a in bt.fetch(out_dtype)]
+    st = bt.status()
+    bt.close()
+    return out, st
+
+
+def generateHarmonics(pitch, attackLen=50, nonlinBalance=0, nonlinDep=0, jitterDep=0, jitterLen=1,
+                      vibratoFreq=100, vibratoDep=0, shimmerDep=0, creakyBreathy=0, rolloff=-18,
+                      rolloffOct=-2, rolloffKHz=-6, rolloffParab=0, rolloffParabHarm=3, rolloffLip=6,
+                      rolloff_perAmpl=12, temperature=0, pitchDriftDep=.5, pitchDriftFreq=.125,
+                      randomWalk_trendStrength=.5, shortestEpoch=300, subFreq=100, subDep=0, amDep=0,
+                      amFreq=30, amplAnchors=None, overlap=75, samplingRate=16000, pitchFloor=75,
+                      pitchCeiling=3500, pitchSamplingRate=3500, throwaway=-120, z=None,
+                      contour_method='loess', want_artefacts=False):
+    """generateHarmonics() (R/source.R:173-205).  `z`: the syllable's normal stream."""
+    pars = dict(locals())
+    for k in ('pitch', 'z', 'amplAnchors', 'contour_method', 'want_artefacts', 'nonlinDep', 'creakyBreathy',
+              'rolloffLip', 'amDep', 'amFreq', 'overlap'):
+        pars.pop(k)
+    bb = BatchBuilder()
+    bb.add_syllable(pitch, z=z, amplAnchors=amplAnchors, contour_method=contour_method, **pars)
+    env = bb.add_envelope(None, samplingRate=samplingRate)
+    wl = int(math.floor(50 / 1000 * samplingRate / 2) * 2)
+    bb.add_bout(0, 1, 0, 0, env, False, wl, samplingRate=samplingRate, throwaway=throwaway)
+    bb.add_call(0, 1)
+    bt = Batch()
+    bt.upload(bb.build())
+    bt.run()
+    art = bt.artefacts(0)
+    if art['status'] == _abi.SGB_ERR_SYNTH:
+        raise SoundgenError(art['status'], 'Failed to generate the new syllable!')
+    if art['status'] != 0:
+        raise SoundgenError(art['status'], 'generateHarmonics failed')
+    y = bt.syllable(0).copy()
+    bt.close()
+    return (y, art) if want_artefacts else y
+
+
+def generateNoise(len, noiseAnchors=((0, 300), (-120, -120)), rolloffNoise=-6, attackLen=10,
+                  windowLength_points=1024, samplingRate=16000, overlap=75, throwaway=-120, filterNoise=None,
+                  u=None, strength=None):
+    """generateNoise() (R/source.R:57-68).  `u`: the runif(nr * nc) draws; filterNoise:
+    None or an (nr x k) matrix (as returned by getSpectralEnvelope)."""
+    if filterNoise is not None:
+        raise NotImplementedError('pass the formant specification through soundgen(formantsNoise=...); '
+                                  'a literal filter matrix is not routed through the batch ABI yet')
+    bb = BatchBuilder()
+    bb.add_silent_syllable(8)
+    bb.add_noise(len, noiseAnchors, u, rolloffNoise=rolloffNoise, attackLen=attackLen,
+                 windowLength_points=windowLength_points, samplingRate=samplingRate, overlap=overlap,
+                 insertion=1, mix=0, strength=strength)
+    env = bb.add_envelope(None, samplingRate=samplingRate)
+    bb.add_bout(0, 1, 0, 1, env, False, max(4, int(windowLength_points)), samplingRate=samplingRate,
+                throwaway=throwaway)
+    bb.add_call(0, 1)
+    bt = Batch()
+    bt.upload(bb.build())
+    bt.run()
+    y = bt.noise(0, len).copy()
+    bt.close()
+    return y
+
+
+def getRolloff(pitch_per_gc=(440,), nHarmonics=100, rolloff=-12, rolloffOct=-2, rolloffParab=0,
+               rolloffParabHarm=2, rolloffParabCeiling=None, rolloffKHz=-6, baseline=200, throwaway=-120,
+               samplingRate=16000, plot=False):
+    """getRolloff() (R/sourceSpectrum.R:71-82): matrix rows x nGC, rownames 1..rows."""
+    L = _abi.load()
+    p = np.ascontiguousarray(np.atleast_1d(pitch_per_gc), dtype=np.float64)
+    v = lambda a: np.ascontiguousarray(np.atleast_1d(a), dtype=np.float64)
+    ro, roct, rk = v(rolloff), v(rolloffOct), v(rolloffKHz)
+    out = np.zeros(int(nHarmonics) * p.size)
+    rows = C.c_int32()
+    _check(L.sgb_get_rolloff(_ptr(p), p.size, int(nHarmonics), _ptr(ro), ro.size, _ptr(roct), roct.size,
+                             _ptr(rk), rk.size, float(rolloffParab), float(rolloffParabHarm),
+                             -1.0 if rolloffParabCeiling is None else float(rolloffParabCeiling),
+                             float(baseline), float(throwaway), float(samplingRate), _ptr(out), C.byref(rows)))
+    m = out.reshape(p.size, int(nHarmonics)).T
+    return m[:rows.value, :].copy()
+
+
+def getSpectralEnvelope(nr, nc, formants=None, formantDep=1, rolloffLip=6, mouthAnchors=None,
+                        mouthOpenThres=0, openMouthBoost=0, vocalTract=None, temperature=0, formDrift=.3,
+                        formDisp=.2, formantDepStoch=30, smoothLinearFactor=1, samplingRate=16000,
+                        speedSound=35400, plot=False, formants_upsampled=None):
+    """getSpectralEnvelope() (R/sourceSpectrum.R:261-283), deterministic part; with
+    temperature > 0 pass the host-drawn tracks as `formants_upsampled`."""
+    if temperature > 0 and formants_upsampled is None:
+        raise NotImplementedError('stochastic formants are drawn on the host from R\'s RNG')
+    L = _abi.load()
+    bb = BatchBuilder()
+    eid = bb.add_envelope(formants, formantDep=formantDep, rolloffLip=rolloffLip, mouthAnchors=mouthAnchors,
+                          mouthOpenThres=mouthOpenThres, openMouthBoost=openMouthBoost, vocalTract=vocalTract,
+                          samplingRate=samplingRate, speedSound=speedSound,
+                          smoothLinearFactor=smoothLinearFactor, tracks=formants_upsampled)
+    e = bb.envs[eid]
+    fm = np.ascontiguousarray(np.concatenate(bb.formants)) if bb.formants else np.zeros(4)
+    fn = np.array([r.n for r in bb.frefs], dtype=np.int32) if bb.frefs else np.zeros(1, dtype=np.int32)
+    an = np.ascontiguousarray(np.concatenate(bb.anchors)) if bb.anchors else np.zeros(2)
+    out = np.zeros(int(nr) * int(nc))
+    _check(L.sgb_get_spectral_envelope(int(nr), int(nc), C.byref(e), _ptr(fm), _ptr(fn), _ptr(an), _ptr(out)))
+    return out.reshape(int(nc), int(nr)).T.copy()
+
+
+def filter_sound(sound, spectralEnvelope, windowLength_points, overlap=75):
+    """The STFT -> envelope -> ISTFT -> /max block of soundgen() (R/soundgen.R:743-807)."""
+    L = _abi.load()
+    s = np.ascontiguousarray(sound, dtype=np.float64)
+    env = np.asarray(spectralEnvelope, dtype=np.float64)
+    if env.ndim == 1:
+        env = env[:, None]
+    e = np.ascontiguousarray(env.T).ravel()   # column-major
+    n = L.sgb_filter_len(s.size, int(windowLength_points), float(overlap))
+    if n < 0:
+        raise SoundgenError(-1, 'sound too short')
+    out = np.zeros(n)
+    _check(L.sgb_filter(_ptr(s), s.size, _ptr(e), env.shape[1], int(windowLength_points), float(overlap),
+                        _ptr(out), out.size))
+    return out

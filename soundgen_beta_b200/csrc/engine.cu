@@ -1,0 +1,1044 @@
+// Host engine + C ABI of libsoundgen_b200.so (include/soundgen_b200.h).
+//
+// The engine owns device memory (grow-only pools), one CUDA stream and the host-side
+// layout logic that R's soundgen() performs implicitly with c() / addVectors()
+// (R/soundgen.R:632-640, 708-714, 743-748, 813-818, 836-849).  All arithmetic on
+// samples happens in the kernels; the host only sizes and places buffers.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "engine.cuh"
+
+// ---- kernel launchers defined in the other translation units ----
+void launch_control(const sgb_syllable *, int, const double *, const double *, const double *, const Pools &,
+                    SylCtrl *, SylLayout *, int64_t *, cudaStream_t);
+void launch_tiles_amp(const sgb_syllable *, int, const SylCtrl *, const SylLayout *, const Pools &, SynthTile *,
+                      int64_t *, double *, cudaStream_t);
+void launch_rolloff_api(const double *, int, int, const double *, int, const double *, int, const double *, int,
+                        double, double, double, double, double, double, double *, int *, double *, int *);
+#define ENV_MAXK_HOST 64
+void launch_synth(const SynthTile *, int, const sgb_syllable *, const SylCtrl *, const SylLayout *, const Pools &,
+                  const double *, float *, cudaStream_t);
+void launch_compose(const sgb_syllable *, int, SylCtrl *, const SylLayout *, const Pools &, const double *,
+                    const float *, float *, const double *, const double *, cudaStream_t);
+void launch_place_voiced(const sgb_syllable *, int, const SylCtrl *, const SylLayout *, const SylPlace *,
+                         const Pools &, const float *, float *, int, cudaStream_t);
+void launch_envelope_f32(const EnvInst *, int, int, const sgb_envelope *, const sgb_formant_ref *, const double *,
+                         const double *, float *, cudaStream_t);
+void launch_envelope_f64(const EnvInst *, int, int, const sgb_envelope *, const sgb_formant_ref *, const double *,
+                         const double *, double *, cudaStream_t);
+size_t stft_smem_bytes(int n, double h_in, double h_out, int mode);
+cudaError_t launch_stft(int mode, int u_is_float, const FftSeg *, int, const FftJob *, const FftPlan *,
+                        const float2 *, const float *, const float *, const void *, const float *, float *, int *,
+                        size_t, cudaStream_t);
+void launch_noise_final(const sgb_noise *, int, const NoiseLayout *, const double *, const double *, const int *, int,
+                        const float *, float *, int, cudaStream_t);
+void launch_sound_mix(const sgb_bout *, int, const BoutLayout *, const sgb_noise *, const NoiseLayout *,
+                      const double *, const float *, float *, int, cudaStream_t);
+void launch_finalize(int, const sgb_bout *, int, const BoutLayout *, const sgb_noise *, const NoiseLayout *,
+                     const float *, const float *, const float *, const int *, void *, int, cudaStream_t);
+
+// ------------------------------------------------------------------ errors ---
+static thread_local std::string g_err;
+static int fail(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CK(call)                                                                               \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess)                                                                     \
+      return fail(SGB_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); \
+  } while (0)
+
+struct SylSummary { int32_t status, out_len, n_up, nGC; };
+__global__ void k_summary(const SylCtrl *ctrl, int S, SylSummary *out) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  out[s].status = ctrl[s].status; out[s].out_len = ctrl[s].out_len; out[s].n_up = ctrl[s].n_up; out[s].nGC = ctrl[s].nGC;
+}
+__global__ void k_fill_int(int *p, int n, int v) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+__global__ void k_f32_to_f64(const float *a, double *b, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) b[i] = (double)a[i];
+}
+__global__ void k_f64_to_f32(const double *a, float *b, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) b[i] = (float)a[i];
+}
+
+// ---------------------------------------------------------------- buffers ---
+struct DBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+static int64_t align4(int64_t x) { return (x + 3) & ~(int64_t)3; }
+
+// seq(from, to, by) length: floor((to-from)/by + 1e-10) + 1
+static int seq_by_count(double from, double to, double by) {
+  if (from == to) return 1;
+  return (int)std::floor((to - from) / by + 1e-10) + 1;
+}
+
+struct sgb_batch {
+  int device = 0;
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev[SGB_T_COUNT + 2];
+  bool have_desc = false, have_run = false;
+  // host copies of the small tables
+  std::vector<sgb_call> calls;
+  std::vector<sgb_bout> bouts;
+  std::vector<sgb_syllable> syls;
+  std::vector<sgb_noise> noises;
+  std::vector<sgb_envelope> envs;
+  std::vector<sgb_formant_ref> frefs;
+  int64_t n_pitch = 0, n_anchors = 0, n_formants = 0, n_z = 0, n_u = 0, n_pre = 0;
+  int u_is_float = 0;
+  // device copies
+  DBuf d_bouts, d_syls, d_noises, d_envs, d_frefs, d_pitch, d_anchors, d_formants, d_z, d_u, d_pre;
+  DBuf d_gc_off, d_h_off, d_ctrl, d_lay, d_totals, d_summary, d_tiles;
+  DBuf p_pitch_w, p_i32[6], p_f64[19];
+  DBuf d_amp, d_wave, d_raw, d_sound, d_voiced, d_filt, d_noise_raw, d_noise_fin, d_env, d_out, d_out64;
+  DBuf d_bl, d_place, d_nl, d_envinst, d_plans, d_tw, d_win, d_fjobs, d_njobs, d_fsegs, d_nsegs, d_max;
+  Pools pools;
+  int64_t gc_total = 0, h_total = 0;
+  // results
+  std::vector<SylSummary> summary;
+  std::vector<BoutLayout> bl;
+  std::vector<SylPlace> place;
+  std::vector<NoiseLayout> nl;
+  std::vector<SylLayout> lay_host;
+  std::vector<int64_t> call_len, call_off;
+  std::vector<int32_t> call_status;
+  int64_t total_out = 0;
+  bool keep_voiced = false;
+  sgb_run_info info;
+};
+
+extern "C" {
+
+int sgb_version(void) { return SGB_VERSION; }
+const char *sgb_last_error(void) { return g_err.c_str(); }
+
+int sgb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+int sgb_set_device(int device) {
+  CK(cudaSetDevice(device));
+  return SGB_OK;
+}
+
+int sgb_batch_create(sgb_batch **out) {
+  if (!out) return fail(SGB_ERR_INVALID, "null out pointer");
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n < 1)
+    return fail(SGB_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  sgb_batch *b = new sgb_batch();
+  CK(cudaGetDevice(&b->device));
+  CK(cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking));
+  for (auto &e : b->ev) CK(cudaEventCreate(&e));
+  memset(&b->info, 0, sizeof b->info);
+  *out = b;
+  return SGB_OK;
+}
+
+void sgb_batch_destroy(sgb_batch *b) {
+  if (!b) return;
+  cudaSetDevice(b->device);
+  cudaStreamSynchronize(b->st);
+  DBuf *all[] = {&b->d_bouts, &b->d_syls, &b->d_noises, &b->d_envs, &b->d_frefs, &b->d_pitch, &b->d_anchors,
+                 &b->d_formants, &b->d_z, &b->d_u, &b->d_pre, &b->d_gc_off, &b->d_h_off, &b->d_ctrl, &b->d_lay,
+                 &b->d_totals, &b->d_summary, &b->d_tiles, &b->p_pitch_w, &b->d_amp, &b->d_wave, &b->d_raw,
+                 &b->d_sound, &b->d_voiced, &b->d_filt, &b->d_noise_raw, &b->d_noise_fin, &b->d_env, &b->d_out,
+                 &b->d_out64, &b->d_bl, &b->d_place, &b->d_nl, &b->d_envinst, &b->d_plans, &b->d_tw, &b->d_win,
+                 &b->d_fjobs, &b->d_njobs, &b->d_fsegs, &b->d_nsegs, &b->d_max};
+  for (auto d : all) d->release();
+  for (auto &d : b->p_i32) d.release();
+  for (auto &d : b->p_f64) d.release();
+  for (auto &e : b->ev) cudaEventDestroy(e);
+  cudaStreamDestroy(b->st);
+  delete b;
+}
+
+static int upload_array(sgb_batch *b, DBuf &d, const void *src, size_t bytes) {
+  CK(d.ensure(bytes ? bytes : 16));
+  if (bytes) CK(cudaMemcpyAsync(d.p, src, bytes, cudaMemcpyHostToDevice, b->st));
+  return SGB_OK;
+}
+
+int sgb_batch_upload(sgb_batch *b, const sgb_batch_desc *D) {
+  if (!b || !D) return fail(SGB_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(b->device));
+  if (D->n_calls < 1 || D->n_bouts < 1 || D->n_syllables < 1)
+    return fail(SGB_ERR_INVALID, "empty batch");
+  // ---- validate ----
+  for (int c = 0; c < D->n_calls; c++) {
+    const sgb_call &C = D->calls[c];
+    if (C.bout_begin < 0 || C.bout_end > D->n_bouts || C.bout_begin >= C.bout_end)
+      return fail(SGB_ERR_INVALID, "call %d: bad bout range", c);
+  }
+  for (int i = 0; i < D->n_bouts; i++) {
+    const sgb_bout &B = D->bouts[i];
+    if (B.syl_begin < 0 || B.syl_end > D->n_syllables || B.syl_begin >= B.syl_end)
+      return fail(SGB_ERR_INVALID, "bout %d: bad syllable range", i);
+    if (B.noise_begin < 0 || B.noise_end > D->n_noises || B.noise_begin > B.noise_end)
+      return fail(SGB_ERR_INVALID, "bout %d: bad noise range", i);
+    if (B.env_id < 0 || B.env_id >= D->n_envelopes) return fail(SGB_ERR_INVALID, "bout %d: bad env_id", i);
+    if (B.wl < 4) return fail(SGB_ERR_INVALID, "bout %d: windowLength_points %d < 4", i, B.wl);
+    if (!(B.overlap >= 0.0 && B.overlap < 100.0)) return fail(SGB_ERR_INVALID, "bout %d: overlap out of range", i);
+    if (!(B.samplingRate > 0)) return fail(SGB_ERR_INVALID, "bout %d: samplingRate", i);
+    if (B.aglobal_n > ENV_MAXK_HOST) return fail(SGB_ERR_UNSUPPORTED, "bout %d: too many amplAnchorsGlobal", i);
+  }
+  for (int s = 0; s < D->n_syllables; s++) {
+    const sgb_syllable &Y = D->syllables[s];
+    if (Y.kind < 0 || Y.kind > 2) return fail(SGB_ERR_INVALID, "syllable %d: bad kind", s);
+    if (Y.kind == 0) { if (Y.silent_len < 0) return fail(SGB_ERR_INVALID, "syllable %d: silent_len", s); continue; }
+    if (Y.pitch_len < 1 || Y.pitch_off < 0 || Y.pitch_off + Y.pitch_len > D->n_pitch)
+      return fail(SGB_ERR_INVALID, "syllable %d: pitch range outside the pool", s);
+    if (Y.kind == 2) continue;
+    if (Y.pitch_len < 3) return fail(SGB_ERR_INVALID, "syllable %d: pitch contour shorter than 3 points", s);
+    if (!(Y.samplingRate > 0) || !(Y.pitchSamplingRate > 0) || !(Y.pitchFloor > 0) || !(Y.pitchCeiling >= Y.pitchFloor))
+      return fail(SGB_ERR_INVALID, "syllable %d: sampling rates / pitch bounds", s);
+    if (Y.pitchCeiling > Y.samplingRate / 4.0)
+      return fail(SGB_ERR_UNSUPPORTED, "syllable %d: pitchCeiling above samplingRate/4 (glottal cycles < 4 samples)", s);
+    if (Y.z_cap < 0 || Y.z_off < 0 || Y.z_off + Y.z_cap > D->n_z) return fail(SGB_ERR_INVALID, "syllable %d: z range", s);
+    if (Y.ampl_n < 0 || Y.ampl_n > SGB_MAX_RW_KNOTS || (Y.ampl_n > 0 && (Y.ampl_off < 0 || Y.ampl_off + Y.ampl_n > D->n_anchors)))
+      return fail(SGB_ERR_INVALID, "syllable %d: amplAnchors range", s);
+    if (!(Y.throwaway < 0)) return fail(SGB_ERR_INVALID, "syllable %d: throwaway must be negative", s);
+  }
+  for (int n = 0; n < D->n_noises; n++) {
+    const sgb_noise &N = D->noises[n];
+    if (N.len < 1) return fail(SGB_ERR_INVALID, "noise %d: len < 1", n);
+    if (N.wl < 4 || (N.wl & 1)) return fail(SGB_ERR_UNSUPPORTED, "noise %d: odd or tiny window", n);
+    if (N.env_id >= D->n_envelopes) return fail(SGB_ERR_INVALID, "noise %d: env_id", n);
+    if (N.strength_pre_off < 0 && (N.anchor_n < 1 || N.anchor_n > ENV_MAXK_HOST || N.anchor_off < 0 || N.anchor_off + N.anchor_n > D->n_anchors))
+      return fail(SGB_ERR_INVALID, "noise %d: anchors", n);
+    if (N.strength_pre_off >= 0 && N.strength_pre_off + N.len > D->n_pre) return fail(SGB_ERR_INVALID, "noise %d: pre-evaluated contour range", n);
+    double h = N.wl - (N.overlap * N.wl / 100.0);
+    if (!(h >= 1.0)) return fail(SGB_ERR_INVALID, "noise %d: hop < 1", n);
+    int nc = seq_by_count(1.0, (double)N.len + N.wl, h);
+    if (N.u_off < 0 || N.u_off + (int64_t)nc * (N.wl / 2) > D->n_u)
+      return fail(SGB_ERR_STREAM, "noise %d: needs %lld uniforms", n, (long long)nc * (N.wl / 2));
+  }
+  for (int e = 0; e < D->n_envelopes; e++) {
+    const sgb_envelope &E = D->envelopes[e];
+    if (E.n_formants < 0 || E.n_formants > 30) return fail(SGB_ERR_UNSUPPORTED, "envelope %d: more than 30 formants", e);
+    if (E.n_formants > 0 && (E.formant_off < 0 || E.formant_off + E.n_formants > D->n_formant_refs))
+      return fail(SGB_ERR_INVALID, "envelope %d: formant refs", e);
+    if (E.mouth_n < 0 || E.mouth_n > ENV_MAXK_HOST) return fail(SGB_ERR_UNSUPPORTED, "envelope %d: mouth anchors", e);
+  }
+  for (int f = 0; f < D->n_formant_refs; f++) {
+    const sgb_formant_ref &R = D->formant_index[f];
+    if (R.n < 1 || R.off < 0 || R.off + R.n > D->n_formants) return fail(SGB_ERR_INVALID, "formant ref %d", f);
+  }
+
+  b->calls.assign(D->calls, D->calls + D->n_calls);
+  b->bouts.assign(D->bouts, D->bouts + D->n_bouts);
+  b->syls.assign(D->syllables, D->syllables + D->n_syllables);
+  b->noises.assign(D->noises, D->noises + D->n_noises);
+  b->envs.assign(D->envelopes, D->envelopes + D->n_envelopes);
+  b->frefs.assign(D->formant_index, D->formant_index + D->n_formant_refs);
+  b->n_pitch = D->n_pitch; b->n_anchors = D->n_anchors; b->n_formants = D->n_formants;
+  b->n_z = D->n_z; b->n_u = D->n_u; b->n_pre = D->n_pre; b->u_is_float = D->u_is_float;
+  const int S = D->n_syllables;
+
+  CK(cudaEventRecord(b->ev[SGB_T_COUNT], b->st));
+  int rc;
+  if ((rc = upload_array(b, b->d_bouts, D->bouts, sizeof(sgb_bout) * D->n_bouts))) return rc;
+  if ((rc = upload_array(b, b->d_syls, D->syllables, sizeof(sgb_syllable) * S))) return rc;
+  if ((rc = upload_array(b, b->d_noises, D->noises, sizeof(sgb_noise) * D->n_noises))) return rc;
+  if ((rc = upload_array(b, b->d_envs, D->envelopes, sizeof(sgb_envelope) * D->n_envelopes))) return rc;
+  if ((rc = upload_array(b, b->d_frefs, D->formant_index, sizeof(sgb_formant_ref) * D->n_formant_refs))) return rc;
+  if ((rc = upload_array(b, b->d_pitch, D->pitch, 8 * (size_t)D->n_pitch))) return rc;
+  if ((rc = upload_array(b, b->d_anchors, D->anchors, 16 * (size_t)D->n_anchors))) return rc;
+  if ((rc = upload_array(b, b->d_formants, D->formants, 32 * (size_t)D->n_formants))) return rc;
+  if ((rc = upload_array(b, b->d_z, D->z, 8 * (size_t)D->n_z))) return rc;
+  if ((rc = upload_array(b, b->d_u, D->u, (D->u_is_float ? 4 : 8) * (size_t)D->n_u))) return rc;
+  if ((rc = upload_array(b, b->d_pre, D->pre, 8 * (size_t)D->n_pre))) return rc;
+
+  // per-syllable scratch capacities (host-known bounds)
+  std::vector<int64_t> gc_off(S + 1), h_off(S + 1);
+  int64_t g = 0, h = 0;
+  for (int s = 0; s < S; s++) {
+    gc_off[s] = g; h_off[s] = h;
+    const sgb_syllable &Y = b->syls[s];
+    if (Y.kind == 1) {
+      g += Y.pitch_len / 2 + 3;
+      h += (int64_t)std::ceil((Y.samplingRate / 2.0 - Y.pitchFloor) / Y.pitchFloor) + 2;
+    } else {
+      g += 1; h += 1;
+    }
+  }
+  gc_off[S] = g; h_off[S] = h;
+  b->gc_total = g; b->h_total = h;
+  if ((rc = upload_array(b, b->d_gc_off, gc_off.data(), 8 * (size_t)(S + 1)))) return rc;
+  if ((rc = upload_array(b, b->d_h_off, h_off.data(), 8 * (size_t)(S + 1)))) return rc;
+  CK(cudaEventRecord(b->ev[SGB_T_COUNT + 1], b->st));
+  CK(cudaStreamSynchronize(b->st));   // gc_off / h_off are stack vectors
+  CK(cudaEventElapsedTime(&b->info.ms[SGB_T_H2D], b->ev[SGB_T_COUNT], b->ev[SGB_T_COUNT + 1]));
+
+  CK(b->p_pitch_w.ensure(8 * (size_t)std::max<int64_t>(1, D->n_pitch)));
+  for (int i = 0; i < 5; i++) CK(b->p_i32[i].ensure(4 * (size_t)g));
+  CK(b->p_i32[5].ensure(4 * (size_t)h));
+  for (auto &d : b->p_f64) CK(d.ensure(8 * (size_t)g));
+  Pools &P = b->pools;
+  P.pitch_w = b->p_pitch_w.as<double>();
+  P.gc = b->p_i32[0].as<int32_t>(); P.nsub = b->p_i32[1].as<int32_t>(); P.rwbin = b->p_i32[2].as<int32_t>();
+  P.jidx = b->p_i32[3].as<int32_t>(); P.gcup = b->p_i32[4].as<int32_t>(); P.rowmap = b->p_i32[5].as<int32_t>();
+  double **dp[] = {&P.ppg, &P.rw, &P.ro, &P.roct, &P.rk, &P.shimmer, &P.drift, &P.subdep, &P.colmax, &P.kt,
+                   &P.sb, &P.sc, &P.sd, &P.phi, &P.t1, &P.t2, &P.t3, &P.t4};
+  for (int i = 0; i < 18; i++) *dp[i] = b->p_f64[i].as<double>();
+  P.gc_off = b->d_gc_off.as<int64_t>();
+  P.h_off = b->d_h_off.as<int64_t>();
+  CK(b->d_ctrl.ensure(sizeof(SylCtrl) * (size_t)S));
+  CK(b->d_lay.ensure(sizeof(SylLayout) * (size_t)S));
+  CK(b->d_totals.ensure(64));
+  CK(b->d_summary.ensure(sizeof(SylSummary) * (size_t)S));
+  b->have_desc = true;
+  b->have_run = false;
+  b->keep_voiced = (D->n_calls <= 64);
+  return SGB_OK;
+}
+
+// radices for the Stockham passes: 4s first, then 2, then odd primes ascending
+static int plan_radices(int n, int *radix) {
+  int np = 0;
+  while (n % 4 == 0 && np < FFT_MAX_PASS) { radix[np++] = 4; n /= 4; }
+  while (n % 2 == 0 && np < FFT_MAX_PASS) { radix[np++] = 2; n /= 2; }
+  for (int p = 3; n > 1; p += 2) {
+    while (n % p == 0) {
+      if (np >= FFT_MAX_PASS) return -1;
+      radix[np++] = p; n /= p;
+    }
+  }
+  return np;
+}
+
+struct PlanKey {
+  int n; double overlap;
+  bool operator<(const PlanKey &o) const { return n < o.n || (n == o.n && overlap < o.overlap); }
+};
+
+// FFT plans + twiddle / window tables (seewave hamming.w / hanning.w, seewave.r:7431-7450)
+struct PlanTable {
+  std::vector<FftPlan> plans;
+  std::map<PlanKey, int> idx;
+  std::vector<float2> tw;
+  std::vector<float> win;
+  int get(int n, double overlap) {
+    PlanKey key{n, overlap};
+    auto it = idx.find(key);
+    if (it != idx.end()) return it->second;
+    FftPlan pl;
+    memset(&pl, 0, sizeof pl);
+    pl.n = n;
+    pl.npass = plan_radices(n, pl.radix);
+    if (pl.npass < 0) return -1;
+    pl.h_in = n - (overlap * n / 100.0);
+    pl.h_out = n * (100.0 - overlap) / 100.0;
+    const size_t t0 = tw.size(), w0 = win.size();
+    pl.tw_off = (int64_t)t0; pl.wa_off = (int64_t)w0; pl.ws_off = (int64_t)w0 + n;
+    tw.resize(t0 + n);
+    win.resize(w0 + 2 * (size_t)n);
+    const double two_pi = 2.0 * 3.141592653589793;
+    double W0 = 0.0;
+    std::vector<double> hann(n);
+    for (int i = 0; i < n; i++) {
+      double ang = two_pi * (double)i / (double)n;
+      tw[t0 + i] = make_float2((float)std::cos(ang), (float)-std::sin(ang));
+      double c = std::cos(two_pi * (double)i / (double)(n - 1));
+      hann[i] = 0.5 - 0.5 * c;
+      W0 += hann[i] * hann[i];
+      win[w0 + i] = (float)((0.54 - 0.46 * c) / (double)n);
+    }
+    for (int i = 0; i < n; i++) win[w0 + n + i] = (float)(hann[i] * pl.h_out / (W0 * (double)n));
+    plans.push_back(pl);
+    idx[key] = (int)plans.size() - 1;
+    return (int)plans.size() - 1;
+  }
+};
+
+// segments: one CTA per sound when there are plenty of sounds, else split runs of frames
+static void make_segs(const std::vector<FftJob> &jobs, std::vector<FftSeg> &segs) {
+  const int target = 2 * 148;
+  int per_job = 1;
+  if ((int)jobs.size() < target && !jobs.empty()) per_job = (target + (int)jobs.size() - 1) / (int)jobs.size();
+  for (int j = 0; j < (int)jobs.size(); j++) {
+    int nc = jobs[j].nc;
+    int nseg = std::max(1, std::min(per_job, nc / 8));
+    int fr = (nc + nseg - 1) / nseg;
+    fr += fr & 1;   // keep pairs aligned
+    for (int ka = 0; ka < nc; ka += fr) {
+      FftSeg sg; sg.job = j; sg.ka = ka; sg.kb = std::min(nc, ka + fr); sg.pad = 0;
+      segs.push_back(sg);
+    }
+  }
+}
+
+// matchLengths(x, len) geometry (R/utilities_math.R:413-444, padDir = 'central')
+static void match_lengths(int xlen, int len, int *pad, int *start0) {
+  *pad = 0;
+  int L = xlen;
+  if (xlen == len) { *start0 = 0; return; }
+  if (xlen < len) { *pad = len; L = xlen + 2 * len; }
+  double halflen = len / 2.0, center = (1 + L) / 2.0;
+  *start0 = (int)std::ceil(center - halflen) - 1;
+}
+
+int sgb_batch_run(sgb_batch *b, sgb_run_info *info_out) {
+  if (!b) return fail(SGB_ERR_INVALID, "null batch");
+  if (!b->have_desc) return fail(SGB_ERR_STATE, "sgb_batch_run before sgb_batch_upload");
+  CK(cudaSetDevice(b->device));
+  cudaStream_t st = b->st;
+  const int S = (int)b->syls.size(), NB = (int)b->bouts.size(), NN = (int)b->noises.size(), NC = (int)b->calls.size();
+  sgb_run_info &info = b->info;
+  float h2d = info.ms[SGB_T_H2D];
+  memset(&info, 0, sizeof info);
+  info.ms[SGB_T_H2D] = h2d;
+  int launches = 0;
+  const Pools &P = b->pools;
+  const sgb_syllable *d_syl = b->d_syls.as<sgb_syllable>();
+  SylCtrl *d_ctrl = b->d_ctrl.as<SylCtrl>();
+  SylLayout *d_lay = b->d_lay.as<SylLayout>();
+  int64_t *d_tot = b->d_totals.as<int64_t>();
+  cudaEvent_t *ev = b->ev;
+  // events: e[0] start, then one after each stage
+  CK(cudaEventRecord(ev[0], st));
+
+  // ---- K0 control + size scan ----
+  CK(cudaMemsetAsync(d_tot, 0, 64, st));
+  launch_control(d_syl, S, b->d_pitch.as<double>(), b->d_anchors.as<double>(), b->d_z.as<double>(), P, d_ctrl, d_lay,
+                 d_tot, st);
+  launches += 2;
+  int64_t tot[8];
+  CK(cudaMemcpyAsync(tot, d_tot, 64, cudaMemcpyDeviceToHost, st));
+  CK(cudaEventRecord(ev[1], st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  const int64_t amp_total = tot[0], wave_total = tot[1], n_tiles = tot[2], raw_total = tot[3];
+  if (n_tiles > 2000000000LL) return fail(SGB_ERR_UNSUPPORTED, "batch too large: %lld synthesis tiles", (long long)n_tiles);
+  CK(b->d_amp.ensure(8 * (size_t)std::max<int64_t>(amp_total, 1)));
+  CK(b->d_wave.ensure(4 * (size_t)std::max<int64_t>(wave_total, 4)));
+  CK(b->d_raw.ensure(4 * (size_t)std::max<int64_t>(raw_total, 4)));
+  CK(b->d_tiles.ensure(sizeof(SynthTile) * (size_t)std::max<int64_t>(n_tiles, 1)));
+
+  // ---- K3 amplitude matrices ----
+  launch_tiles_amp(d_syl, S, d_ctrl, d_lay, P, b->d_tiles.as<SynthTile>(), d_tot, b->d_amp.as<double>(), st);
+  launches += 2;
+  CK(cudaEventRecord(ev[2], st));
+  // ---- K1 synthesis ----
+  launch_synth(b->d_tiles.as<SynthTile>(), (int)n_tiles, d_syl, d_ctrl, d_lay, P, b->d_amp.as<double>(),
+               b->d_wave.as<float>(), st);
+  if (n_tiles > 0) launches++;
+  CK(cudaEventRecord(ev[3], st));
+  // ---- K6 compose ----
+  launch_compose(d_syl, S, d_ctrl, d_lay, P, b->d_amp.as<double>(), b->d_wave.as<float>(), b->d_raw.as<float>(),
+                 b->d_anchors.as<double>(), b->d_pitch.as<double>(), st);
+  k_summary<<<(S + 255) / 256, 256, 0, st>>>(d_ctrl, S, b->d_summary.as<SylSummary>());
+  launches += 2;
+  b->summary.resize(S);
+  b->lay_host.resize(S);
+  CK(cudaMemcpyAsync(b->summary.data(), b->d_summary.p, sizeof(SylSummary) * (size_t)S, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(b->lay_host.data(), d_lay, sizeof(SylLayout) * (size_t)S, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(tot, d_tot, 64, cudaMemcpyDeviceToHost, st));
+  CK(cudaEventRecord(ev[4], st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  info.synth_partials = tot[4];
+  info.synth_samples = tot[5];
+
+  // ---- host layout (soundgen.R:632-640, 708-714, 743-748, 813-818, 836-849) ----
+  b->bl.assign(NB, BoutLayout());
+  b->place.assign(S, SylPlace());
+  b->nl.assign(NN, NoiseLayout());
+  b->call_len.assign(NC, 0); b->call_off.assign(NC, 0); b->call_status.assign(NC, SGB_OK);
+  std::vector<EnvInst> envinst;
+  std::vector<FftJob> fjobs, njobs;
+  int64_t sound_total = 0, filt_total = 0, env_total = 0, out_total = 0, noise_total = 0;
+  int n_failed = 0;
+
+  PlanTable PT;
+  auto get_plan = [&](int n, double overlap) -> int { return PT.get(n, overlap); };
+
+  for (int c = 0; c < NC; c++) {
+    const sgb_call &CL = b->calls[c];
+    b->call_off[c] = out_total;
+    int64_t clen = 0;
+    int wl_running = -1;
+    for (int bi = CL.bout_begin; bi < CL.bout_end; bi++) {
+      const sgb_bout &B = b->bouts[bi];
+      BoutLayout &L = b->bl[bi];
+      memset(&L, 0, sizeof L);
+      // voiced = c(voiced, syllable, pause)
+      std::vector<int64_t> syl_pos(B.syl_end - B.syl_begin);
+      int64_t vlen = 0;
+      bool any_voiced = false;
+      for (int s = B.syl_begin; s < B.syl_end; s++) {
+        const SylSummary &Y = b->summary[s];
+        int len = Y.out_len;
+        if (Y.status != SGB_OK) { b->call_status[c] = Y.status; len = 0; }
+        else if (b->syls[s].kind != 0 && len > 0) any_voiced = true;
+        syl_pos[s - B.syl_begin] = vlen;
+        b->place[s].len = len;
+        b->place[s].bout = bi;
+        vlen += len + b->syls[s].pause_after;
+      }
+      // pre-filter noise: sound = addVectors(sound, unvoiced[[s]], syllableStartIdx[s])
+      int64_t cur = vlen, shift = 0;
+      std::vector<int64_t> npos(std::max(0, B.noise_end - B.noise_begin), 0);
+      bool any_pre = false;
+      for (int n = B.noise_begin; n < B.noise_end; n++) {
+        const sgb_noise &N = b->noises[n];
+        if (N.mix != 0) continue;
+        any_pre = true;
+        int ip = N.insertion;
+        if (ip > 1) { npos[n - B.noise_begin] = ip; cur = std::max<int64_t>(cur, (int64_t)ip + N.len); }
+        else if (ip < 1) {
+          int64_t pad = 1 - ip;
+          shift += pad;
+          for (int m = B.noise_begin; m < n; m++) if (b->noises[m].mix == 0) npos[m - B.noise_begin] += pad;
+          npos[n - B.noise_begin] = 0;
+          cur = std::max<int64_t>(cur + pad, N.len);
+        } else { npos[n - B.noise_begin] = 0; cur = std::max<int64_t>(cur, N.len); }
+      }
+      L.sound_len = (int32_t)cur;
+      L.voiced_shift = (int32_t)shift;
+      L.sound_off = sound_total;
+      for (int s = B.syl_begin; s < B.syl_end; s++) b->place[s].dst_off = L.sound_off + shift + syl_pos[s - B.syl_begin];
+      for (int n = B.noise_begin; n < B.noise_end; n++)
+        if (b->noises[n].mix == 0) b->nl[n].dst_off = L.sound_off + npos[n - B.noise_begin];
+      // filter geometry
+      L.bypass = (!any_voiced && !any_pre) ? 1 : 0;   // sum(sound) == 0 (soundgen.R:736)
+      if (wl_running < 0) wl_running = B.wl;
+      if (!L.bypass) {
+        int wl = std::min(wl_running, (int)(cur / 2));     // soundgen.R:743 (persists across bouts)
+        wl_running = wl;
+        if (wl < 4 || (wl & 1)) {
+          b->call_status[c] = SGB_ERR_UNSUPPORTED;
+          L.bypass = 1;
+        } else {
+          L.wl = wl;
+          double h_in = wl - (B.overlap * wl / 100.0), h_out = wl * (100.0 - B.overlap) / 100.0;
+          L.nc = seq_by_count(1.0, std::max<double>(1.0, (double)(cur - wl)), h_in);
+          L.nint = B.moving ? L.nc : 1;
+          L.filt_len = (int32_t)std::floor(wl + (L.nc - 1) * h_out);
+          L.fft_plan = get_plan(wl, B.overlap);
+          if (L.fft_plan < 0) { b->call_status[c] = SGB_ERR_UNSUPPORTED; L.bypass = 1; }
+        }
+      }
+      if (L.bypass) { L.filt_len = L.sound_len; L.nc = 0; L.nint = 0; }
+      sound_total += align4(cur + 8) + (L.bypass ? 0 : L.wl + 16);
+      if (!L.bypass) {
+        L.filt_off = filt_total; filt_total += align4(L.filt_len + 4);
+        L.env_off = env_total; env_total += align4((int64_t)(L.wl / 2) * L.nint);
+        EnvInst I; I.out_off = L.env_off; I.env_id = B.env_id; I.nr = L.wl / 2; I.nc = L.nint; I.pad = 0;
+        envinst.push_back(I);
+        FftJob J; memset(&J, 0, sizeof J);
+        J.in_off = L.sound_off; J.out_off = L.filt_off; J.env_off = L.env_off; J.plan = L.fft_plan;
+        J.nc = L.nc; J.nint = L.nint; J.xlen = L.filt_len; J.out_len = L.filt_len; J.shift = 0; J.max_slot = bi;
+        fjobs.push_back(J);
+        info.filter_frames += L.nc;
+        info.filter_samples += L.filt_len;
+      }
+      // post-filter noise: soundFiltered = addVectors(soundFiltered, unvoiced[[s]], syllableStartIdx[s])
+      int64_t fcur = L.filt_len, fshift = 0;
+      std::vector<int64_t> fpos(npos.size(), 0);
+      for (int n = B.noise_begin; n < B.noise_end; n++) {
+        const sgb_noise &N = b->noises[n];
+        if (N.mix != 1) continue;
+        int ip = N.insertion;
+        if (ip > 1) { fpos[n - B.noise_begin] = ip; fcur = std::max<int64_t>(fcur, (int64_t)ip + N.len); }
+        else if (ip < 1) {
+          int64_t pad = 1 - ip;
+          fshift += pad;
+          for (int m = B.noise_begin; m < n; m++) if (b->noises[m].mix == 1) fpos[m - B.noise_begin] += pad;
+          fpos[n - B.noise_begin] = 0;
+          fcur = std::max<int64_t>(fcur + pad, N.len);
+        } else { fpos[n - B.noise_begin] = 0; fcur = std::max<int64_t>(fcur, N.len); }
+      }
+      L.final_len = (int32_t)fcur;
+      L.final_shift = (int32_t)fshift;
+      L.out_off = out_total + clen + B.lead_silence;
+      for (int n = B.noise_begin; n < B.noise_end; n++)
+        if (b->noises[n].mix == 1) b->nl[n].dst_off = L.out_off + fpos[n - B.noise_begin];
+      clen += (int64_t)B.lead_silence + fcur + B.tail_silence;
+      // noise generation jobs
+      for (int n = B.noise_begin; n < B.noise_end; n++) {
+        const sgb_noise &N = b->noises[n];
+        NoiseLayout &Q = b->nl[n];
+        Q.bout = bi;
+        Q.raw_off = noise_total; noise_total += align4(N.len + 4);
+        double h_in = N.wl - (N.overlap * N.wl / 100.0), h_out = N.wl * (100.0 - N.overlap) / 100.0;
+        Q.nc = seq_by_count(1.0, (double)N.len + N.wl, h_in);
+        Q.xlen = (int32_t)std::floor(N.wl + (Q.nc - 1) * h_out);
+        match_lengths(Q.xlen, N.len, &Q.pad_len, &Q.trim_start);
+        Q.fft_plan = get_plan(N.wl, N.overlap);
+        Q.env_off = -1; Q.nc_env = 0;
+        if (Q.fft_plan < 0) { b->call_status[c] = SGB_ERR_UNSUPPORTED; continue; }
+        if (N.env_id >= 0) {
+          const sgb_envelope &E = b->envs[N.env_id];
+          Q.nc_env = std::max(1, E.nc_fixed);
+          Q.env_off = env_total; env_total += align4((int64_t)(N.wl / 2) * Q.nc_env);
+          EnvInst I; I.out_off = Q.env_off; I.env_id = N.env_id; I.nr = N.wl / 2; I.nc = Q.nc_env; I.pad = 0;
+          envinst.push_back(I);
+        }
+        FftJob J; memset(&J, 0, sizeof J);
+        J.in_off = N.u_off; J.out_off = Q.raw_off; J.env_off = Q.env_off; J.plan = Q.fft_plan; J.nc = Q.nc;
+        J.nint = Q.nc_env; J.xlen = Q.xlen; J.out_len = N.len; J.shift = Q.trim_start - Q.pad_len;
+        J.max_slot = NB + n; J.rolloffNoise = N.rolloffNoise;
+        njobs.push_back(J);
+        info.noise_samples += N.len;
+      }
+    }
+    b->call_len[c] = clen;
+    out_total += align4(clen);
+    if (b->call_status[c] != SGB_OK) n_failed++;
+  }
+  b->total_out = out_total;
+  info.n_failed = n_failed;
+  for (int c = 0; c < NC; c++) info.total_samples += b->call_len[c];
+
+  std::vector<FftSeg> fsegs, nsegs;
+  make_segs(fjobs, fsegs);
+  make_segs(njobs, nsegs);
+
+  std::vector<FftPlan> &plans = PT.plans;
+  std::vector<float2> &tw_host = PT.tw;
+  std::vector<float> &win_host = PT.win;
+  const int64_t tw_total = (int64_t)tw_host.size(), win_total = (int64_t)win_host.size();
+  // ---- upload layout ----
+  CK(b->d_bl.ensure(sizeof(BoutLayout) * (size_t)NB));
+  CK(b->d_place.ensure(sizeof(SylPlace) * (size_t)S));
+  CK(b->d_nl.ensure(sizeof(NoiseLayout) * (size_t)std::max(NN, 1)));
+  CK(b->d_envinst.ensure(sizeof(EnvInst) * std::max<size_t>(envinst.size(), 1)));
+  CK(b->d_plans.ensure(sizeof(FftPlan) * std::max<size_t>(plans.size(), 1)));
+  CK(b->d_tw.ensure(8 * (size_t)std::max<int64_t>(tw_total, 1)));
+  CK(b->d_win.ensure(4 * (size_t)std::max<int64_t>(win_total, 1)));
+  CK(b->d_fjobs.ensure(sizeof(FftJob) * std::max<size_t>(fjobs.size(), 1)));
+  CK(b->d_njobs.ensure(sizeof(FftJob) * std::max<size_t>(njobs.size(), 1)));
+  CK(b->d_fsegs.ensure(sizeof(FftSeg) * std::max<size_t>(fsegs.size(), 1)));
+  CK(b->d_nsegs.ensure(sizeof(FftSeg) * std::max<size_t>(nsegs.size(), 1)));
+  CK(b->d_max.ensure(4 * (size_t)(NB + NN + 1)));
+  CK(b->d_sound.ensure(4 * (size_t)(sound_total + 64)));
+  CK(b->d_filt.ensure(4 * (size_t)(filt_total + 64)));
+  CK(b->d_env.ensure(4 * (size_t)(env_total + 64)));
+  CK(b->d_noise_raw.ensure(4 * (size_t)(noise_total + 64)));
+  CK(b->d_noise_fin.ensure(4 * (size_t)(noise_total + 64)));
+  CK(b->d_out.ensure(4 * (size_t)(out_total + 64)));
+  auto up = [&](DBuf &d, const void *src, size_t bytes) -> cudaError_t {
+    if (!bytes) return cudaSuccess;
+    return cudaMemcpyAsync(d.p, src, bytes, cudaMemcpyHostToDevice, st);
+  };
+  CK(up(b->d_bl, b->bl.data(), sizeof(BoutLayout) * (size_t)NB));
+  CK(up(b->d_place, b->place.data(), sizeof(SylPlace) * (size_t)S));
+  CK(up(b->d_nl, b->nl.data(), sizeof(NoiseLayout) * (size_t)NN));
+  CK(up(b->d_envinst, envinst.data(), sizeof(EnvInst) * envinst.size()));
+  CK(up(b->d_plans, plans.data(), sizeof(FftPlan) * plans.size()));
+  CK(up(b->d_tw, tw_host.data(), 8 * (size_t)tw_total));
+  CK(up(b->d_win, win_host.data(), 4 * (size_t)win_total));
+  CK(up(b->d_fjobs, fjobs.data(), sizeof(FftJob) * fjobs.size()));
+  CK(up(b->d_njobs, njobs.data(), sizeof(FftJob) * njobs.size()));
+  CK(up(b->d_fsegs, fsegs.data(), sizeof(FftSeg) * fsegs.size()));
+  CK(up(b->d_nsegs, nsegs.data(), sizeof(FftSeg) * nsegs.size()));
+  CK(cudaMemsetAsync(b->d_sound.p, 0, 4 * (size_t)(sound_total + 64), st));
+  CK(cudaMemsetAsync(b->d_out.p, 0, 4 * (size_t)(out_total + 64), st));
+  if (noise_total) CK(cudaMemsetAsync(b->d_noise_raw.p, 0, 4 * (size_t)(noise_total + 64), st));
+  k_fill_int<<<(NB + NN + 256) / 256, 256, 0, st>>>(b->d_max.as<int>(), NB + NN + 1, ORDERED_NEG_INF);
+  launches++;
+
+  const int chunks = (NB >= 1024) ? 4 : ((NB >= 64) ? 16 : 64);
+  // ---- voiced syllables -> sound ----
+  launch_place_voiced(d_syl, S, d_ctrl, d_lay, b->d_place.as<SylPlace>(), P, b->d_raw.as<float>(),
+                      b->d_sound.as<float>(), chunks, st);
+  launches++;
+  if (b->keep_voiced) {
+    CK(b->d_voiced.ensure(4 * (size_t)(sound_total + 64)));
+    CK(cudaMemcpyAsync(b->d_voiced.p, b->d_sound.p, 4 * (size_t)(sound_total + 64), cudaMemcpyDeviceToDevice, st));
+  }
+  CK(cudaEventRecord(ev[5], st));   // assemble (part 1)
+  // ---- K4 envelopes (bouts + noises) ----
+  int max_nc = 0;
+  for (auto &I : envinst) max_nc = std::max(max_nc, I.nc);
+  launch_envelope_f32(b->d_envinst.as<EnvInst>(), (int)envinst.size(), max_nc, b->d_envs.as<sgb_envelope>(),
+                      b->d_frefs.as<sgb_formant_ref>(), b->d_formants.as<double>(), b->d_anchors.as<double>(),
+                      b->d_env.as<float>(), st);
+  if (!envinst.empty()) launches++;
+  CK(cudaEventRecord(ev[6], st));
+  // ---- K5 noise ----
+  if (!nsegs.empty()) {
+    size_t smem = 0;
+    for (auto &J : njobs) smem = std::max(smem, stft_smem_bytes(plans[J.plan].n, plans[J.plan].h_in, plans[J.plan].h_out, 1));
+    if (smem > 226 * 1024) return fail(SGB_ERR_UNSUPPORTED, "noise window too long for shared memory (%zu bytes)", smem);
+    CK(launch_stft(1, b->u_is_float, b->d_nsegs.as<FftSeg>(), (int)nsegs.size(), b->d_njobs.as<FftJob>(),
+                   b->d_plans.as<FftPlan>(), b->d_tw.as<float2>(), b->d_win.as<float>(), nullptr, b->d_u.p,
+                   b->d_env.as<float>(), b->d_noise_raw.as<float>(), b->d_max.as<int>(), smem, st));
+    launch_noise_final(b->d_noises.as<sgb_noise>(), NN, b->d_nl.as<NoiseLayout>(), b->d_anchors.as<double>(),
+                       b->d_pre.as<double>(), b->d_max.as<int>(), NB, b->d_noise_raw.as<float>(),
+                       b->d_noise_fin.as<float>(), 16, st);
+    launches += 2;
+  }
+  CK(cudaEventRecord(ev[7], st));
+  // ---- sound = voiced + breathing, global envelope ----
+  launch_sound_mix(b->d_bouts.as<sgb_bout>(), NB, b->d_bl.as<BoutLayout>(), b->d_noises.as<sgb_noise>(),
+                   b->d_nl.as<NoiseLayout>(), b->d_anchors.as<double>(), b->d_noise_fin.as<float>(),
+                   b->d_sound.as<float>(), chunks, st);
+  launches++;
+  CK(cudaEventRecord(ev[8], st));
+  // ---- K2 filter ----
+  if (!fsegs.empty()) {
+    size_t smem = 0;
+    for (auto &J : fjobs) smem = std::max(smem, stft_smem_bytes(plans[J.plan].n, plans[J.plan].h_in, plans[J.plan].h_out, 0));
+    if (smem > 226 * 1024) return fail(SGB_ERR_UNSUPPORTED, "window too long for shared memory (%zu bytes)", smem);
+    CK(launch_stft(0, 0, b->d_fsegs.as<FftSeg>(), (int)fsegs.size(), b->d_fjobs.as<FftJob>(),
+                   b->d_plans.as<FftPlan>(), b->d_tw.as<float2>(), b->d_win.as<float>(), b->d_sound.as<float>(),
+                   nullptr, b->d_env.as<float>(), b->d_filt.as<float>(), b->d_max.as<int>(), smem, st));
+    launches++;
+  }
+  CK(cudaEventRecord(ev[9], st));
+  // ---- normalise, post-filter noise, AM, silences ----
+  launch_finalize(0, b->d_bouts.as<sgb_bout>(), NB, b->d_bl.as<BoutLayout>(), b->d_noises.as<sgb_noise>(),
+                  b->d_nl.as<NoiseLayout>(), b->d_sound.as<float>(), b->d_filt.as<float>(),
+                  b->d_noise_fin.as<float>(), b->d_max.as<int>(), b->d_out.p, chunks, st);
+  launches++;
+  CK(cudaEventRecord(ev[10], st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  info.kernel_launches = launches;
+  float ms;
+  CK(cudaEventElapsedTime(&ms, ev[0], ev[1])); info.ms[SGB_T_CONTROL] = ms;
+  CK(cudaEventElapsedTime(&ms, ev[1], ev[2])); info.ms[SGB_T_AMPL] = ms;
+  CK(cudaEventElapsedTime(&ms, ev[2], ev[3])); info.ms[SGB_T_SYNTH] = ms;
+  CK(cudaEventElapsedTime(&ms, ev[3], ev[4])); info.ms[SGB_T_COMPOSE] = ms;
+  CK(cudaEventElapsedTime(&ms, ev[4], ev[5])); info.ms[SGB_T_ASSEMBLE] = ms;
+  CK(cudaEventElapsedTime(&ms, ev[5], ev[6])); info.ms[SGB_T_ENVELOPE] = ms;
+  CK(cudaEventElapsedTime(&ms, ev[6], ev[7])); info.ms[SGB_T_NOISE] = ms;
+  CK(cudaEventElapsedTime(&ms, ev[7], ev[8])); info.ms[SGB_T_ASSEMBLE] += ms;
+  CK(cudaEventElapsedTime(&ms, ev[8], ev[9])); info.ms[SGB_T_FILTER] = ms;
+  CK(cudaEventElapsedTime(&ms, ev[9], ev[10])); info.ms[SGB_T_FINALIZE] = ms;
+  CK(cudaEventElapsedTime(&ms, ev[0], ev[10])); info.ms[SGB_T_TOTAL] = ms;
+  b->have_run = true;
+  if (info_out) *info_out = info;
+  return SGB_OK;
+}
+
+int sgb_batch_lengths(sgb_batch *b, int64_t *out_len) {
+  if (!b || !out_len) return fail(SGB_ERR_INVALID, "null argument");
+  if (!b->have_run) return fail(SGB_ERR_STATE, "no completed run");
+  for (size_t c = 0; c < b->call_len.size(); c++) out_len[c] = b->call_len[c];
+  return SGB_OK;
+}
+
+int sgb_batch_status(sgb_batch *b, int32_t *out_status) {
+  if (!b || !out_status) return fail(SGB_ERR_INVALID, "null argument");
+  if (!b->have_run) return fail(SGB_ERR_STATE, "no completed run");
+  for (size_t c = 0; c < b->call_status.size(); c++) out_status[c] = b->call_status[c];
+  return SGB_OK;
+}
+
+static int fetch_common(sgb_batch *b, void *out, int64_t n, bool f64) {
+  if (!b || !out) return fail(SGB_ERR_INVALID, "null argument");
+  if (!b->have_run) return fail(SGB_ERR_STATE, "no completed run");
+  CK(cudaSetDevice(b->device));
+  int64_t need = 0;
+  for (auto l : b->call_len) need += l;
+  if (n < need) return fail(SGB_ERR_INVALID, "output buffer too small: %lld < %lld", (long long)n, (long long)need);
+  cudaStream_t st = b->st;
+  CK(cudaEventRecord(b->ev[SGB_T_COUNT], st));
+  const void *src = b->d_out.p;
+  size_t esz = 4;
+  if (f64) {
+    CK(b->d_out64.ensure(8 * (size_t)(b->total_out + 64)));
+    int64_t m = b->total_out;
+    if (m > 0) k_f32_to_f64<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(b->d_out.as<float>(), b->d_out64.as<double>(), m);
+    src = b->d_out64.p; esz = 8;
+  }
+  int64_t pos = 0;
+  for (size_t c = 0; c < b->call_len.size(); c++) {
+    if (b->call_len[c] > 0)
+      CK(cudaMemcpyAsync((char *)out + pos * esz, (const char *)src + b->call_off[c] * esz, (size_t)b->call_len[c] * esz,
+                         cudaMemcpyDeviceToHost, st));
+    pos += b->call_len[c];
+  }
+  CK(cudaEventRecord(b->ev[SGB_T_COUNT + 1], st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaEventElapsedTime(&b->info.ms[SGB_T_D2H], b->ev[SGB_T_COUNT], b->ev[SGB_T_COUNT + 1]));
+  return SGB_OK;
+}
+int sgb_batch_fetch_f32(sgb_batch *b, float *out, int64_t n) { return fetch_common(b, out, n, false); }
+int sgb_batch_fetch_f64(sgb_batch *b, double *out, int64_t n) { return fetch_common(b, out, n, true); }
+
+int sgb_batch_syllable_len(sgb_batch *b, int32_t syl, int64_t *out_len) {
+  if (!b || !out_len) return fail(SGB_ERR_INVALID, "null argument");
+  if (!b->have_run) return fail(SGB_ERR_STATE, "no completed run");
+  if (syl < 0 || syl >= (int)b->syls.size()) return fail(SGB_ERR_INVALID, "syllable index");
+  if (b->summary[syl].status != SGB_OK) return fail(b->summary[syl].status, "syllable %d failed (status %d)", syl, b->summary[syl].status);
+  *out_len = b->place[syl].len;
+  return SGB_OK;
+}
+
+int sgb_batch_syllable_fetch(sgb_batch *b, int32_t syl, double *out, int64_t n) {
+  int64_t len;
+  int rc = sgb_batch_syllable_len(b, syl, &len);
+  if (rc) return rc;
+  if (!b->keep_voiced) return fail(SGB_ERR_STATE, "intermediates are kept only for batches of <= 64 calls");
+  if (n < len) return fail(SGB_ERR_INVALID, "buffer too small");
+  CK(cudaSetDevice(b->device));
+  std::vector<float> tmp((size_t)len);
+  CK(cudaMemcpy(tmp.data(), b->d_voiced.as<float>() + b->place[syl].dst_off, 4 * (size_t)len, cudaMemcpyDeviceToHost));
+  for (int64_t i = 0; i < len; i++) out[i] = (double)tmp[i];
+  return SGB_OK;
+}
+
+int sgb_batch_noise_fetch(sgb_batch *b, int32_t noise, double *out, int64_t n) {
+  if (!b || !out) return fail(SGB_ERR_INVALID, "null argument");
+  if (!b->have_run) return fail(SGB_ERR_STATE, "no completed run");
+  if (noise < 0 || noise >= (int)b->noises.size()) return fail(SGB_ERR_INVALID, "noise index");
+  int64_t len = b->noises[noise].len;
+  if (n < len) return fail(SGB_ERR_INVALID, "buffer too small");
+  CK(cudaSetDevice(b->device));
+  std::vector<float> tmp((size_t)len);
+  CK(cudaMemcpy(tmp.data(), b->d_noise_fin.as<float>() + b->nl[noise].raw_off, 4 * (size_t)len, cudaMemcpyDeviceToHost));
+  for (int64_t i = 0; i < len; i++) out[i] = (double)tmp[i];
+  return SGB_OK;
+}
+
+static int get_ctrl(sgb_batch *b, int32_t syl, SylCtrl *C) {
+  if (!b) return fail(SGB_ERR_INVALID, "null batch");
+  if (!b->have_run) return fail(SGB_ERR_STATE, "no completed run");
+  if (syl < 0 || syl >= (int)b->syls.size()) return fail(SGB_ERR_INVALID, "syllable index");
+  CK(cudaSetDevice(b->device));
+  CK(cudaMemcpy(C, b->d_ctrl.as<SylCtrl>() + syl, sizeof(SylCtrl), cudaMemcpyDeviceToHost));
+  return SGB_OK;
+}
+
+int sgb_batch_artefacts(sgb_batch *b, int32_t syl, sgb_syl_artefacts *out) {
+  if (!out) return fail(SGB_ERR_INVALID, "null argument");
+  SylCtrl C;
+  int rc = get_ctrl(b, syl, &C);
+  if (rc) return rc;
+  out->nGC = C.nGC; out->nHarmonics = C.nHarmonics; out->rows_kept = C.rows_kept; out->nEpochs = C.nEpochs;
+  out->n_upsampled = C.n_up; out->n_jitter_idx = C.n_jidx; out->z_used = C.z_used; out->status = C.status;
+  out->raw_max = C.raw_max;
+  return SGB_OK;
+}
+
+int sgb_batch_artefact_ints(sgb_batch *b, int32_t syl, int which, int32_t *out, int32_t cap) {
+  if (!out) return fail(SGB_ERR_INVALID, "null argument");
+  SylCtrl C;
+  int rc = get_ctrl(b, syl, &C);
+  if (rc) return rc;
+  std::vector<int64_t> gc_off(2);
+  CK(cudaMemcpy(gc_off.data(), b->d_gc_off.as<int64_t>() + syl, 8, cudaMemcpyDeviceToHost));
+  const int64_t o = gc_off[0];
+  const int32_t *src = nullptr;
+  int n = 0;
+  switch (which) {
+    case 0: src = b->pools.gc + o; n = C.nGC; break;
+    case 1: src = b->pools.gcup + o; n = C.nGC + 1; break;
+    case 2: src = b->pools.nsub + o; n = C.nGC; break;
+    case 3: src = b->pools.rwbin + o; n = C.nGC; break;
+    case 4: src = b->pools.jidx + o; n = C.n_jidx; break;
+    case 5:
+      n = 2 * C.nEpochs;
+      if (cap < n) return fail(SGB_ERR_INVALID, "buffer too small");
+      for (int e = 0; e < C.nEpochs; e++) { out[2 * e] = C.ep_start[e]; out[2 * e + 1] = C.ep_end[e]; }
+      return n;
+    case 6:
+      n = 2 * C.nEpochs;
+      if (cap < n) return fail(SGB_ERR_INVALID, "buffer too small");
+      for (int e = 0; e < C.nEpochs; e++) { out[2 * e] = C.ep_zc1[e]; out[2 * e + 1] = C.ep_zc2[e]; }
+      return n;
+    default: return fail(SGB_ERR_INVALID, "unknown artefact %d", which);
+  }
+  if (cap < n) return fail(SGB_ERR_INVALID, "buffer too small");
+  if (n > 0) CK(cudaMemcpy(out, src, 4 * (size_t)n, cudaMemcpyDeviceToHost));
+  return n;
+}
+
+int sgb_batch_pitch_per_gc(sgb_batch *b, int32_t syl, double *out, int32_t cap) {
+  if (!out) return fail(SGB_ERR_INVALID, "null argument");
+  SylCtrl C;
+  int rc = get_ctrl(b, syl, &C);
+  if (rc) return rc;
+  if (cap < C.nGC) return fail(SGB_ERR_INVALID, "buffer too small");
+  int64_t o;
+  CK(cudaMemcpy(&o, b->d_gc_off.as<int64_t>() + syl, 8, cudaMemcpyDeviceToHost));
+  if (C.nGC > 0) CK(cudaMemcpy(out, b->pools.ppg + o, 8 * (size_t)C.nGC, cudaMemcpyDeviceToHost));
+  return C.nGC;
+}
+
+// ------------------------------------------------------------ single calls ---
+int sgb_get_rolloff(const double *pitch_per_gc, int32_t nGC, int32_t nHarmonics, const double *rolloff,
+                    int32_t n_rolloff, const double *rolloffOct, int32_t n_rolloffOct, const double *rolloffKHz,
+                    int32_t n_rolloffKHz, double rolloffParab, double rolloffParabHarm,
+                    double rolloffParabCeiling, double baseline, double throwaway, double samplingRate,
+                    double *out, int32_t *out_rows) {
+  if (!pitch_per_gc || !rolloff || !rolloffOct || !rolloffKHz || !out || !out_rows) return fail(SGB_ERR_INVALID, "null argument");
+  if (nGC < 1 || nHarmonics < 2) return fail(SGB_ERR_INVALID, "need nGC >= 1 and nHarmonics >= 2");
+  auto okn = [&](int n) { return n == 1 || n == nGC; };
+  if (!okn(n_rolloff) || !okn(n_rolloffOct) || !okn(n_rolloffKHz)) return fail(SGB_ERR_INVALID, "vector arguments must have length 1 or nGC");
+  int nd = 0;
+  if (cudaGetDeviceCount(&nd) != cudaSuccess || nd < 1) return fail(SGB_ERR_CUDA, "no CUDA device available (no CPU fallback)");
+  DBuf dp, dr, dro, drk, dout, drows, dcm, dkept;
+  int rc = SGB_OK;
+  auto run = [&]() -> int {
+    CK(dp.ensure(8 * (size_t)nGC)); CK(dr.ensure(8 * (size_t)n_rolloff)); CK(dro.ensure(8 * (size_t)n_rolloffOct));
+    CK(drk.ensure(8 * (size_t)n_rolloffKHz)); CK(dout.ensure(8 * (size_t)nGC * nHarmonics)); CK(drows.ensure(16));
+    CK(dcm.ensure(8 * (size_t)nGC)); CK(dkept.ensure(4 * (size_t)nHarmonics));
+    CK(cudaMemcpy(dp.p, pitch_per_gc, 8 * (size_t)nGC, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dr.p, rolloff, 8 * (size_t)n_rolloff, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dro.p, rolloffOct, 8 * (size_t)n_rolloffOct, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(drk.p, rolloffKHz, 8 * (size_t)n_rolloffKHz, cudaMemcpyHostToDevice));
+    launch_rolloff_api(dp.as<double>(), nGC, nHarmonics, dr.as<double>(), n_rolloff, dro.as<double>(), n_rolloffOct,
+                              drk.as<double>(), n_rolloffKHz, rolloffParab, rolloffParabHarm, rolloffParabCeiling,
+                              baseline, throwaway, samplingRate, dout.as<double>(), drows.as<int>(), dcm.as<double>(),
+                              dkept.as<int>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(out, dout.p, 8 * (size_t)nGC * nHarmonics, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out_rows, drows.p, 4, cudaMemcpyDeviceToHost));
+    return SGB_OK;
+  };
+  rc = run();
+  dp.release(); dr.release(); dro.release(); drk.release(); dout.release(); drows.release(); dcm.release(); dkept.release();
+  return rc;
+}
+
+int sgb_get_spectral_envelope(int32_t nr, int32_t nc, const sgb_envelope *env, const double *formants,
+                              const int32_t *formant_n, const double *mouth_anchors, double *out) {
+  if (!env || !out) return fail(SGB_ERR_INVALID, "null argument");
+  if (nr < 1 || nc < 1) return fail(SGB_ERR_INVALID, "nr and nc must be positive");
+  if (env->n_formants < 0 || env->n_formants > 30) return fail(SGB_ERR_UNSUPPORTED, "more than 30 formants");
+  if (env->n_formants > 0 && (!formants || !formant_n)) return fail(SGB_ERR_INVALID, "formants missing");
+  if (env->mouth_n > 0 && !mouth_anchors) return fail(SGB_ERR_INVALID, "mouth anchors missing");
+  int nd = 0;
+  if (cudaGetDeviceCount(&nd) != cudaSuccess || nd < 1) return fail(SGB_ERR_CUDA, "no CUDA device available (no CPU fallback)");
+  sgb_envelope E = *env;
+  std::vector<sgb_formant_ref> refs(std::max(1, E.n_formants));
+  int64_t rows = 0;
+  for (int f = 0; f < E.n_formants; f++) {
+    int n = E.tracks_given ? nc : formant_n[f];
+    if (n < 1) return fail(SGB_ERR_INVALID, "formant %d has no rows", f);
+    refs[f].off = rows; refs[f].n = n; refs[f].pad = 0; rows += n;
+  }
+  E.formant_off = 0; E.mouth_off = 0;
+  EnvInst I; I.out_off = 0; I.env_id = 0; I.nr = nr; I.nc = nc; I.pad = 0;
+  DBuf dE, dR, dF, dA, dI, dO;
+  auto run = [&]() -> int {
+    CK(dE.ensure(sizeof E)); CK(dR.ensure(sizeof(sgb_formant_ref) * refs.size())); CK(dF.ensure(32 * (size_t)std::max<int64_t>(rows, 1)));
+    CK(dA.ensure(16 * (size_t)std::max(1, E.mouth_n))); CK(dI.ensure(sizeof I)); CK(dO.ensure(8 * (size_t)nr * nc));
+    CK(cudaMemcpy(dE.p, &E, sizeof E, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dR.p, refs.data(), sizeof(sgb_formant_ref) * refs.size(), cudaMemcpyHostToDevice));
+    if (rows) CK(cudaMemcpy(dF.p, formants, 32 * (size_t)rows, cudaMemcpyHostToDevice));
+    if (E.mouth_n) CK(cudaMemcpy(dA.p, mouth_anchors, 16 * (size_t)E.mouth_n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dI.p, &I, sizeof I, cudaMemcpyHostToDevice));
+    launch_envelope_f64(dI.as<EnvInst>(), 1, nc, dE.as<sgb_envelope>(), dR.as<sgb_formant_ref>(), dF.as<double>(),
+                        dA.as<double>(), dO.as<double>(), 0);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(out, dO.p, 8 * (size_t)nr * nc, cudaMemcpyDeviceToHost));
+    return SGB_OK;
+  };
+  int rc = run();
+  dE.release(); dR.release(); dF.release(); dA.release(); dI.release(); dO.release();
+  return rc;
+}
+
+int64_t sgb_filter_len(int64_t len, int32_t wl, double overlap) {
+  if (len < 8 || wl < 4) return -1;
+  int w = (int)std::min<int64_t>(wl, len / 2);
+  double h_in = w - (overlap * w / 100.0), h_out = w * (100.0 - overlap) / 100.0;
+  int nc = seq_by_count(1.0, std::max<double>(1.0, (double)(len - w)), h_in);
+  return (int64_t)std::floor(w + (nc - 1) * h_out);
+}
+
+int sgb_filter(const double *sound, int64_t len, const double *envelope, int32_t nInt, int32_t wl,
+               double overlap, double *out, int64_t out_cap) {
+  if (!sound || !envelope || !out) return fail(SGB_ERR_INVALID, "null argument");
+  int nd = 0;
+  if (cudaGetDeviceCount(&nd) != cudaSuccess || nd < 1) return fail(SGB_ERR_CUDA, "no CUDA device available (no CPU fallback)");
+  if (len < 8 || len > 2000000000LL) return fail(SGB_ERR_INVALID, "sound length out of range");
+  if (!(overlap >= 0.0 && overlap < 100.0)) return fail(SGB_ERR_INVALID, "overlap out of range");
+  int w = (int)std::min<int64_t>(wl, len / 2);     // soundgen.R:743
+  if (w < 4 || (w & 1)) return fail(SGB_ERR_UNSUPPORTED, "window of %d points (odd or < 4) is not supported", w);
+  PlanTable PT;
+  int pi = PT.get(w, overlap);
+  if (pi < 0) return fail(SGB_ERR_UNSUPPORTED, "cannot factor window length %d", w);
+  const FftPlan &pl = PT.plans[pi];
+  const int nr = w / 2;
+  const int nc = seq_by_count(1.0, std::max<double>(1.0, (double)(len - w)), pl.h_in);
+  if (nInt != 1 && nInt != nc) return fail(SGB_ERR_INVALID, "envelope must have 1 or %d columns, got %d", nc, nInt);
+  const int64_t xlen = (int64_t)std::floor(w + (nc - 1) * pl.h_out);
+  if (out_cap < xlen) return fail(SGB_ERR_INVALID, "output buffer too small: need %lld", (long long)xlen);
+  size_t smem = stft_smem_bytes(w, pl.h_in, pl.h_out, 0);
+  if (smem > 226 * 1024) return fail(SGB_ERR_UNSUPPORTED, "window too long for shared memory");
+  FftJob J; memset(&J, 0, sizeof J);
+  J.in_off = 0; J.out_off = 0; J.env_off = 0; J.plan = 0; J.nc = nc; J.nint = nInt; J.xlen = (int32_t)xlen;
+  J.out_len = (int32_t)xlen; J.shift = 0; J.max_slot = 0;
+  std::vector<FftJob> jobs(1, J);
+  std::vector<FftSeg> segs;
+  make_segs(jobs, segs);
+  DBuf d64, dS, dE64, dE, dO, dPl, dTw, dWin, dJ, dSg, dMax, dO64;
+  auto run = [&]() -> int {
+    const size_t nenv = (size_t)nr * nInt;
+    CK(d64.ensure(8 * (size_t)len)); CK(dS.ensure(4 * (size_t)(len + w + 64))); CK(dE64.ensure(8 * nenv));
+    CK(dE.ensure(4 * nenv)); CK(dO.ensure(4 * (size_t)(xlen + 64))); CK(dO64.ensure(8 * (size_t)(xlen + 64)));
+    CK(dPl.ensure(sizeof(FftPlan))); CK(dTw.ensure(8 * PT.tw.size())); CK(dWin.ensure(4 * PT.win.size()));
+    CK(dJ.ensure(sizeof(FftJob))); CK(dSg.ensure(sizeof(FftSeg) * segs.size())); CK(dMax.ensure(16));
+    CK(cudaMemcpy(d64.p, sound, 8 * (size_t)len, cudaMemcpyHostToDevice));
+    CK(cudaMemset(dS.p, 0, 4 * (size_t)(len + w + 64)));
+    k_f64_to_f32<<<(unsigned)((len + 255) / 256), 256>>>(d64.as<double>(), dS.as<float>(), len);
+    CK(cudaMemcpy(dE64.p, envelope, 8 * nenv, cudaMemcpyHostToDevice));
+    k_f64_to_f32<<<(unsigned)((nenv + 255) / 256), 256>>>(dE64.as<double>(), dE.as<float>(), (int64_t)nenv);
+    CK(cudaMemcpy(dPl.p, &pl, sizeof(FftPlan), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dTw.p, PT.tw.data(), 8 * PT.tw.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dWin.p, PT.win.data(), 4 * PT.win.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dJ.p, &J, sizeof J, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dSg.p, segs.data(), sizeof(FftSeg) * segs.size(), cudaMemcpyHostToDevice));
+    k_fill_int<<<1, 32>>>(dMax.as<int>(), 4, ORDERED_NEG_INF);
+    CK(launch_stft(0, 0, dSg.as<FftSeg>(), (int)segs.size(), dJ.as<FftJob>(), dPl.as<FftPlan>(), dTw.as<float2>(),
+                   dWin.as<float>(), dS.as<float>(), nullptr, dE.as<float>(), dO.as<float>(), dMax.as<int>(), smem, 0));
+    CK(cudaDeviceSynchronize());
+    int mi;
+    CK(cudaMemcpy(&mi, dMax.p, 4, cudaMemcpyDeviceToHost));
+    int fi = (mi >= 0) ? mi : (mi ^ 0x7FFFFFFF);
+    float mx;
+    memcpy(&mx, &fi, 4);
+    std::vector<float> tmp((size_t)xlen);
+    CK(cudaMemcpy(tmp.data(), dO.p, 4 * (size_t)xlen, cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < xlen; i++) out[i] = (double)tmp[i] / (double)mx;   // soundgen.R:807
+    return SGB_OK;
+  };
+  int rc = run();
+  DBuf *all[] = {&d64, &dS, &dE64, &dE, &dO, &dPl, &dTw, &dWin, &dJ, &dSg, &dMax, &dO64};
+  for (auto d : all) d->release();
+  return rc;
+}
+
+}  // extern "C"

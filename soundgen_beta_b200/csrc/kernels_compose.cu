@@ -1,0 +1,336 @@
+// K6: epoch joining and post-synthesis effects of generateHarmonics
+// (R/source.R:386-467): crossFade at upward zero crossings
+// (R/utilities_soundgen.R:255-375), amplitude envelope, signed-max normalisation,
+// attack fade, drift amplitude.  One CTA per syllable, epochs in sequence.
+//
+// The zero-crossing searches decide the syllable's LENGTH, so a sign flip from FP32
+// rounding would shift the whole waveform.  K1's float samples are therefore only
+// trusted when |w| is well above their error bound; samples closer to zero are
+// re-evaluated in FP64 with the reference's own formula (exact_epoch_sample).
+#include "engine.cuh"
+
+#define COMPOSE_THREADS 256
+#define ZC_REL_TOL 2e-4f
+
+struct SylView {
+  const int32_t *gcup;
+  const double *kt, *py, *sb, *sc, *sd, *phi;
+  const SylCtrl *C;
+  const double *amp;     // syllable's amplitude block
+  double sr;
+  int G;
+};
+
+// waveform_epoch[k] (0-based k) exactly as R/source.R:403-409 computes it, in double.
+__device__ double exact_epoch_sample(const SylView &V, int e, int k) {
+  const SylCtrl &C = *V.C;
+  const int g_first = C.ep_start[e] - 1, g_lastStart = C.ep_end[e] - 1;
+  const int nsub = C.vf_active ? C.ep_nsub[e] : 0;
+  const int J = C.ep_rows[e];
+  const int x_first_i = V.gcup[g_first];
+  const double x_first = (double)x_first_i, x_last = (double)V.gcup[g_lastStart];
+  const int Ne = V.gcup[C.ep_end[e]] - x_first_i + 1;
+  const double by = (x_last - x_first) / (double)(Ne - 1);
+  const int nk = g_lastStart - g_first + 1;
+  double v = (k >= Ne - 1) ? x_last : (x_first + (double)k * by);
+  int lo = 0, hi = nk - 1;
+  while (hi > lo + 1) {
+    int mid = (lo + hi) >> 1;
+    if (v < (double)V.gcup[g_first + mid]) hi = mid; else lo = mid;
+  }
+  double xg = (double)V.gcup[g_first + lo], xn = (double)V.gcup[g_first + lo + 1];
+  double wfrac = (v - xg) / (xn - xg);
+  double u = (double)(x_first_i + k);
+  int a = 0, b = V.G;
+  while (b > a + 1) {
+    int mid = (a + b) >> 1;
+    if (u < V.kt[mid]) b = mid; else a = mid;
+  }
+  double M = u - V.kt[a];
+  double s1 = M * (M + 1.0) * 0.5, s2 = M * (M + 1.0) * (2.0 * M + 1.0) / 6.0, s3 = s1 * s1;
+  double integr = (V.phi[a] + V.py[a] * (M + 1.0) + V.sb[a] * s1 + V.sc[a] * s2 + V.sd[a] * s3) / V.sr;
+  const double *col = V.amp + C.ep_amp_off[e] + (int64_t)lo * J;
+  double sum = 0.0;
+  for (int j = 1; j <= J; j++) {
+    double y0 = col[j - 1], y1 = col[J + j - 1];
+    if (y0 == 0.0 && y1 == 0.0) continue;
+    double am = y0 + (y1 - y0) * wfrac;
+    double x = integr * ((double)j / (double)(nsub + 1));
+    x -= floor(x);
+    sum += sinpi(2.0 * x) * am;
+  }
+  return sum;
+}
+
+__device__ float block_maxabs(const float *x, int n, float *red) {
+  float m = 0.0f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(x[i]));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0f;
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (threadIdx.x == 0) red[0] = v;
+  }
+  __syncthreads();
+  float r = red[0];
+  __syncthreads();
+  return r;
+}
+
+// sign (-1, 0, +1) of epoch sample k, exact when the float value is within tol of zero
+__device__ int sign_epoch(const SylView &V, const float *w, int e, int k, float tol) {
+  float v = w[k];
+  if (fabsf(v) >= tol) return v > 0.0f ? 1 : -1;
+  double x = exact_epoch_sample(V, e, k);
+  return x > 0.0 ? 1 : (x < 0.0 ? -1 : 0);
+}
+
+__global__ void __launch_bounds__(COMPOSE_THREADS)
+k_compose(const sgb_syllable *__restrict__ syl, int S, SylCtrl *__restrict__ ctrl,
+          const SylLayout *__restrict__ lay, Pools P, const double *__restrict__ amp,
+          const float *__restrict__ wave, float *__restrict__ raw, const double *__restrict__ anchors,
+          const double *__restrict__ pitch_pool) {
+  const int s = blockIdx.x;
+  if (s >= S) return;
+  SylCtrl &C = ctrl[s];
+  const sgb_syllable sp = syl[s];
+  float *comp = raw + lay[s].raw_off;
+  __shared__ float red[32];
+  __shared__ int sh_found;
+  __shared__ int red_i[32];
+
+  if (sp.kind == 2) {   // raw samples supplied by the caller (sgb_filter)
+    const double *src = pitch_pool + sp.pitch_off;
+    for (int i = threadIdx.x; i < sp.pitch_len; i += blockDim.x) comp[i] = (float)src[i];
+    return;
+  }
+  if (sp.kind != 1) return;
+  if (C.status != SGB_OK) { if (threadIdx.x == 0) C.out_len = 0; return; }
+
+  SylView V;
+  const int64_t o = P.gc_off[s];
+  V.gcup = P.gcup + o; V.kt = P.kt + o; V.py = P.ppg + o; V.sb = P.sb + o; V.sc = P.sc + o;
+  V.sd = P.sd + o; V.phi = P.phi + o; V.C = &C; V.amp = amp + lay[s].amp_off;
+  V.sr = sp.samplingRate; V.G = C.nGC;
+
+  int Lc = 1;                 // `waveform = 0` (source.R:386)
+  if (threadIdx.x == 0) comp[0] = 0.0f;
+  int tail_e = -1, tail_start = 0, tail_koff = 0;   // comp[pos] == epoch_tail_e[pos - tail_koff] for pos >= tail_start
+  float tail_tol = 0.0f;
+  const int crossMax = (int)floor(15.0 * sp.samplingRate / 1000.0);
+  __syncthreads();
+
+  for (int e = 0; e < C.nEpochs; e++) {
+    const float *w2 = wave + lay[s].wave_off + C.ep_wave_off[e];
+    const int Ne = V.gcup[C.ep_end[e]] - V.gcup[C.ep_start[e] - 1] + 1;
+    const float tol2 = ZC_REL_TOL * block_maxabs(w2, Ne, red);
+
+    // ---- zc1: last upward zero crossing of the sound so far (findZeroCrossing(ampl1, len)) ----
+    int Lc1;
+    int zc1 = 0;
+    if (Lc == 1) {
+      zc1 = 1; Lc1 = 2;
+      if (threadIdx.x == 0) comp[1] = 0.0f;
+    } else {
+      // largest p in [0, Lc-2] with comp[p] < 0 && comp[p+1] > 0
+      int found = -1;
+      for (int top = Lc - 2; top >= 0 && found < 0; top -= COMPOSE_THREADS) {
+        int p = top - (int)threadIdx.x;
+        int hit = -1;
+        if (p >= 0) {
+          int s0, s1;
+          if (p >= tail_start) s0 = sign_epoch(V, wave + lay[s].wave_off + C.ep_wave_off[tail_e], tail_e, p - tail_koff, tail_tol);
+          else { float v = comp[p]; s0 = v > 0.0f ? 1 : (v < 0.0f ? -1 : 0); }
+          if (p + 1 >= tail_start) s1 = sign_epoch(V, wave + lay[s].wave_off + C.ep_wave_off[tail_e], tail_e, p + 1 - tail_koff, tail_tol);
+          else { float v = comp[p + 1]; s1 = v > 0.0f ? 1 : (v < 0.0f ? -1 : 0); }
+          if (s0 < 0 && s1 > 0) hit = p;
+        }
+        // block max of hit
+        for (int of = 16; of > 0; of >>= 1) hit = max(hit, __shfl_xor_sync(0xffffffffu, hit, of));
+        if ((threadIdx.x & 31) == 0) red_i[threadIdx.x >> 5] = hit;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          int m = -1;
+          for (int i = 0; i < (COMPOSE_THREADS >> 5); i++) m = max(m, red_i[i]);
+          sh_found = m;
+        }
+        __syncthreads();
+        found = sh_found;
+        __syncthreads();
+      }
+      if (found >= 0) {
+        zc1 = found + 1;
+        Lc1 = found + 2;
+        if (threadIdx.x == 0) comp[found + 1] = 0.0f;
+      } else {
+        Lc1 = Lc;
+      }
+    }
+
+    // ---- zc2: first upward zero crossing of the new epoch (findZeroCrossing(ampl2, 1)) ----
+    int zc2 = 0;
+    {
+      int found = -1;
+      for (int base = 0; base <= Ne - 3 && found < 0; base += COMPOSE_THREADS) {
+        int p = base + (int)threadIdx.x;
+        int hit = 0x7fffffff;
+        if (p <= Ne - 3) {
+          int s0 = sign_epoch(V, w2, e, p, tol2);
+          if (s0 < 0) {
+            int s1 = sign_epoch(V, w2, e, p + 1, tol2);
+            if (s1 > 0) hit = p;
+          }
+        }
+        for (int of = 16; of > 0; of >>= 1) hit = min(hit, __shfl_xor_sync(0xffffffffu, hit, of));
+        if ((threadIdx.x & 31) == 0) red_i[threadIdx.x >> 5] = hit;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          int m = 0x7fffffff;
+          for (int i = 0; i < (COMPOSE_THREADS >> 5); i++) m = min(m, red_i[i]);
+          sh_found = (m == 0x7fffffff) ? -1 : m;
+        }
+        __syncthreads();
+        found = sh_found;
+        __syncthreads();
+      }
+      if (found >= 0) zc2 = found + 1;
+    }
+    const int L2 = Ne - zc2;                 // ampl2 = ampl2[(zc2 + 1):length(ampl2)]
+    const float *a2 = w2 + zc2;
+    int cl = min(crossMax, min(Lc1 - 1, L2 - 1));
+    __syncthreads();
+    int Lnew;
+    if (cl < 2) {
+      for (int i = threadIdx.x; i < L2; i += blockDim.x) comp[Lc1 + i] = a2[i];
+      Lnew = Lc1 + L2;
+    } else {
+      const int idx1 = Lc1 - cl;
+      const double byc = 1.0 / (double)(cl - 1);     // multipl = seq(0, 1, length.out = cl)
+      for (int i = threadIdx.x; i < cl; i += blockDim.x) {
+        double mu = (i == cl - 1) ? 1.0 : (double)i * byc;
+        int ir = cl - 1 - i;
+        double mr = (ir == cl - 1) ? 1.0 : (double)ir * byc;   // rev(multipl)[i]
+        comp[idx1 + i] = (float)(mr * (double)comp[idx1 + i] + mu * (double)a2[i]);
+      }
+      for (int i = cl + threadIdx.x; i < L2; i += blockDim.x) comp[idx1 + i] = a2[i];
+      Lnew = idx1 + L2;
+    }
+    if (threadIdx.x == 0) { C.ep_zc1[e] = zc1; C.ep_zc2[e] = zc2; }
+    tail_e = e;
+    tail_koff = Lnew - Ne;
+    tail_start = Lnew - L2 + max(cl, 0);
+    if (cl < 2) tail_start = Lnew - L2;
+    tail_tol = tol2;
+    Lc = Lnew;
+    __syncthreads();
+  }
+
+  // ---- amplitude envelope (source.R:436-448) ----
+  if (C.use_ampl) {
+    const double *an = anchors + 2 * sp.ampl_off;
+    const int n = sp.ampl_n;
+    __shared__ double tx[SGB_MAX_RW_KNOTS], vy[SGB_MAX_RW_KNOTS], cb[SGB_MAX_RW_KNOTS],
+        cc[SGB_MAX_RW_KNOTS], cd[SGB_MAX_RW_KNOTS];
+    if (threadIdx.x == 0) {
+      double tmin = an[0], tmax = an[0];
+      for (int i = 1; i < n; i++) { tmin = fmin(tmin, an[2 * i]); tmax = fmax(tmax, an[2 * i]); }
+      for (int i = 0; i < n; i++) {
+        double v = an[2 * i + 1];
+        if (v < 0.0) v = 0.0;
+        vy[i] = v;
+        tx[i] = (an[2 * i] - tmin) / (tmax - tmin);
+      }
+      if (n >= 3) fmm_coef(n, tx, vy, cb, cc, cd);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < Lc; k += blockDim.x) {
+      double v;
+      if (n == 1) v = vy[0];
+      else if (n == 2) v = r_seq_at(vy[0], vy[1], Lc, k);
+      else { v = r_spline_at(n, tx, vy, cb, cc, cd, Lc, k); if (v < 0.0) v = 0.0; }
+      comp[k] = (float)((double)comp[k] * exp2(v / 10.0));
+    }
+    __syncthreads();
+  }
+
+  // ---- signed maximum (source.R:449: max(waveform), not max|.|) ----
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < Lc; i += blockDim.x) m = fmaxf(m, comp[i]);
+  for (int of = 16; of > 0; of >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, of));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = red[0];
+    for (int i = 1; i < (COMPOSE_THREADS >> 5); i++) v = fmaxf(v, red[i]);
+    C.raw_max = (double)v;
+    C.out_len = Lc;
+  }
+}
+
+// Normalised, faded syllables placed into their bout's `sound` buffer
+// (source.R:449-467 and the concatenation soundgen.R:632-640).  grid: (chunks, S).
+__global__ void __launch_bounds__(256)
+k_place_voiced(const sgb_syllable *__restrict__ syl, int S, const SylCtrl *__restrict__ ctrl,
+               const SylLayout *__restrict__ lay, const SylPlace *__restrict__ place, Pools P,
+               const float *__restrict__ raw, float *__restrict__ sound) {
+  const int s = blockIdx.y;
+  const SylCtrl &C = ctrl[s];
+  const sgb_syllable &sp = syl[s];
+  const int L = place[s].len;
+  float *dst = sound + place[s].dst_off;
+  const float *src = raw + lay[s].raw_off;
+  if (sp.kind == 0 || C.status != SGB_OK) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < L; k += gridDim.x * blockDim.x) dst[k] = 0.0f;
+    return;
+  }
+  if (sp.kind == 2) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < L; k += gridDim.x * blockDim.x) dst[k] = src[k];
+    return;
+  }
+  const double inv_max = C.raw_max;
+  int lf = 0;
+  if (sp.attackLen > 0.0) {
+    lf = (int)floor(sp.attackLen * sp.samplingRate / 1000.0);
+    if (lf < 2) lf = 0;
+    if (lf > L) lf = L;
+  }
+  const bool drift_on = sp.temperature > 0.0;
+  const int64_t o = P.gc_off[s];
+  const int32_t *gcup = P.gcup + o;
+  const double *drift = P.drift + o;
+  const int G = C.nGC;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < L; k += gridDim.x * blockDim.x) {
+    double v = (double)src[k] / inv_max;
+    if (lf > 0) {
+      if (k < lf) v = v * r_seq_at(0.0, 1.0, lf, k);                        // fade-in
+      if (k >= L - lf) v = v * r_seq_at(0.0, 1.0, lf, (L - 1) - k);         // fade-out = rev(fadeIn)
+    }
+    if (drift_on) {
+      // approx(drift, n = L, x = gc_upsampled[-length(gc_upsampled)]) (source.R:460-462)
+      double xv = r_seq_at((double)gcup[0], (double)gcup[G - 1], L, k);
+      int lo = 0, hi = G - 1;
+      while (hi > lo + 1) { int mid = (lo + hi) >> 1; if (xv < (double)gcup[mid]) hi = mid; else lo = mid; }
+      double xi = (double)gcup[lo], xj = (double)gcup[lo + 1];
+      double d = drift[lo] + (drift[lo + 1] - drift[lo]) * ((xv - xi) / (xj - xi));
+      v = v * d;
+    }
+    dst[k] = (float)v;
+  }
+}
+
+void launch_compose(const sgb_syllable *syl, int S, SylCtrl *ctrl, const SylLayout *lay, const Pools &P,
+                    const double *amp, const float *wave, float *raw, const double *anchors,
+                    const double *pitch_pool, cudaStream_t st) {
+  if (S <= 0) return;
+  k_compose<<<S, COMPOSE_THREADS, 0, st>>>(syl, S, ctrl, lay, P, amp, wave, raw, anchors, pitch_pool);
+}
+
+void launch_place_voiced(const sgb_syllable *syl, int S, const SylCtrl *ctrl, const SylLayout *lay,
+                         const SylPlace *place, const Pools &P, const float *raw, float *sound,
+                         int chunks, cudaStream_t st) {
+  if (S <= 0) return;
+  dim3 g(chunks, S);
+  k_place_voiced<<<g, 256, 0, st>>>(syl, S, ctrl, lay, place, P, raw, sound);
+}

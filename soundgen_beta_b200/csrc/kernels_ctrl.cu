@@ -1,0 +1,202 @@
+// K0 (control-rate prologue), size scan, K1 work list, K3 (amplitude matrices).
+#include "engine.cuh"
+
+// One CTA per syllable.  Parallel: vibrato, column maxima, row pruning.
+// Sequential (thread 0): glottal cycles, random walks, jitter, drift, epochs,
+// upsampling knots -- R/source.R:206-385.
+__global__ void __launch_bounds__(128)
+k_control(const sgb_syllable *syl, int S, const double *pitch, const double *anchors, const double *z,
+          Pools P, SylCtrl *ctrl) {
+  int s = blockIdx.x;
+  if (s >= S) return;
+  const sgb_syllable sp = syl[s];
+  SylCtrl &C = ctrl[s];
+  __shared__ int sh_status;
+  if (sp.kind != 1) {
+    if (threadIdx.x == 0) {
+      C.status = SGB_OK; C.nGC = 0; C.nEpochs = 0; C.tiles = 0; C.amp_elems = 0; C.wave_elems = 0;
+      C.n_up = 0; C.rows_kept = 0; C.nHarmonics = 0; C.n_jidx = 0; C.z_used = 0; C.use_ampl = 0;
+      C.out_len = (sp.kind == 0) ? sp.silent_len : sp.pitch_len;
+      C.raw_max = 1.0;
+    }
+    return;
+  }
+  SylArrays A = make_arrays(P, sp, s);
+  const double *pin = pitch + sp.pitch_off;
+  for (int i = threadIdx.x; i < sp.pitch_len; i += blockDim.x) A.pitch[i] = ctrl_vibrato(sp, i + 1, pin[i]);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ctrl_sequential(sp, anchors, z, A, C);
+    sh_status = C.status;
+  }
+  __syncthreads();
+  if (sh_status != SGB_OK) return;
+  const int G = C.nGC, nH = C.nHarmonics;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) A.colmax[g] = ctrl_colmax(sp, A, C, g);
+  for (int h = 1 + threadIdx.x; h <= nH; h += blockDim.x) A.rowmap[h - 1] = ctrl_rowkept(sp, A, C, h) ? 1 : 0;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int kept = 0;
+    for (int h = 1; h <= nH; h++) if (A.rowmap[h - 1]) A.rowmap[kept++] = h;
+    C.rows_kept = kept;
+    if (kept < 1) C.status = SGB_ERR_SYNTH;
+    ctrl_sizes(A, C, SYNTH_TILE);
+    if (C.status != SGB_OK) { C.tiles = 0; C.amp_elems = 0; C.wave_elems = 0; }
+  }
+}
+
+// Exclusive prefix sums of the per-syllable scratch sizes (single CTA).
+// totals: [0] amp doubles, [1] wave floats, [2] tiles, [3] raw floats, [4] synth partials,
+//         [5] synth samples (4,5 filled by k_build_tiles), [6] failed syllables
+__device__ inline int64_t raw_cap(const SylCtrl &C) {
+  return (((int64_t)(C.nGC > 0 ? C.n_up + 2 : C.out_len)) + 3) & ~(int64_t)3;
+}
+__global__ void __launch_bounds__(1024)
+k_scan_sizes(const SylCtrl *ctrl, int S, SylLayout *lay, int64_t *totals) {
+  __shared__ int64_t part[5][1024];
+  const int t = threadIdx.x, nt = blockDim.x;
+  const int per = (S + nt - 1) / nt;
+  const int lo = min(S, t * per), hi = min(S, lo + per);
+  int64_t a = 0, w = 0, tl = 0, r = 0, failed = 0;
+  for (int s = lo; s < hi; s++) {
+    const SylCtrl &C = ctrl[s];
+    bool ok = (C.status == SGB_OK);
+    if (!ok) failed++;
+    a += ok ? C.amp_elems : 0; w += ok ? C.wave_elems : 0; tl += ok ? C.tiles : 0;
+    r += raw_cap(C);
+  }
+  part[0][t] = a; part[1][t] = w; part[2][t] = tl; part[3][t] = r; part[4][t] = failed;
+  __syncthreads();
+  if (t < 5) {   // serial scan of <= 1024 partials per quantity: negligible
+    int64_t run = 0;
+    for (int i = 0; i < nt; i++) { int64_t v = part[t][i]; part[t][i] = run; run += v; }
+    totals[t == 4 ? 6 : t] = run;
+  }
+  __syncthreads();
+  a = part[0][t]; w = part[1][t]; tl = part[2][t]; r = part[3][t];
+  for (int s = lo; s < hi; s++) {
+    const SylCtrl &C = ctrl[s];
+    bool ok = (C.status == SGB_OK);
+    lay[s].amp_off = a; lay[s].wave_off = w; lay[s].tile_off = (int32_t)tl; lay[s].raw_off = r;
+    lay[s].pad = 0;
+    a += ok ? C.amp_elems : 0; w += ok ? C.wave_elems : 0; tl += ok ? C.tiles : 0;
+    r += raw_cap(C);
+  }
+}
+
+// K1 work list: one thread per syllable writes its (epoch, k0) tiles; also accumulates the
+// algorithmic work counters (rows x samples) used for the K1 roofline.
+__global__ void k_build_tiles(const SylCtrl *ctrl, int S, const SylLayout *lay, const Pools P,
+                              SynthTile *tiles, int64_t *totals) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  const SylCtrl &C = ctrl[s];
+  if (C.status != SGB_OK || C.nGC == 0) return;
+  const int32_t *gcup = P.gcup + P.gc_off[s];
+  int t = lay[s].tile_off;
+  int64_t partials = 0, samples = 0;
+  for (int e = 0; e < C.nEpochs; e++) {
+    int Ne = gcup[C.ep_end[e]] - gcup[C.ep_start[e] - 1] + 1;
+    for (int k0 = 0; k0 < Ne; k0 += SYNTH_TILE) {
+      SynthTile T; T.syl = s; T.epoch = e; T.k0 = k0; T.pad = 0;
+      tiles[t++] = T;
+    }
+    partials += (int64_t)Ne * C.ep_rows[e];
+    samples += Ne;
+  }
+  atomicAdd((unsigned long long *)&totals[4], (unsigned long long)partials);
+  atomicAdd((unsigned long long *)&totals[5], (unsigned long long)samples);
+}
+
+// K3: dense per-epoch amplitude matrices A[e][g][j] (column per glottal cycle, rows =
+// multiples of f0/(nSubharm+1)), exact doubles: getRolloff + shimmer + getVocalFry
+// (R/sourceSpectrum.R:71-186, R/source.R:348-375, R/subharmonics.R:25-163).
+__global__ void __launch_bounds__(256)
+k_amp(const sgb_syllable *syl, int S, const SylCtrl *ctrl, const SylLayout *lay, Pools P, double *amp) {
+  int s = blockIdx.x;
+  if (s >= S) return;
+  const SylCtrl &C = ctrl[s];
+  if (C.status != SGB_OK || C.nGC == 0) return;
+  const sgb_syllable sp = syl[s];
+  SylArrays A = make_arrays(P, sp, s);
+  double *out = amp + lay[s].amp_off;
+  const int64_t chunk = (C.amp_elems + gridDim.y - 1) / gridDim.y;
+  const int64_t lo = chunk * blockIdx.y, hi = min(C.amp_elems, lo + chunk);
+  for (int64_t idx = lo + threadIdx.x; idx < hi; idx += blockDim.x) {
+    int e = 0;
+    while (e + 1 < C.nEpochs && idx >= C.ep_amp_off[e + 1]) e++;
+    int64_t rel = idx - C.ep_amp_off[e];
+    int rows = C.ep_rows[e];
+    int gi = (int)(rel / rows);
+    int j = (int)(rel % rows) + 1;
+    out[idx] = ampl_exact(sp, A, C, e, j, C.ep_start[e] - 1 + gi);
+  }
+}
+
+// getRolloff as a stand-alone call (R/sourceSpectrum.R:71-186).  Single CTA; out is
+// nHarmonics x nGC column-major with the kept rows compacted to the top; scratch:
+// colmax[nGC] doubles, kept[nHarmonics] ints.
+__global__ void __launch_bounds__(256)
+k_rolloff_api(const double *p, int G, int nH, const double *ro, int n_ro, const double *roct, int n_roct,
+              const double *rk, int n_rk, double rolloffParab, double rolloffParabHarm, double parabCeiling,
+              double baseline, double throwaway, double sr, double *out, int *out_rows, double *colmax,
+              int *kept) {
+  __shared__ int any_oct;
+  if (threadIdx.x == 0) any_oct = 0;
+  __syncthreads();
+  for (int g = threadIdx.x; g < G; g += blockDim.x) if (roct[n_roct == 1 ? 0 : g] != 0.0) any_oct = 1;
+  __syncthreads();
+  const bool ao = any_oct != 0;
+  auto rdb = [&](int h, int g) -> double {
+    double ph = (parabCeiling >= 0.0) ? rint(parabCeiling / p[g]) : rint(rolloffParabHarm);
+    if (ph == 2.0) ph = 3.0;
+    int phi = (int)fmin(ph, (double)nH);
+    double a = -4.0 * rolloffParab / ((ph - 1.0) * (ph - 1.0));
+    double b = -a * (1.0 + ph), c = a * ph;
+    return rolloff_db(h, p[g], ro[n_ro == 1 ? 0 : g], roct[n_roct == 1 ? 0 : g], rk[n_rk == 1 ? 0 : g], ao,
+                      rolloffParab, phi, a, b, c, baseline, throwaway, sr);
+  };
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    double m = -INFINITY;
+    for (int h = 1; h <= nH; h++) m = fmax(m, rdb(h, g));
+    colmax[g] = m;
+  }
+  for (int h = 1 + threadIdx.x; h <= nH; h += blockDim.x) {
+    int k = 0;
+    for (int g = 0; g < G && !k; g++) if (rdb(h, g) > -INFINITY) k = 1;
+    kept[h - 1] = k;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int n = 0;
+    for (int h = 1; h <= nH; h++) if (kept[h - 1]) kept[n++] = h;
+    *out_rows = n;
+    for (int i = n; i < nH; i++) kept[i] = 0;
+  }
+  __syncthreads();
+  const int n = *out_rows;
+  for (int idx = threadIdx.x; idx < nH * G; idx += blockDim.x) {
+    int g = idx / nH, k = idx - g * nH;
+    out[idx] = (k < n) ? exp2((rdb(kept[k], g) - colmax[g]) / 10.0) : 0.0;
+  }
+}
+
+// ---- host launchers (kernels stay private to this translation unit) ----
+void launch_control(const sgb_syllable *syl, int S, const double *pitch, const double *anchors, const double *z,
+                    const Pools &P, SylCtrl *ctrl, SylLayout *lay, int64_t *totals, cudaStream_t st) {
+  k_control<<<S, 128, 0, st>>>(syl, S, pitch, anchors, z, P, ctrl);
+  k_scan_sizes<<<1, 1024, 0, st>>>(ctrl, S, lay, totals);
+}
+void launch_tiles_amp(const sgb_syllable *syl, int S, const SylCtrl *ctrl, const SylLayout *lay, const Pools &P,
+                      SynthTile *tiles, int64_t *totals, double *amp, cudaStream_t st) {
+  k_build_tiles<<<(S + 127) / 128, 128, 0, st>>>(ctrl, S, lay, P, tiles, totals);
+  dim3 g(S, 4);
+  k_amp<<<g, 256, 0, st>>>(syl, S, ctrl, lay, P, amp);
+}
+void launch_rolloff_api(const double *p, int G, int nH, const double *ro, int n_ro, const double *roct, int n_roct,
+                        const double *rk, int n_rk, double rolloffParab, double rolloffParabHarm,
+                        double parabCeiling, double baseline, double throwaway, double sr, double *out,
+                        int *out_rows, double *colmax, int *kept) {
+  k_rolloff_api<<<1, 256>>>(p, G, nH, ro, n_ro, roct, n_roct, rk, n_rk, rolloffParab, rolloffParabHarm, parabCeiling,
+                            baseline, throwaway, sr, out, out_rows, colmax, kept);
+}

@@ -1,0 +1,137 @@
+// K4: spectral envelope -- getSpectralEnvelope (R/sourceSpectrum.R:261-566), the
+// deterministic part: formant tracks -> gamma-density bumps + lip radiation + mouth
+// opening + nasalisation -> 2^(dB/10).  One CTA per (column, instance), FP64.
+#include "engine.cuh"
+#include "contour.cuh"
+
+#define ENV_THREADS 128
+#define ENV_MAXF 32        // formants per filter (incl. nasal pole / zero)
+#define ENV_MAXK 64        // knots after the approx() pre-smoothing
+
+template <typename OutT>
+__global__ void __launch_bounds__(ENV_THREADS)
+k_envelope(const EnvInst *__restrict__ inst, const sgb_envelope *__restrict__ envs,
+           const sgb_formant_ref *__restrict__ fidx, const double *__restrict__ formants,
+           const double *__restrict__ anchors, OutT *__restrict__ out) {
+  const EnvInst I = inst[blockIdx.y];
+  const int c = blockIdx.x;
+  if (c >= I.nc) return;
+  const sgb_envelope E = envs[I.env_id];
+  const int nr = I.nr, nc = I.nc;
+  __shared__ double f_freq[ENV_MAXF], f_amp[ENV_MAXF], f_width[ENV_MAXF];
+  __shared__ double g_shape[ENV_MAXF], g_rate[ENV_MAXF], g_ref[ENV_MAXF], g_amp[ENV_MAXF];
+  __shared__ int nF;
+  __shared__ double mouth_open, mouth_bin;
+  const int F = min(E.n_formants, ENV_MAXF - 2);
+
+  // ---- formant values at column c (sourceSpectrum.R:321-344) ----
+  if ((int)threadIdx.x < F) {
+    const sgb_formant_ref R = fidx[E.formant_off + threadIdx.x];
+    const double *rows = formants + 4 * R.off;
+    double val[3];
+    if (E.tracks_given) {
+      for (int j = 0; j < 3; j++) val[j] = rows[4 * c + 1 + j];
+    } else if (R.n <= 1) {
+      for (int j = 0; j < 3; j++) val[j] = rows[1 + j];
+    } else {
+      int nPoints = 0;
+      for (int f = 0; f < F; f++) nPoints = max(nPoints, fidx[E.formant_off + f].n);
+      int na = (int)ceil((double)nPoints + exp2(E.smoothLinearFactor));
+      if (na > ENV_MAXK) na = ENV_MAXK;
+      int n = min(R.n, ENV_MAXK);
+      double tx[ENV_MAXK], ty[ENV_MAXK], ax[ENV_MAXK], ay[ENV_MAXK], b[ENV_MAXK], cc[ENV_MAXK], d[ENV_MAXK];
+      for (int i = 0; i < n; i++) tx[i] = rows[4 * i];
+      for (int i = 0; i < na; i++) ax[i] = (double)(i + 1);
+      for (int j = 0; j < 3; j++) {
+        for (int i = 0; i < n; i++) ty[i] = rows[4 * i + 1 + j];
+        for (int i = 0; i < na; i++) ay[i] = r_approx_at(n, tx, ty, na, i);   // approx(y, n = na, x = time)
+        fmm_coef(na, ax, ay, b, cc, d);
+        val[j] = r_spline_at(na, ax, ay, b, cc, d, nc, c);                     // spline(., n = nc)
+      }
+    }
+    f_freq[threadIdx.x] = val[0]; f_amp[threadIdx.x] = val[1]; f_width[threadIdx.x] = val[2];
+  }
+  __syncthreads();
+
+  // ---- Hz -> bins, mouth opening, nasalisation (sourceSpectrum.R:417-504) ----
+  if (threadIdx.x == 0) {
+    double mo = 0.5, mb = 1.0;
+    int n = 0;
+    if (F > 0) {
+      const double bin_width = E.samplingRate / 2.0 / (double)nr;
+      if (E.mouth_n > 0) {
+        mo = contour_at(anchors + 2 * E.mouth_off, E.mouth_n, nc, c, 0.0, 1.0);
+        if (mo < E.mouthOpenThres) mo = 0.0;
+        mb = (mo > 0.0) ? 1.0 : 0.0;
+      }
+      double adj = 0.0;
+      if (isfinite(E.vocalTract)) {
+        double adj_hz = (mo - 0.5) * E.speedSound / (4.0 * E.vocalTract);
+        adj = (adj_hz - bin_width / 2.0) / bin_width + 1.0;
+      }
+      for (int f = 0; f < F; f++) {
+        double fr = (f_freq[f] - bin_width / 2.0) / bin_width + 1.0;
+        fr = fr + adj;
+        if (fr < 1.0) fr = 1.0;
+        f_freq[f] = fr;
+        f_width[f] = f_width[f] / bin_width;
+      }
+      n = F;
+      if (mb == 0.0) {   // nasalise: pole + zero, modified f1
+        double f1f = f_freq[0], f1a = f_amp[0], f1w = f_width[0];
+        double pf = (f1f > 550.0 / bin_width) ? f1f - 250.0 / bin_width : f1f + 250.0 / bin_width;
+        f_freq[n] = pf; f_amp[n] = f1a * 2.0 / 3.0; f_width[n] = f1w * 2.0 / 3.0; n++;
+        f_freq[n] = (pf + f1f) / 2.0; f_amp[n] = -f1a * 2.0 / 3.0; f_width[n] = f1w * 2.0 / 3.0; n++;
+        f_amp[0] = f1a * 4.0 / 5.0; f_width[0] = f1w * 5.0 / 4.0;
+      }
+      for (int f = 0; f < n; f++) {   // gamma bumps (sourceSpectrum.R:507-520)
+        double mg = f_freq[f], sdg = f_width[f];
+        if (sdg == 0.0) sdg = 1.0;
+        double shape = (mg * mg) / (sdg * sdg);
+        double rate = mg / (sdg * sdg);
+        // arg-max of dgamma over the integer bins 1..nr
+        double xs = 1.0;
+        if (shape > 1.0) {
+          double mode = (shape - 1.0) / rate;
+          double a = fmin(fmax(floor(mode), 1.0), (double)nr), b = fmin(fmax(ceil(mode), 1.0), (double)nr);
+          double la = (shape - 1.0) * log(a) - rate * a, lb = (shape - 1.0) * log(b) - rate * b;
+          xs = (lb > la) ? b : a;
+        }
+        g_shape[f] = shape; g_rate[f] = rate; g_amp[f] = f_amp[f];
+        g_ref[f] = (shape - 1.0) * log(xs) - rate * xs;
+      }
+    }
+    nF = n; mouth_open = mo; mouth_bin = mb;
+  }
+  __syncthreads();
+
+  const int n = nF;
+  const double boost = exp2(mouth_open * E.openMouthBoost / 10.0);
+  OutT *col = out + I.out_off + (int64_t)c * nr;
+  for (int r = threadIdx.x; r < nr; r += blockDim.x) {
+    double x = (double)(r + 1), lx = log(x);
+    double v = 0.0;
+    for (int f = 0; f < n; f++) {
+      double ld = (g_shape[f] - 1.0) * lx - g_rate[f] * x - g_ref[f];
+      v += exp(ld) * g_amp[f];
+    }
+    v = v * E.formantDep;
+    v = (v + E.rolloffLip * log2(x) * mouth_bin) * boost;
+    col[r] = (OutT)exp2(v / 10.0);
+  }
+}
+
+void launch_envelope_f32(const EnvInst *inst, int n_inst, int max_nc, const sgb_envelope *envs,
+                         const sgb_formant_ref *fidx, const double *formants, const double *anchors,
+                         float *out, cudaStream_t st) {
+  if (n_inst <= 0 || max_nc <= 0) return;
+  dim3 g(max_nc, n_inst);
+  k_envelope<float><<<g, ENV_THREADS, 0, st>>>(inst, envs, fidx, formants, anchors, out);
+}
+void launch_envelope_f64(const EnvInst *inst, int n_inst, int max_nc, const sgb_envelope *envs,
+                         const sgb_formant_ref *fidx, const double *formants, const double *anchors,
+                         double *out, cudaStream_t st) {
+  if (n_inst <= 0 || max_nc <= 0) return;
+  dim3 g(max_nc, n_inst);
+  k_envelope<double><<<g, ENV_THREADS, 0, st>>>(inst, envs, fidx, formants, anchors, out);
+}

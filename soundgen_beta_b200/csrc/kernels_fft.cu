@@ -1,0 +1,354 @@
+// K2: fused STFT -> envelope multiply -> ISTFT overlap-add (R/soundgen.R:743-806 with
+// seewave::stft / istft, seewave.r:7782-7818 and :3447-3487), and
+// K5: noise spectrum -> ISTFT overlap-add (R/source.R:88-124).
+//
+// One CTA walks a run of consecutive frames of one sound.  Two real frames share one
+// complex FFT (A + iB); the FFT is a hand-written shared-memory Stockham autosort with
+// radix-4 / radix-2 register butterflies and a table-driven generic radix for the odd
+// factors soundgen's window sizes need (3, 5, 19, 29, or any prime after the clamp at
+// soundgen.R:743).  Frame inputs are staged by TMA bulk copies (cp.async.bulk +
+// mbarrier) into a double buffer while the previous pair is transformed; the weighted
+// overlap-add lives in a shared-memory ring and every output sample is written once.
+#include "engine.cuh"
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                 " selp.b32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+  }
+}
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+
+// One Stockham pass (decimation in frequency): N points, stride s (product of the
+// radices already done), radix r.  DIR = -1 forward, +1 inverse (conjugated twiddles).
+template <int DIR>
+__device__ void fft_pass(const float2 *__restrict__ x, float2 *__restrict__ y, int N, int s, int r,
+                         const float2 *__restrict__ tw) {
+  const int nb = N / r;             // butterflies
+  const int m = nb / s;             // N / (s * r)
+  if (r == 4) {
+    for (int b = threadIdx.x; b < nb; b += FFT_THREADS) {
+      int p = b / s, q = b - p * s;
+      const float2 *xi = x + q + s * p;
+      float2 a0 = xi[0], a1 = xi[s * m], a2 = xi[2 * s * m], a3 = xi[3 * s * m];
+      float2 t0 = make_float2(a0.x + a2.x, a0.y + a2.y), t1 = make_float2(a0.x - a2.x, a0.y - a2.y);
+      float2 t2 = make_float2(a1.x + a3.x, a1.y + a3.y), t3 = make_float2(a1.x - a3.x, a1.y - a3.y);
+      // forward: b1 = t1 - i t3, b3 = t1 + i t3 ; inverse swaps them
+      float2 mi = (DIR < 0) ? make_float2(t3.y, -t3.x) : make_float2(-t3.y, t3.x);   // (-i or +i) * t3
+      float2 b0 = make_float2(t0.x + t2.x, t0.y + t2.y);
+      float2 b2 = make_float2(t0.x - t2.x, t0.y - t2.y);
+      float2 b1 = make_float2(t1.x + mi.x, t1.y + mi.y);
+      float2 b3 = make_float2(t1.x - mi.x, t1.y - mi.y);
+      float2 *yo = y + q + s * 4 * p;
+      int ti = p * s;
+      float2 w1 = tw[ti], w2 = tw[2 * ti], w3 = tw[3 * ti];
+      if (DIR > 0) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
+      yo[0] = b0; yo[s] = cmul(b1, w1); yo[2 * s] = cmul(b2, w2); yo[3 * s] = cmul(b3, w3);
+    }
+  } else if (r == 2) {
+    for (int b = threadIdx.x; b < nb; b += FFT_THREADS) {
+      int p = b / s, q = b - p * s;
+      float2 a0 = x[q + s * p], a1 = x[q + s * (p + m)];
+      float2 w1 = tw[p * s];
+      if (DIR > 0) w1.y = -w1.y;
+      y[q + s * 2 * p] = make_float2(a0.x + a1.x, a0.y + a1.y);
+      y[q + s * (2 * p + 1)] = cmul(make_float2(a0.x - a1.x, a0.y - a1.y), w1);
+    }
+  } else {
+    // generic radix: one output per work item, omega_r^(jk) looked up in the N-point table
+    const int wstep = N / r;
+    for (int idx = threadIdx.x; idx < N; idx += FFT_THREADS) {
+      int j = idx / nb, b = idx - j * nb;
+      int p = b / s, q = b - p * s;
+      const float2 *xi = x + q + s * p;
+      const int sm = s * m;
+      float2 acc = xi[0];
+      int t = 0;
+      const int st = j * wstep;
+      for (int k = 1; k < r; k++) {
+        t += st;
+        if (t >= N) t -= N;
+        float2 w = tw[t];
+        if (DIR > 0) w.y = -w.y;
+        float2 a = xi[k * sm];
+        acc.x = fmaf(a.x, w.x, fmaf(-a.y, w.y, acc.x));
+        acc.y = fmaf(a.x, w.y, fmaf(a.y, w.x, acc.y));
+      }
+      float2 w2 = tw[p * j * s];
+      if (DIR > 0) w2.y = -w2.y;
+      y[q + s * (r * p + j)] = cmul(acc, w2);
+    }
+  }
+}
+
+// full transform; returns the buffer holding the result
+template <int DIR>
+__device__ float2 *fft_run(float2 *a, float2 *b, const FftPlan &pl, const float2 *tw) {
+  int s = 1;
+  float2 *src = a, *dst = b;
+  for (int i = 0; i < pl.npass; i++) {
+    int r = pl.radix[i];
+    fft_pass<DIR>(src, dst, pl.n, s, r, tw);
+    __syncthreads();
+    s *= r;
+    float2 *t = src; src = dst; dst = t;
+  }
+  return src;
+}
+
+__device__ __forceinline__ int frame_in_start(const FftPlan &pl, int k) {   // 0-based
+  return (int)floor(1.0 + (double)k * pl.h_in) - 1;
+}
+__device__ __forceinline__ int frame_out_start(const FftPlan &pl, int k) {
+  return (int)floor((double)k * pl.h_out + 1.0) - 1;
+}
+
+// MODE 0: filter (K2).  MODE 1: noise (K5), UT = uniform dtype.
+template <int MODE, typename UT>
+__global__ void __launch_bounds__(FFT_THREADS)
+k_stft(const FftSeg *__restrict__ segs, const FftJob *__restrict__ jobs, const FftPlan *__restrict__ plans,
+       const float2 *__restrict__ twpool, const float *__restrict__ winpool,
+       const float *__restrict__ in_f, const UT *__restrict__ in_u, const float *__restrict__ envpool,
+       float *__restrict__ outpool, int *__restrict__ maxpool) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ uint64_t bars[2];
+  __shared__ float red[FFT_THREADS / 32];
+
+  const FftSeg sg = segs[blockIdx.x];
+  const FftJob jb = jobs[sg.job];
+  const FftPlan pl = plans[jb.plan];
+  const int N = pl.n, nr = N / 2;
+  const int hceil = (int)ceil(pl.h_out) + 2;
+  const int ring = N + 2 * hceil + 4;
+  const int stage_len = (N + (int)ceil(pl.h_in) + 12) & ~3;     // floats per staging buffer
+
+  float2 *bufA = reinterpret_cast<float2 *>(smem_raw);
+  float2 *bufB = bufA + N;
+  float2 *tw = bufB + N;
+  float *ola = reinterpret_cast<float *>(tw + N);
+  float *stage0 = ola + ((ring + 3) & ~3);
+  float *stage1 = stage0 + stage_len;
+  float *vec = stage1 + ((MODE == 0) ? stage_len : 0);           // noise: rolloff vector [nr]
+
+  const float2 *twg = twpool + pl.tw_off;
+  const float *wa = winpool + pl.wa_off;
+  const float *ws = winpool + pl.ws_off;
+  for (int i = threadIdx.x; i < N; i += FFT_THREADS) tw[i] = twg[i];
+  for (int i = threadIdx.x; i < ring; i += FFT_THREADS) ola[i] = 0.0f;
+  if (MODE == 1) {
+    // rolloff vector 2^(rolloffNoise/10 * log2(1:nr)) (source.R:103-105)
+    for (int i = threadIdx.x; i < nr; i += FFT_THREADS)
+      vec[i] = (float)exp2(jb.rolloffNoise / 10.0 * log2((double)(i + 1)));
+  }
+  if (MODE == 0 && threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int nwarm = (int)ceil((double)N / pl.h_out) - 1;
+  const int kstart = max(0, sg.ka - nwarm);
+  const int flush_lo = (sg.ka == 0) ? 0 : frame_out_start(pl, sg.ka);
+  const int flush_hi = (sg.kb >= jb.nc) ? jb.xlen : frame_out_start(pl, sg.kb);
+  int flushed = frame_out_start(pl, kstart);      // ring position accounted so far
+  if (sg.ka == 0) flushed = 0;
+  const float *src_f = (MODE == 0) ? (in_f + jb.in_off) : nullptr;
+  float vmax = -INFINITY;
+
+  // TMA prefetch of the first pair
+  uint32_t phase[2] = {0u, 0u};
+  auto issue_load = [&](int k, int buf) {
+    // frames k, k+1 need input [s_k, s_{k+1} + N)
+    int sA = frame_in_start(pl, k);
+    int kB = min(k + 1, jb.nc - 1);
+    int sB = frame_in_start(pl, kB);
+    int a0 = sA & ~3;
+    int cnt = ((sB + N - a0) + 3) & ~3;
+    if (cnt > stage_len) cnt = stage_len;
+    uint32_t bytes = (uint32_t)cnt * 4u;
+    mbar_expect_tx(&bars[buf], bytes);
+    tma_load_1d(buf ? stage1 : stage0, src_f + a0, bytes, &bars[buf]);
+  };
+  if (MODE == 0 && threadIdx.x == 0 && kstart < sg.kb) issue_load(kstart, 0);
+
+  int cur = 0;
+  for (int k = kstart; k < sg.kb; k += 2) {
+    const bool hasB = (k + 1 < sg.kb) && (k + 1 < jb.nc);
+    float2 *spec;
+    if (MODE == 0) {
+      // ---- wait for the staged input, prefetch the next pair ----
+      mbar_wait(&bars[cur], phase[cur]);
+      phase[cur] ^= 1u;
+      if (threadIdx.x == 0 && k + 2 < sg.kb) issue_load(k + 2, cur ^ 1);
+      const float *st = cur ? stage1 : stage0;
+      const int sA = frame_in_start(pl, k);
+      const int a0 = sA & ~3;
+      const int offA = sA - a0;
+      const int offB = hasB ? (frame_in_start(pl, k + 1) - a0) : 0;
+      for (int i = threadIdx.x; i < N; i += FFT_THREADS) {
+        float wv = wa[i];
+        float xa = st[offA + i] * wv;
+        float xb = hasB ? st[offB + i] * wv : 0.0f;
+        bufA[i] = make_float2(xa, xb);
+      }
+      __syncthreads();
+      // all generic-proxy reads of this staging buffer are done: make it safe for the next TMA write
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      float2 *Z = fft_run<-1>(bufA, bufB, pl, tw);
+      // ---- split the two spectra, multiply by the envelope, rebuild Hermitian halves ----
+      const float *eA = envpool + jb.env_off + (int64_t)((jb.nint > 1) ? k : 0) * nr;
+      const float *eB = envpool + jb.env_off + (int64_t)((jb.nint > 1 && hasB) ? (k + 1) : 0) * nr;
+      for (int kk = threadIdx.x; kk < nr; kk += FFT_THREADS) {
+        if (kk == 0) {
+          float2 z0 = Z[0];
+          Z[0] = make_float2(eA[0] * z0.x, eB[0] * z0.y);
+        } else {
+          float2 zk = Z[kk], zm = Z[N - kk];
+          // XA = (zk + conj(zm))/2 ; XB = (zk - conj(zm))/(2i)
+          float2 XA = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+          float2 XB = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
+          float ea = eA[kk], eb = eB[kk];
+          float2 FA = make_float2(ea * XA.x, ea * XA.y), FB = make_float2(eb * XB.x, eb * XB.y);
+          Z[kk] = make_float2(FA.x - FB.y, FA.y + FB.x);            // FA + i FB
+          Z[N - kk] = make_float2(FA.x + FB.y, FB.x - FA.y);        // conj(FA) + i conj(FB)
+          if (kk == nr - 1) Z[nr] = make_float2(FA.x, FB.x);        // Nyquist := Re(last bin) (seewave.r:3474)
+        }
+      }
+      __syncthreads();
+      spec = Z;
+    } else {
+      // ---- noise: real, zero-phase spectrum u * filter (source.R:111-114) ----
+      const UT *uA = in_u + jb.in_off + (int64_t)k * nr;
+      const UT *uB = in_u + jb.in_off + (int64_t)(k + 1) * nr;
+      const float *fA = nullptr, *fB = nullptr;
+      if (jb.env_off >= 0) {
+        // filterRowIdx = round(seq(1, ncol, length.out = nc)) (source.R:99)
+        int cA = (int)rint(r_seq_at(1.0, (double)jb.nint, jb.nc, k)) - 1;
+        int cB = hasB ? (int)rint(r_seq_at(1.0, (double)jb.nint, jb.nc, k + 1)) - 1 : 0;
+        fA = envpool + jb.env_off + (int64_t)cA * nr;
+        fB = envpool + jb.env_off + (int64_t)cB * nr;
+      }
+      for (int kk = threadIdx.x; kk < nr; kk += FFT_THREADS) {
+        float ro = vec[kk];
+        float va = (float)uA[kk] * ro * (fA ? fA[kk] : 1.0f);
+        float vb = hasB ? (float)uB[kk] * ro * (fB ? fB[kk] : 1.0f) : 0.0f;
+        float2 v = make_float2(va, vb);
+        bufA[kk] = v;
+        if (kk > 0) bufA[N - kk] = v;
+        if (kk == nr - 1) bufA[nr] = v;
+      }
+      __syncthreads();
+      spec = bufA;
+    }
+    float2 *other = (spec == bufA) ? bufB : bufA;
+    float2 *Y = fft_run<+1>(spec, other, pl, tw);
+
+    // ---- weighted overlap-add into the ring (frame A, then frame B) ----
+    const int oA = frame_out_start(pl, k);
+    for (int i = threadIdx.x; i < N; i += FFT_THREADS) {
+      int slot = (oA + i) % ring;
+      ola[slot] += Y[i].x * ws[i];
+    }
+    __syncthreads();
+    if (hasB) {
+      const int oB = frame_out_start(pl, k + 1);
+      for (int i = threadIdx.x; i < N; i += FFT_THREADS) {
+        int slot = (oB + i) % ring;
+        ola[slot] += Y[i].y * ws[i];
+      }
+      __syncthreads();
+    }
+    // ---- samples before the next frame's start are final: write them out once ----
+    int knext = k + 2;
+    int done_to = (knext < sg.kb) ? frame_out_start(pl, knext) : ((sg.kb >= jb.nc) ? jb.xlen : frame_out_start(pl, sg.kb));
+    if (knext >= sg.kb && sg.kb < jb.nc) done_to = flush_hi;
+    for (int t = flushed + threadIdx.x; t < done_to; t += FFT_THREADS) {
+      int slot = t % ring;
+      float v = ola[slot];
+      ola[slot] = 0.0f;
+      if (t >= flush_lo && t < flush_hi) {
+        int oi = t - jb.shift;
+        if (oi >= 0 && oi < jb.out_len) {
+          outpool[jb.out_off + oi] = v;
+          vmax = fmaxf(vmax, v);
+        }
+      }
+    }
+    flushed = max(flushed, done_to);
+    __syncthreads();
+    cur ^= 1;
+  }
+
+  // ---- signed maximum of what this CTA emitted ----
+  for (int of = 16; of > 0; of >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, of));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = vmax;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = red[0];
+    for (int i = 1; i < FFT_THREADS / 32; i++) v = fmaxf(v, red[i]);
+    if (v > -INFINITY) atomicMax(&maxpool[jb.max_slot], float_to_ordered(v));
+  }
+}
+
+size_t stft_smem_bytes(int n, double h_in, double h_out, int mode) {
+  int hceil = (int)ceil(h_out) + 2;
+  int ring = n + 2 * hceil + 4;
+  int stage_len = (n + (int)ceil(h_in) + 12) & ~3;
+  size_t floats = (size_t)6 * n + ((ring + 3) & ~3) + (mode == 0 ? 2 * (size_t)stage_len : (size_t)stage_len + n / 2 + 4);
+  return floats * 4 + 64;
+}
+
+static size_t attr_smem[3] = {0, 0, 0};
+
+template <typename K>
+static cudaError_t ensure_smem(K kf, int slot, size_t smem) {
+  if (smem <= 48 * 1024 || smem <= attr_smem[slot]) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) attr_smem[slot] = smem;
+  return e;
+}
+
+cudaError_t launch_stft(int mode, int u_is_float, const FftSeg *segs, int n_segs, const FftJob *jobs,
+                        const FftPlan *plans, const float2 *tw, const float *win, const float *in_f,
+                        const void *in_u, const float *env, float *out, int *maxpool, size_t smem,
+                        cudaStream_t st) {
+  if (n_segs <= 0) return cudaSuccess;
+  cudaError_t e = cudaSuccess;
+  if (mode == 0) {
+    auto kf = k_stft<0, float>;
+    if ((e = ensure_smem(kf, 0, smem)) != cudaSuccess) return e;
+    kf<<<n_segs, FFT_THREADS, smem, st>>>(segs, jobs, plans, tw, win, in_f, nullptr, env, out, maxpool);
+  } else if (u_is_float) {
+    auto kf = k_stft<1, float>;
+    if ((e = ensure_smem(kf, 1, smem)) != cudaSuccess) return e;
+    kf<<<n_segs, FFT_THREADS, smem, st>>>(segs, jobs, plans, tw, win, nullptr, (const float *)in_u, env, out, maxpool);
+  } else {
+    auto kf = k_stft<1, double>;
+    if ((e = ensure_smem(kf, 2, smem)) != cudaSuccess) return e;
+    kf<<<n_segs, FFT_THREADS, smem, st>>>(segs, jobs, plans, tw, win, nullptr, (const double *)in_u, env, out, maxpool);
+  }
+  return cudaGetLastError();
+}
