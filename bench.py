@@ -1,0 +1,287 @@
+#!/usr/bin/env python
+"""Benchmark of the soundgen source-filter synthesis path on B200.
+
+  python bench.py --gpus N --steps K --warmup W [--config 3] [--batch B]
+  python bench.py --impl reference ...      (the reference algorithm on the host cores)
+
+A "step" is one pass of the whole hot path (control stage, amplitude matrices, additive
+synthesis, epoch joining, envelopes, noise, fused STFT filter, mixing) over one batch of
+synthetic soundgen() calls of the chosen BASELINE.json config.  `value` is audio seconds
+synthesised per second with inputs resident in HBM; `e2e` includes the H2D copy of the
+step's inputs from pinned host memory and the D2H read of every waveform.
+One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'audio_seconds_synthesised_per_second'
+UNIT = 'audio-s/s'
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(',')])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        sm, mx, reasons = [], 0.0, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for i, nm in enumerate(names):
+                    if r[3 + i].lower().startswith('active'):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx or None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def oracle_one(kw):
+    """One soundgen() call through the CPU oracle; returns (seconds of audio, samples)."""
+    from oracle import soundgen_oracle as so
+    from oracle.soundgen_call import soundgen as osg
+    kw = dict(kw)
+    z = kw.pop('z', None)
+    u = kw.pop('u', None)
+    rng = so.RStream(z=np.concatenate(z) if z else None, u=np.concatenate(u) if u else None)
+    y = osg(rng=rng, **kw)
+    return y.size / float(kw.get('samplingRate', 16000))
+
+
+def run_reference(args, rank, world):
+    """The reference algorithm (CPU restatement under oracle/) on all host cores, bounded sample."""
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    from soundgen_beta_b200 import workloads
+    cores = os.cpu_count() or 1
+    per_step = max(cores, 2 * cores if args.config in (1,) else cores)
+    calls = workloads.CONFIGS[args.config](n=per_step) if args.config != 0 else workloads.config0() * per_step
+    with mp.Pool(cores) as pool:
+        for _ in range(args.warmup):
+            pool.map(oracle_one, calls[:cores])
+        t0 = time.perf_counter()
+        audio = 0.0
+        for _ in range(args.steps):
+            audio += sum(pool.map(oracle_one, calls))
+        dt = time.perf_counter() - t0
+    val = audio / dt
+    line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic', 'gpu_launches': 0,
+            'config': {'workload': workloads.NAMES[args.config], 'calls_per_step': len(calls)},
+            'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                             'sample': '%d calls of %s per step (numpy restatement of the R reference; '
+                                       'R itself is not installed)' % (len(calls), workloads.NAMES[args.config])},
+            'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200')
+    ap.add_argument('--config', type=int, default=3)
+    ap.add_argument('--batch', type=int, default=0, help='calls per GPU per step (default: the config size)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    rank, world, local = env_int('RANK', 0), env_int('WORLD_SIZE', 1), env_int('LOCAL_RANK', 0)
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+
+    import __graft_entry__ as ge
+    ge.build()
+    import soundgen_beta_b200 as sg
+    from soundgen_beta_b200 import _abi, workloads
+    L = _abi.load()
+    if L.sgb_device_count() < 1:
+        raise SystemExit('bench.py: no CUDA device (the product path has no CPU fallback)')
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    assert L.sgb_set_device(local) == 0
+
+    sizes = {0: 1, 1: 1024, 2: 4096, 3: 8192}
+    n = args.batch or sizes[args.config]
+    gen = workloads.CONFIGS[args.config]
+    calls = gen(n=n, seed=20260000 + args.config + 1000 * rank) if args.config != 0 else workloads.config0()
+    sr = workloads.SAMPLING_RATE[args.config]
+    bb = sg.BatchBuilder(u_dtype=np.float32)   # uniforms travel as float32 (halves the PCIe bytes)
+    for kw in calls:
+        bb.add_soundgen(**kw)
+    desc = bb.build()
+    for k in ('pitch', 'anchors', 'formants', 'z', 'u', 'pre'):   # pin the host pools
+        a = desc._keep[k]
+        if a.size:
+            L.sgb_pin(a.ctypes.data, a.nbytes)
+    bt = sg.Batch()
+    bt.upload(desc)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    # ---- warm-up (also sizes the device pools) ----
+    info = None
+    for _ in range(max(args.warmup, 1)):
+        info = bt.run()
+    lens = bt.lengths()
+    audio_s = float(lens.sum()) / sr
+    out = np.zeros(int(lens.sum()), dtype=np.float32)
+    L.sgb_pin(out.ctypes.data, out.nbytes)
+    bt.fetch(np.float32, out=out)
+
+    # ---- timed: inputs resident in HBM ----
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    barrier()
+    stage_ms = np.zeros(len(_abi.T_NAMES))
+    t0 = time.perf_counter()
+    launches = 0
+    for _ in range(args.steps):
+        info = bt.run()   # ends with a stream synchronise
+        stage_ms += np.array(list(info.ms))
+        launches += info.kernel_launches
+    barrier()
+    dt = time.perf_counter() - t0
+    # ---- timed: end to end through the public batch API (H2D + run + D2H) ----
+    barrier()
+    t1 = time.perf_counter()
+    for _ in range(args.steps):
+        bt.upload(desc)
+        bt.run()
+        bt.fetch(np.float32, out=out)
+    barrier()
+    dt_e2e = time.perf_counter() - t1
+    clocks = sampler.stop()
+    stage_ms /= args.steps
+
+    if dist is not None:
+        import torch
+        t = torch.tensor([dt, dt_e2e, audio_s], dtype=torch.float64, device='cuda')
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        dt, dt_e2e = float(tmax[0]), float(tmax[1])
+        audio_total = float(tsum[2])
+    else:
+        audio_total = audio_s
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    value = audio_total * args.steps / dt
+    e2e = audio_total * args.steps / dt_e2e
+    # ---- roofline of the dominant kernel (K1 additive synthesis: FP32-pipe bound) ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    import ctypes
+    fp32 = ctypes.c_double(0)
+    L.sgb_measure_fp32_peak(ctypes.byref(fp32))
+    ms_synth = float(stage_ms[_abi.T_NAMES.index('synth')])
+    ms_filter = float(stage_ms[_abi.T_NAMES.index('filter')])
+    ms_noise = float(stage_ms[_abi.T_NAMES.index('noise')])
+    roofline = None
+    if ms_synth > 0 and info.synth_partials > 0:
+        ach = 6.0 * info.synth_partials / (ms_synth * 1e-3) / 1e12
+        roofline = {'kernel': 'k_synth', 'bound': 'fp32', 'achieved': ach, 'peak': fp32.value,
+                    'unit': 'TFLOP/s', 'frac': ach / fp32.value if fp32.value else None, 'traffic': None,
+                    'peak_source': 'measured in this run: sgb_measure_fp32_peak (FFMA2 chains)',
+                    'algorithmic': '6 flop per partial-sample x %d partial-samples per launch' % info.synth_partials}
+    hbm = peaks.get('hbm_gbs', 6650.0)
+    roof_filter = None
+    if ms_filter > 0 and info.filter_samples > 0:
+        ach = 8.0 * info.filter_samples / (ms_filter * 1e-3) / 1e9
+        roof_filter = {'kernel': 'k_stft<filter>', 'bound': 'hbm', 'achieved': ach, 'peak': hbm, 'unit': 'GB/s',
+                       'frac': ach / hbm, 'traffic': None,
+                       'peak_source': 'MEASURED_PEAKS.json' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s',
+                       'algorithmic': '8 B per output sample x %d samples per launch' % info.filter_samples}
+    if roofline is None:
+        roofline = roof_filter
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        m = {0: 8, 1: 24, 2: 4, 3: 6}[args.config]
+        sample = (calls * m)[:m]
+        tc = time.perf_counter()
+        a = sum(oracle_one(kw) for kw in sample)
+        tc = time.perf_counter() - tc
+        cpu = {'value': a / tc, 'unit': UNIT, 'cores': 1, 'kind': 'port',
+               'sample': 'first %d calls of the workload, numpy restatement of the R reference '
+                         '(R is not installed on this image)' % len(sample)}
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 (f64 phase / control)', 'data': 'synthetic',
+            'config': {'workload': workloads.NAMES[args.config], 'calls_per_gpu': len(calls),
+                       'audio_seconds_per_gpu_step': audio_s, 'l2': 'inputs and intermediates larger than L2',
+                       'uniforms': 'float32'},
+            'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': int(bb.h2d_bytes()),
+                    'd2h_bytes_per_step': int(out.nbytes), 'ms_per_step': dt_e2e / args.steps * 1e3},
+            'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline,
+            'roofline_filter': roof_filter, 'cpu_baseline': cpu,
+            'stage_ms': {nm: float(v) for nm, v in zip(_abi.T_NAMES, stage_ms)},
+            'failed_calls': int(info.n_failed)}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

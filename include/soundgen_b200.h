@@ -45,6 +45,15 @@ const char *sgb_last_error(void);
 int         sgb_device_count(void);
 int         sgb_set_device(int device);
 
+/* Page-locks / unlocks a caller-owned host buffer so that the library's
+ * cudaMemcpyAsync calls on it are true DMA transfers (optional). */
+int sgb_pin(void *ptr, int64_t bytes);
+int sgb_unpin(void *ptr);
+/* Measures the FP32 FMA throughput of the current device with a dependent-chain
+ * FFMA2 kernel (TFLOP/s, FMA = 2 flop); used as the roofline denominator of the
+ * additive-synthesis kernel, which is bound by the FP32 pipe, not by HBM. */
+int sgb_measure_fp32_peak(double *out_tflops);
+
 /* ------------------------------------------------------------------------- */
 /* Batched whole-path interface: replaces the bout loop of soundgen()         */
 /* (R/soundgen.R:482-849) for many calls at once.                             */

@@ -84,7 +84,8 @@ class SylArtefacts(C.Structure):
                 ('raw_max', f64)]
 
 
-EXPORTS = ['sgb_version', 'sgb_last_error', 'sgb_device_count', 'sgb_set_device',
+EXPORTS = ['sgb_version', 'sgb_last_error', 'sgb_device_count', 'sgb_set_device', 'sgb_pin', 'sgb_unpin',
+           'sgb_measure_fp32_peak',
            'sgb_batch_create', 'sgb_batch_destroy', 'sgb_batch_upload', 'sgb_batch_run',
            'sgb_batch_lengths', 'sgb_batch_fetch_f32', 'sgb_batch_fetch_f64', 'sgb_batch_status',
            'sgb_batch_syllable_len', 'sgb_batch_syllable_fetch', 'sgb_batch_noise_fetch',
@@ -114,6 +115,9 @@ def load():
     L.sgb_last_error.restype = C.c_char_p
     L.sgb_device_count.restype = C.c_int
     L.sgb_set_device.argtypes = [C.c_int]
+    L.sgb_pin.argtypes = [vp, i64]
+    L.sgb_unpin.argtypes = [vp]
+    L.sgb_measure_fp32_peak.argtypes = [C.POINTER(f64)]
     L.sgb_batch_create.argtypes = [C.POINTER(vp)]
     L.sgb_batch_destroy.argtypes = [vp]
     L.sgb_batch_destroy.restype = None

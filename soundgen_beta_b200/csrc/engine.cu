@@ -22,6 +22,7 @@ void launch_tiles_amp(const sgb_syllable *, int, const SylCtrl *, const SylLayou
                       int64_t *, double *, cudaStream_t);
 void launch_rolloff_api(const double *, int, int, const double *, int, const double *, int, const double *, int,
                         double, double, double, double, double, double, double *, int *, double *, int *);
+void launch_fp32_peak(float2 *, int, int, int);
 #define ENV_MAXK_HOST 64
 void launch_synth(const SynthTile *, int, const sgb_syllable *, const SylCtrl *, const SylLayout *, const Pools &,
                   const double *, float *, cudaStream_t);
@@ -153,6 +154,45 @@ int sgb_device_count(void) {
 }
 int sgb_set_device(int device) {
   CK(cudaSetDevice(device));
+  return SGB_OK;
+}
+
+int sgb_pin(void *ptr, int64_t bytes) {
+  if (!ptr || bytes <= 0) return fail(SGB_ERR_INVALID, "bad buffer");
+  CK(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault));
+  return SGB_OK;
+}
+int sgb_unpin(void *ptr) {
+  if (!ptr) return fail(SGB_ERR_INVALID, "bad buffer");
+  CK(cudaHostUnregister(ptr));
+  return SGB_OK;
+}
+int sgb_measure_fp32_peak(double *out_tflops) {
+  if (!out_tflops) return fail(SGB_ERR_INVALID, "null argument");
+  int dev = 0, sms = 0;
+  CK(cudaGetDevice(&dev));
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  DBuf d;
+  CK(d.ensure(sizeof(float2) * 1024));
+  CK(cudaMemset(d.p, 0, sizeof(float2) * 1024));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  const int iters = 4096, blocks = sms * 8, threads = 256;
+  double best = 0.0;
+  for (int rep = 0; rep < 5; rep++) {
+    CK(cudaEventRecord(e0));
+    launch_fp32_peak(d.as<float2>(), iters, blocks, threads);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    // 8 independent FFMA2 chains x 2 lanes x 2 flop per iteration per thread
+    double flop = (double)blocks * threads * (double)iters * 8.0 * 2.0 * 2.0;
+    best = std::max(best, flop / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  d.release();
+  *out_tflops = best;
   return SGB_OK;
 }
 

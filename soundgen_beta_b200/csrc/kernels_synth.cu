@@ -171,3 +171,22 @@ void launch_synth(const SynthTile *tiles, int n_tiles, const sgb_syllable *syl, 
   if (n_tiles <= 0) return;
   k_synth<<<n_tiles, SYNTH_THREADS, 0, st>>>(tiles, syl, ctrl, lay, P, amp, wave);
 }
+
+// FP32 pipe peak: 8 independent FFMA2 dependency chains per thread.
+__global__ void __launch_bounds__(256) k_fp32_peak(float2 *out, int iters) {
+  float2 a[8];
+  const float2 m = make_float2(1.0000001f, 0.9999999f), c = make_float2(1e-9f, -1e-9f);
+#pragma unroll
+  for (int i = 0; i < 8; i++) a[i] = make_float2(1.0f + i + threadIdx.x * 1e-3f, 2.0f + i);
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = __ffma2_rn(a[i], m, c);
+  }
+  float2 s = a[0];
+#pragma unroll
+  for (int i = 1; i < 8; i++) { s.x += a[i].x; s.y += a[i].y; }
+  if (s.x == 123.456f) out[threadIdx.x] = s;   // never true: keeps the chains alive
+}
+void launch_fp32_peak(float2 *out, int iters, int blocks, int threads) {
+  k_fp32_peak<<<blocks, threads>>>(out, iters);
+}
