@@ -339,11 +339,8 @@ class BatchBuilder:
         env_main = self.add_envelope(formants, formantDep=formantDep, rolloffLip=rolloffLip,
                                      mouthAnchors=mouthAnchors, vocalTract=vocalTract,
                                      samplingRate=samplingRate)
-        ag = None
-        if amplAnchorsGlobal is not None and np.sum(amplAnchorsGlobal[1] < -throwaway) > 0:   # :721-724
-            if 3 <= amplAnchorsGlobal[0].size <= 10:
-                raise NotImplementedError('amplAnchorsGlobal with 3-10 anchors use loess in the reference')
-            ag = amplAnchorsGlobal
+        if amplAnchorsGlobal is not None and 3 <= amplAnchorsGlobal[0].size <= 10:
+            raise NotImplementedError('amplAnchorsGlobal with 3-10 anchors use loess in the reference')
         bout0 = len(self.bouts)
         n_sil = int(host.rint(samplingRate / 1000 * addSilence)) if addSilence is not None else 0
         for b in range(repeatBout):   # :482
@@ -406,6 +403,11 @@ class BatchBuilder:
                                    overlap=overlap, env_id=env_n, insertion=int(startIdx[s]),
                                    mix=0 if formantsNoise is None else 1)
                     ui += 1
+            ag = None
+            if amplAnchorsGlobal is not None and np.sum(amplAnchorsGlobal[1] < -throwaway) > 0:   # :721-724
+                # the reference converts the anchors in place, so a later bout sees converted values
+                amplAnchorsGlobal = (amplAnchorsGlobal[0], 2 ** (amplAnchorsGlobal[1] / 10))
+                ag = amplAnchorsGlobal
             lead = n_sil if b == 0 else int(pauseLen * samplingRate / 1000)   # :836-849
             tail = n_sil if b == repeatBout - 1 else 0
             self.add_bout(syl_begin, len(self.syls), noise_begin, len(self.noises), env_main, moving, wl_points,

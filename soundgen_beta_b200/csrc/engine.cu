@@ -19,15 +19,15 @@
 void launch_control(const sgb_syllable *, int, const double *, const double *, const double *, const Pools &,
                     SylCtrl *, SylLayout *, int64_t *, cudaStream_t);
 void launch_tiles_amp(const sgb_syllable *, int, const SylCtrl *, const SylLayout *, const Pools &, SynthTile *,
-                      int64_t *, double *, cudaStream_t);
+                      int64_t *, double *, float2 *, cudaStream_t);
 void launch_rolloff_api(const double *, int, int, const double *, int, const double *, int, const double *, int,
                         double, double, double, double, double, double, double *, int *, double *, int *);
 void launch_fp32_peak(float2 *, int, int, int);
 #define ENV_MAXK_HOST 64
 void launch_synth(const SynthTile *, int, const sgb_syllable *, const SylCtrl *, const SylLayout *, const Pools &,
-                  const double *, float *, cudaStream_t);
+                  const float2 *, float *, int *, cudaStream_t);
 void launch_compose(const sgb_syllable *, int, SylCtrl *, const SylLayout *, const Pools &, const double *,
-                    const float *, float *, const double *, const double *, cudaStream_t);
+                    const float *, float *, const double *, const double *, const int *, cudaStream_t);
 void launch_place_voiced(const sgb_syllable *, int, const SylCtrl *, const SylLayout *, const SylPlace *,
                          const Pools &, const float *, float *, int, cudaStream_t);
 void launch_envelope_f32(const EnvInst *, int, int, const sgb_envelope *, const sgb_formant_ref *, const double *,
@@ -123,9 +123,9 @@ struct sgb_batch {
   int u_is_float = 0;
   // device copies
   DBuf d_bouts, d_syls, d_noises, d_envs, d_frefs, d_pitch, d_anchors, d_formants, d_z, d_u, d_pre;
-  DBuf d_gc_off, d_h_off, d_ctrl, d_lay, d_totals, d_summary, d_tiles;
+  DBuf d_gc_off, d_h_off, d_ctrl, d_lay, d_totals, d_summary, d_tiles, d_epmax;
   DBuf p_pitch_w, p_i32[6], p_f64[19];
-  DBuf d_amp, d_wave, d_raw, d_sound, d_voiced, d_filt, d_noise_raw, d_noise_fin, d_env, d_out, d_out64;
+  DBuf d_amp, d_amp32, d_wave, d_raw, d_sound, d_voiced, d_filt, d_noise_raw, d_noise_fin, d_env, d_out, d_out64;
   DBuf d_bl, d_place, d_nl, d_envinst, d_plans, d_tw, d_win, d_fjobs, d_njobs, d_fsegs, d_nsegs, d_max;
   Pools pools;
   int64_t gc_total = 0, h_total = 0;
@@ -216,7 +216,7 @@ void sgb_batch_destroy(sgb_batch *b) {
   cudaStreamSynchronize(b->st);
   DBuf *all[] = {&b->d_bouts, &b->d_syls, &b->d_noises, &b->d_envs, &b->d_frefs, &b->d_pitch, &b->d_anchors,
                  &b->d_formants, &b->d_z, &b->d_u, &b->d_pre, &b->d_gc_off, &b->d_h_off, &b->d_ctrl, &b->d_lay,
-                 &b->d_totals, &b->d_summary, &b->d_tiles, &b->p_pitch_w, &b->d_amp, &b->d_wave, &b->d_raw,
+                 &b->d_totals, &b->d_summary, &b->d_tiles, &b->d_epmax, &b->p_pitch_w, &b->d_amp, &b->d_amp32, &b->d_wave, &b->d_raw,
                  &b->d_sound, &b->d_voiced, &b->d_filt, &b->d_noise_raw, &b->d_noise_fin, &b->d_env, &b->d_out,
                  &b->d_out64, &b->d_bl, &b->d_place, &b->d_nl, &b->d_envinst, &b->d_plans, &b->d_tw, &b->d_win,
                  &b->d_fjobs, &b->d_njobs, &b->d_fsegs, &b->d_nsegs, &b->d_max};
@@ -362,23 +362,32 @@ int sgb_batch_upload(sgb_batch *b, const sgb_batch_desc *D) {
   CK(b->d_lay.ensure(sizeof(SylLayout) * (size_t)S));
   CK(b->d_totals.ensure(64));
   CK(b->d_summary.ensure(sizeof(SylSummary) * (size_t)S));
+  CK(b->d_epmax.ensure(4 * (size_t)S * SGB_MAX_EPOCHS));
   b->have_desc = true;
   b->have_run = false;
   b->keep_voiced = (D->n_calls <= 64);
   return SGB_OK;
 }
 
-// radices for the Stockham passes: 4s first, then 2, then odd primes ascending
+// radices for the Stockham passes.  Odd factors go first (largest first): the early passes
+// scatter their outputs with stride r, and an odd stride spreads over the shared-memory
+// banks where a power of two would collide; by the time the radix-4 / 2 passes run the
+// stride s is >= 32 and the accesses are contiguous.
 static int plan_radices(int n, int *radix) {
-  int np = 0;
-  while (n % 4 == 0 && np < FFT_MAX_PASS) { radix[np++] = 4; n /= 4; }
-  while (n % 2 == 0 && np < FFT_MAX_PASS) { radix[np++] = 2; n /= 2; }
-  for (int p = 3; n > 1; p += 2) {
-    while (n % p == 0) {
-      if (np >= FFT_MAX_PASS) return -1;
-      radix[np++] = p; n /= p;
+  int np = 0, odd[FFT_MAX_PASS], no = 0;
+  int m = n;
+  while (m % 2 == 0) m /= 2;
+  for (int p = 3; m > 1; p += 2) {
+    while (m % p == 0) {
+      if (no >= FFT_MAX_PASS) return -1;
+      odd[no++] = p; m /= p;
     }
   }
+  for (int i = no - 1; i >= 0; i--) radix[np++] = odd[i];
+  int pw = n;
+  for (int i = 0; i < no; i++) pw /= odd[i];
+  while (pw % 4 == 0) { if (np >= FFT_MAX_PASS) return -1; radix[np++] = 4; pw /= 4; }
+  while (pw % 2 == 0) { if (np >= FFT_MAX_PASS) return -1; radix[np++] = 2; pw /= 2; }
   return np;
 }
 
@@ -486,22 +495,25 @@ int sgb_batch_run(sgb_batch *b, sgb_run_info *info_out) {
   const int64_t amp_total = tot[0], wave_total = tot[1], n_tiles = tot[2], raw_total = tot[3];
   if (n_tiles > 2000000000LL) return fail(SGB_ERR_UNSUPPORTED, "batch too large: %lld synthesis tiles", (long long)n_tiles);
   CK(b->d_amp.ensure(8 * (size_t)std::max<int64_t>(amp_total, 1)));
+  CK(b->d_amp32.ensure(8 * (size_t)std::max<int64_t>(amp_total, 1)));
   CK(b->d_wave.ensure(4 * (size_t)std::max<int64_t>(wave_total, 4)));
   CK(b->d_raw.ensure(4 * (size_t)std::max<int64_t>(raw_total, 4)));
   CK(b->d_tiles.ensure(sizeof(SynthTile) * (size_t)std::max<int64_t>(n_tiles, 1)));
 
   // ---- K3 amplitude matrices ----
-  launch_tiles_amp(d_syl, S, d_ctrl, d_lay, P, b->d_tiles.as<SynthTile>(), d_tot, b->d_amp.as<double>(), st);
+  launch_tiles_amp(d_syl, S, d_ctrl, d_lay, P, b->d_tiles.as<SynthTile>(), d_tot, b->d_amp.as<double>(),
+                   b->d_amp32.as<float2>(), st);
   launches += 2;
   CK(cudaEventRecord(ev[2], st));
   // ---- K1 synthesis ----
-  launch_synth(b->d_tiles.as<SynthTile>(), (int)n_tiles, d_syl, d_ctrl, d_lay, P, b->d_amp.as<double>(),
-               b->d_wave.as<float>(), st);
+  CK(cudaMemsetAsync(b->d_epmax.p, 0, 4 * (size_t)S * SGB_MAX_EPOCHS, st));
+  launch_synth(b->d_tiles.as<SynthTile>(), (int)n_tiles, d_syl, d_ctrl, d_lay, P, b->d_amp32.as<float2>(),
+               b->d_wave.as<float>(), b->d_epmax.as<int>(), st);
   if (n_tiles > 0) launches++;
   CK(cudaEventRecord(ev[3], st));
   // ---- K6 compose ----
   launch_compose(d_syl, S, d_ctrl, d_lay, P, b->d_amp.as<double>(), b->d_wave.as<float>(), b->d_raw.as<float>(),
-                 b->d_anchors.as<double>(), b->d_pitch.as<double>(), st);
+                 b->d_anchors.as<double>(), b->d_pitch.as<double>(), b->d_epmax.as<int>(), st);
   k_summary<<<(S + 255) / 256, 256, 0, st>>>(d_ctrl, S, b->d_summary.as<SylSummary>());
   launches += 2;
   b->summary.resize(S);
@@ -595,7 +607,7 @@ int sgb_batch_run(sgb_batch *b, sgb_run_info *info_out) {
         }
       }
       if (L.bypass) { L.filt_len = L.sound_len; L.nc = 0; L.nint = 0; }
-      sound_total += align4(cur + 8) + (L.bypass ? 0 : L.wl + 16);
+      sound_total += align4(cur + 8 + (L.bypass ? 0 : L.wl + 16));
       if (!L.bypass) {
         L.filt_off = filt_total; filt_total += align4(L.filt_len + 4);
         L.env_off = env_total; env_total += align4((int64_t)(L.wl / 2) * L.nint);

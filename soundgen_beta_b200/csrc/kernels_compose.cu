@@ -22,7 +22,9 @@ struct SylView {
 };
 
 // waveform_epoch[k] (0-based k) exactly as R/source.R:403-409 computes it, in double.
-__device__ double exact_epoch_sample(const SylView &V, int e, int k) {
+// Cooperative: every thread of the CTA calls it with the same (e, k); the rows are split
+// across the threads and the partial sums are combined in a fixed order.
+__device__ double exact_epoch_sample(const SylView &V, int e, int k, double *red) {
   const SylCtrl &C = *V.C;
   const int g_first = C.ep_start[e] - 1, g_lastStart = C.ep_end[e] - 1;
   const int nsub = C.vf_active ? C.ep_nsub[e] : 0;
@@ -51,7 +53,7 @@ __device__ double exact_epoch_sample(const SylView &V, int e, int k) {
   double integr = (V.phi[a] + V.py[a] * (M + 1.0) + V.sb[a] * s1 + V.sc[a] * s2 + V.sd[a] * s3) / V.sr;
   const double *col = V.amp + C.ep_amp_off[e] + (int64_t)lo * J;
   double sum = 0.0;
-  for (int j = 1; j <= J; j++) {
+  for (int j = 1 + threadIdx.x; j <= J; j += blockDim.x) {
     double y0 = col[j - 1], y1 = col[J + j - 1];
     if (y0 == 0.0 && y1 == 0.0) continue;
     double am = y0 + (y1 - y0) * wfrac;
@@ -59,45 +61,33 @@ __device__ double exact_epoch_sample(const SylView &V, int e, int k) {
     x -= floor(x);
     sum += sinpi(2.0 * x) * am;
   }
-  return sum;
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  double tot = 0.0;
+  for (int i = 0; i < (int)(blockDim.x >> 5); i++) tot += red[i];
+  __syncthreads();
+  return tot;
 }
 
-__device__ float block_maxabs(const float *x, int n, float *red) {
-  float m = 0.0f;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(x[i]));
-  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    float v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0f;
-    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    if (threadIdx.x == 0) red[0] = v;
-  }
-  __syncthreads();
-  float r = red[0];
-  __syncthreads();
-  return r;
-}
-
-// sign (-1, 0, +1) of epoch sample k, exact when the float value is within tol of zero
-__device__ int sign_epoch(const SylView &V, const float *w, int e, int k, float tol) {
-  float v = w[k];
-  if (fabsf(v) >= tol) return v > 0.0f ? 1 : -1;
-  double x = exact_epoch_sample(V, e, k);
-  return x > 0.0 ? 1 : (x < 0.0 ? -1 : 0);
+// three-valued sign of a float sample: -1 / +1 when |v| >= tol, 0 = too close to call
+__device__ __forceinline__ int sign3(float v, float tol) {
+  return (fabsf(v) >= tol) ? (v > 0.0f ? 1 : -1) : 0;
 }
 
 __global__ void __launch_bounds__(COMPOSE_THREADS)
 k_compose(const sgb_syllable *__restrict__ syl, int S, SylCtrl *__restrict__ ctrl,
           const SylLayout *__restrict__ lay, Pools P, const double *__restrict__ amp,
           const float *__restrict__ wave, float *__restrict__ raw, const double *__restrict__ anchors,
-          const double *__restrict__ pitch_pool) {
+          const double *__restrict__ pitch_pool, const int *__restrict__ epmax) {
   const int s = blockIdx.x;
   if (s >= S) return;
   SylCtrl &C = ctrl[s];
   const sgb_syllable sp = syl[s];
   float *comp = raw + lay[s].raw_off;
   __shared__ float red[32];
+  __shared__ double redd[32];
   __shared__ int sh_found;
   __shared__ int red_i[32];
 
@@ -125,7 +115,7 @@ k_compose(const sgb_syllable *__restrict__ syl, int S, SylCtrl *__restrict__ ctr
   for (int e = 0; e < C.nEpochs; e++) {
     const float *w2 = wave + lay[s].wave_off + C.ep_wave_off[e];
     const int Ne = V.gcup[C.ep_end[e]] - V.gcup[C.ep_start[e] - 1] + 1;
-    const float tol2 = ZC_REL_TOL * block_maxabs(w2, Ne, red);
+    const float tol2 = ZC_REL_TOL * ordered_to_float(epmax[(int64_t)s * SGB_MAX_EPOCHS + e]);
 
     // ---- zc1: last upward zero crossing of the sound so far (findZeroCrossing(ampl1, len)) ----
     int Lc1;
@@ -134,20 +124,21 @@ k_compose(const sgb_syllable *__restrict__ syl, int S, SylCtrl *__restrict__ ctr
       zc1 = 1; Lc1 = 2;
       if (threadIdx.x == 0) comp[1] = 0.0f;
     } else {
-      // largest p in [0, Lc-2] with comp[p] < 0 && comp[p+1] > 0
+      // largest p in [0, Lc-2] with comp[p] < 0 && comp[p+1] > 0.  Candidates are pairs that are,
+      // or could be (a value within tol of zero), an upward crossing; each candidate is then
+      // settled in FP64.  Only samples of the tail epoch (not yet cross-faded) are re-evaluated.
       int found = -1;
-      for (int top = Lc - 2; top >= 0 && found < 0; top -= COMPOSE_THREADS) {
+      int top = Lc - 2;
+      while (top >= 0 && found < 0) {
         int p = top - (int)threadIdx.x;
         int hit = -1;
         if (p >= 0) {
-          int s0, s1;
-          if (p >= tail_start) s0 = sign_epoch(V, wave + lay[s].wave_off + C.ep_wave_off[tail_e], tail_e, p - tail_koff, tail_tol);
-          else { float v = comp[p]; s0 = v > 0.0f ? 1 : (v < 0.0f ? -1 : 0); }
-          if (p + 1 >= tail_start) s1 = sign_epoch(V, wave + lay[s].wave_off + C.ep_wave_off[tail_e], tail_e, p + 1 - tail_koff, tail_tol);
-          else { float v = comp[p + 1]; s1 = v > 0.0f ? 1 : (v < 0.0f ? -1 : 0); }
-          if (s0 < 0 && s1 > 0) hit = p;
+          float t0 = (p >= tail_start) ? tail_tol : 0.0f, t1 = (p + 1 >= tail_start) ? tail_tol : 0.0f;
+          float v0 = comp[p], v1 = comp[p + 1];
+          bool neg0 = (t0 > 0.0f) ? (sign3(v0, t0) <= 0) : (v0 < 0.0f);
+          bool pos1 = (t1 > 0.0f) ? (sign3(v1, t1) >= 0) : (v1 > 0.0f);
+          if (neg0 && pos1) hit = p;
         }
-        // block max of hit
         for (int of = 16; of > 0; of >>= 1) hit = max(hit, __shfl_xor_sync(0xffffffffu, hit, of));
         if ((threadIdx.x & 31) == 0) red_i[threadIdx.x >> 5] = hit;
         __syncthreads();
@@ -157,8 +148,16 @@ k_compose(const sgb_syllable *__restrict__ syl, int S, SylCtrl *__restrict__ ctr
           sh_found = m;
         }
         __syncthreads();
-        found = sh_found;
+        int cand = sh_found;
         __syncthreads();
+        if (cand < 0) { top -= COMPOSE_THREADS; continue; }
+        float v0 = comp[cand], v1 = comp[cand + 1];
+        bool ok0, ok1;
+        if (cand >= tail_start && fabsf(v0) < tail_tol) ok0 = exact_epoch_sample(V, tail_e, cand - tail_koff, redd) < 0.0;
+        else ok0 = v0 < 0.0f;
+        if (cand + 1 >= tail_start && fabsf(v1) < tail_tol) ok1 = exact_epoch_sample(V, tail_e, cand + 1 - tail_koff, redd) > 0.0;
+        else ok1 = v1 > 0.0f;
+        if (ok0 && ok1) found = cand; else top = cand - 1;
       }
       if (found >= 0) {
         zc1 = found + 1;
@@ -173,15 +172,13 @@ k_compose(const sgb_syllable *__restrict__ syl, int S, SylCtrl *__restrict__ ctr
     int zc2 = 0;
     {
       int found = -1;
-      for (int base = 0; base <= Ne - 3 && found < 0; base += COMPOSE_THREADS) {
+      int base = 0;
+      while (base <= Ne - 3 && found < 0) {
         int p = base + (int)threadIdx.x;
         int hit = 0x7fffffff;
         if (p <= Ne - 3) {
-          int s0 = sign_epoch(V, w2, e, p, tol2);
-          if (s0 < 0) {
-            int s1 = sign_epoch(V, w2, e, p + 1, tol2);
-            if (s1 > 0) hit = p;
-          }
+          int s0 = sign3(w2[p], tol2), s1 = sign3(w2[p + 1], tol2);
+          if (s0 <= 0 && s1 >= 0) hit = p;
         }
         for (int of = 16; of > 0; of >>= 1) hit = min(hit, __shfl_xor_sync(0xffffffffu, hit, of));
         if ((threadIdx.x & 31) == 0) red_i[threadIdx.x >> 5] = hit;
@@ -192,8 +189,13 @@ k_compose(const sgb_syllable *__restrict__ syl, int S, SylCtrl *__restrict__ ctr
           sh_found = (m == 0x7fffffff) ? -1 : m;
         }
         __syncthreads();
-        found = sh_found;
+        int cand = sh_found;
         __syncthreads();
+        if (cand < 0) { base += COMPOSE_THREADS; continue; }
+        float v0 = w2[cand], v1 = w2[cand + 1];
+        bool ok0 = (fabsf(v0) < tol2) ? (exact_epoch_sample(V, e, cand, redd) < 0.0) : (v0 < 0.0f);
+        bool ok1 = (fabsf(v1) < tol2) ? (exact_epoch_sample(V, e, cand + 1, redd) > 0.0) : (v1 > 0.0f);
+        if (ok0 && ok1) found = cand; else base = cand + 1;
       }
       if (found >= 0) zc2 = found + 1;
     }
@@ -322,9 +324,9 @@ k_place_voiced(const sgb_syllable *__restrict__ syl, int S, const SylCtrl *__res
 
 void launch_compose(const sgb_syllable *syl, int S, SylCtrl *ctrl, const SylLayout *lay, const Pools &P,
                     const double *amp, const float *wave, float *raw, const double *anchors,
-                    const double *pitch_pool, cudaStream_t st) {
+                    const double *pitch_pool, const int *epmax, cudaStream_t st) {
   if (S <= 0) return;
-  k_compose<<<S, COMPOSE_THREADS, 0, st>>>(syl, S, ctrl, lay, P, amp, wave, raw, anchors, pitch_pool);
+  k_compose<<<S, COMPOSE_THREADS, 0, st>>>(syl, S, ctrl, lay, P, amp, wave, raw, anchors, pitch_pool, epmax);
 }
 
 void launch_place_voiced(const sgb_syllable *syl, int S, const SylCtrl *ctrl, const SylLayout *lay,

@@ -111,8 +111,17 @@ __global__ void k_build_tiles(const SylCtrl *ctrl, int S, const SylLayout *lay, 
 // K3: dense per-epoch amplitude matrices A[e][g][j] (column per glottal cycle, rows =
 // multiples of f0/(nSubharm+1)), exact doubles: getRolloff + shimmer + getVocalFry
 // (R/sourceSpectrum.R:71-186, R/source.R:348-375, R/subharmonics.R:25-163).
+// grid (S, chunks of glottal cycles).  Per epoch the CTA tabulates what the reference's
+// quirk makes column-independent -- the f-harmonic amplitudes of the epoch's FIRST cycle
+// (subharmonics.R:76-77) -- and the per-(s, cycle) sideband multipliers, so that an f row
+// costs one exp2 and a g row two FMAs.
+#define AMP_MAXH 1024
+#define AMP_MAXS 16
+#define AMP_CG 32
+#define AMP_RPT 8
 __global__ void __launch_bounds__(256)
-k_amp(const sgb_syllable *syl, int S, const SylCtrl *ctrl, const SylLayout *lay, Pools P, double *amp) {
+k_amp(const sgb_syllable *syl, int S, const SylCtrl *ctrl, const SylLayout *lay, Pools P, double *amp,
+      float2 *amp32) {
   int s = blockIdx.x;
   if (s >= S) return;
   const SylCtrl &C = ctrl[s];
@@ -120,16 +129,81 @@ k_amp(const sgb_syllable *syl, int S, const SylCtrl *ctrl, const SylLayout *lay,
   const sgb_syllable sp = syl[s];
   SylArrays A = make_arrays(P, sp, s);
   double *out = amp + lay[s].amp_off;
-  const int64_t chunk = (C.amp_elems + gridDim.y - 1) / gridDim.y;
-  const int64_t lo = chunk * blockIdx.y, hi = min(C.amp_elems, lo + chunk);
-  for (int64_t idx = lo + threadIdx.x; idx < hi; idx += blockDim.x) {
-    int e = 0;
-    while (e + 1 < C.nEpochs && idx >= C.ep_amp_off[e + 1]) e++;
-    int64_t rel = idx - C.ep_amp_off[e];
-    int rows = C.ep_rows[e];
-    int gi = (int)(rel / rows);
-    int j = (int)(rel % rows) + 1;
-    out[idx] = ampl_exact(sp, A, C, e, j, C.ep_start[e] - 1 + gi);
+  float2 *out32 = amp32 + lay[s].amp_off;
+  __shared__ double A0[AMP_MAXH + 2];
+  __shared__ double ML[AMP_MAXS * (AMP_CG + 1)], MU[AMP_MAXS * (AMP_CG + 1)];
+  const int G = C.nGC, Hk = C.rows_kept;
+  const double thr01 = exp2(sp.throwaway / 10.0);
+  for (int c0 = blockIdx.y * AMP_CG; c0 < G; c0 += gridDim.y * AMP_CG) {
+    const int c1 = min(G, c0 + AMP_CG);
+    for (int e = 0; e < C.nEpochs; e++) {
+      const int ga = max(c0, C.ep_start[e] - 1), gb = min(c1, C.ep_end[e]);   // [ga, gb) 0-based
+      if (ga >= gb) continue;
+      const int gx = min(gb + 1, C.ep_end[e]);     // one extra column for the differences
+      const int n = C.vf_active ? C.ep_nsub[e] : 0;
+      const int rows = C.ep_rows[e];
+      const int g0 = C.ep_start[e] - 1;
+      double *oe = out + C.ep_amp_off[e];
+      float2 *oe32 = out32 + C.ep_amp_off[e];
+      const bool tabled = (n == 0) || (Hk <= AMP_MAXH && n <= AMP_MAXS);
+      __syncthreads();
+      if (tabled && n > 0) {
+        for (int k = threadIdx.x; k <= Hk + 1; k += blockDim.x) {   // A0[k], k = 0..Hk+1 (ends are 0)
+          double v = 0.0;
+          if (k >= 1 && k <= Hk) {
+            int h = A.rowmap[k - 1];
+            double r = rolloff_db(h, A.ppg[g0], A.ro[g0], A.roct[g0], A.rk[g0], C.any_oct != 0, sp.rolloffParab,
+                                  C.parab_harm, C.parab_a, C.parab_b, C.parab_c, 200.0, sp.throwaway, sp.samplingRate);
+            v = exp2((r - A.colmax[g0]) / 10.0) * A.shimmer[g0];
+          }
+          A0[k] = v;
+        }
+        const int ncol = gx - ga;
+        for (int idx = threadIdx.x; idx < n * ncol; idx += blockDim.x) {
+          int si = idx / ncol, gi = idx - si * ncol;
+          int g = ga + gi, sidx = si + 1;
+          double sw = A.subdep[g];
+          double dl = A.ppg[g] * (double)sidx / (double)(n + 1);
+          double du = A.ppg[g] * (double)(n + 1 - sidx) / (double)(n + 1);
+          double ml = 0.0, mu = 0.0;
+          if (sw != 0.0) { ml = exp(-0.5 * (dl / sw) * (dl / sw)); mu = exp(-0.5 * (du / sw) * (du / sw)); }
+          ML[si * (AMP_CG + 1) + gi] = ml; MU[si * (AMP_CG + 1) + gi] = mu;
+        }
+      }
+      __syncthreads();
+      // each thread owns rows j = rb + tid + i*256 and walks the columns, so that the FP32
+      // {Y_g, Y_{g+1} - Y_g} table K1 consumes falls out of the same pass
+      for (int rb = 0; rb < rows; rb += 256 * AMP_RPT) {
+        double prev[AMP_RPT];
+        for (int g = ga; g < gx; g++) {
+          const int gi = g - ga;
+#pragma unroll
+          for (int i = 0; i < AMP_RPT; i++) {
+            const int j = rb + i * 256 + (int)threadIdx.x + 1;
+            if (j > rows) continue;
+            double v;
+            if (!tabled) {
+              v = ampl_exact(sp, A, C, e, j, g);
+            } else {
+              int k = (n == 0) ? j : j / (n + 1), si = (n == 0) ? 0 : j % (n + 1);
+              if (si == 0) {
+                int h = A.rowmap[k - 1];
+                double r = rolloff_db(h, A.ppg[g], A.ro[g], A.roct[g], A.rk[g], C.any_oct != 0, sp.rolloffParab,
+                                      C.parab_harm, C.parab_a, C.parab_b, C.parab_c, 200.0, sp.throwaway,
+                                      sp.samplingRate);
+                v = exp2((r - A.colmax[g]) / 10.0) * A.shimmer[g];
+              } else {
+                v = A0[k] * ML[(si - 1) * (AMP_CG + 1) + gi] + A0[k + 1] * MU[(si - 1) * (AMP_CG + 1) + gi];
+              }
+              if (n > 0 && v < thr01) v = 0.0;
+            }
+            if (g < gb) oe[(int64_t)(g - g0) * rows + (j - 1)] = v;
+            if (g > ga) oe32[(int64_t)(g - 1 - g0) * rows + (j - 1)] = make_float2((float)prev[i], (float)(v - prev[i]));
+            prev[i] = v;
+          }
+        }
+      }
+    }
   }
 }
 
@@ -188,10 +262,10 @@ void launch_control(const sgb_syllable *syl, int S, const double *pitch, const d
   k_scan_sizes<<<1, 1024, 0, st>>>(ctrl, S, lay, totals);
 }
 void launch_tiles_amp(const sgb_syllable *syl, int S, const SylCtrl *ctrl, const SylLayout *lay, const Pools &P,
-                      SynthTile *tiles, int64_t *totals, double *amp, cudaStream_t st) {
+                      SynthTile *tiles, int64_t *totals, double *amp, float2 *amp32, cudaStream_t st) {
   k_build_tiles<<<(S + 127) / 128, 128, 0, st>>>(ctrl, S, lay, P, tiles, totals);
-  dim3 g(S, 4);
-  k_amp<<<g, 256, 0, st>>>(syl, S, ctrl, lay, P, amp);
+  dim3 g(S, S >= 2048 ? 1 : (S >= 256 ? 4 : 16));
+  k_amp<<<g, 256, 0, st>>>(syl, S, ctrl, lay, P, amp, amp32);
 }
 void launch_rolloff_api(const double *p, int G, int nH, const double *ro, int n_ro, const double *roct, int n_roct,
                         const double *rk, int n_rk, double rolloffParab, double rolloffParabHarm,

@@ -67,6 +67,52 @@ __device__ void fft_pass(const float2 *__restrict__ x, float2 *__restrict__ y, i
       if (DIR > 0) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
       yo[0] = b0; yo[s] = cmul(b1, w1); yo[2 * s] = cmul(b2, w2); yo[3 * s] = cmul(b3, w3);
     }
+  } else if (r == 3) {
+    const float c3 = 0.86602540378443864676f;   // sin(2 pi / 3)
+    for (int b = threadIdx.x; b < nb; b += FFT_THREADS) {
+      int p = b / s, q = b - p * s;
+      const float2 *xi = x + q + s * p;
+      const int sm = s * m;
+      float2 a0 = xi[0], a1 = xi[sm], a2 = xi[2 * sm];
+      float2 t = make_float2(a1.x + a2.x, a1.y + a2.y), u = make_float2(a1.x - a2.x, a1.y - a2.y);
+      float2 mm = make_float2(fmaf(-0.5f, t.x, a0.x), fmaf(-0.5f, t.y, a0.y));
+      // forward: -i * c3 * u ; inverse: +i * c3 * u
+      float2 v = (DIR < 0) ? make_float2(c3 * u.y, -c3 * u.x) : make_float2(-c3 * u.y, c3 * u.x);
+      float2 *yo = y + q + s * 3 * p;
+      int ti = p * s;
+      float2 w1 = tw[ti], w2 = tw[2 * ti];
+      if (DIR > 0) { w1.y = -w1.y; w2.y = -w2.y; }
+      yo[0] = make_float2(a0.x + t.x, a0.y + t.y);
+      yo[s] = cmul(make_float2(mm.x + v.x, mm.y + v.y), w1);
+      yo[2 * s] = cmul(make_float2(mm.x - v.x, mm.y - v.y), w2);
+    }
+  } else if (r == 5) {
+    const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
+    const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
+    for (int b = threadIdx.x; b < nb; b += FFT_THREADS) {
+      int p = b / s, q = b - p * s;
+      const float2 *xi = x + q + s * p;
+      const int sm = s * m;
+      float2 a0 = xi[0], a1 = xi[sm], a2 = xi[2 * sm], a3 = xi[3 * sm], a4 = xi[4 * sm];
+      float2 t1 = make_float2(a1.x + a4.x, a1.y + a4.y), t2 = make_float2(a2.x + a3.x, a2.y + a3.y);
+      float2 t3 = make_float2(a1.x - a4.x, a1.y - a4.y), t4 = make_float2(a2.x - a3.x, a2.y - a3.y);
+      float2 m1 = make_float2(fmaf(c1, t1.x, fmaf(c2, t2.x, a0.x)), fmaf(c1, t1.y, fmaf(c2, t2.y, a0.y)));
+      float2 m2 = make_float2(fmaf(c2, t1.x, fmaf(c1, t2.x, a0.x)), fmaf(c2, t1.y, fmaf(c1, t2.y, a0.y)));
+      float2 n1 = make_float2(fmaf(s1, t3.x, s2 * t4.x), fmaf(s1, t3.y, s2 * t4.y));
+      float2 n2 = make_float2(fmaf(s2, t3.x, -s1 * t4.x), fmaf(s2, t3.y, -s1 * t4.y));
+      // forward: b1 = m1 - i n1, b4 = m1 + i n1, b2 = m2 - i n2, b3 = m2 + i n2 (inverse: conjugate)
+      float2 i1 = (DIR < 0) ? make_float2(n1.y, -n1.x) : make_float2(-n1.y, n1.x);
+      float2 i2 = (DIR < 0) ? make_float2(n2.y, -n2.x) : make_float2(-n2.y, n2.x);
+      float2 *yo = y + q + s * 5 * p;
+      int ti = p * s;
+      float2 w1 = tw[ti], w2 = tw[2 * ti], w3 = tw[3 * ti], w4 = tw[4 * ti];
+      if (DIR > 0) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; w4.y = -w4.y; }
+      yo[0] = make_float2(a0.x + t1.x + t2.x, a0.y + t1.y + t2.y);
+      yo[s] = cmul(make_float2(m1.x + i1.x, m1.y + i1.y), w1);
+      yo[2 * s] = cmul(make_float2(m2.x + i2.x, m2.y + i2.y), w2);
+      yo[3 * s] = cmul(make_float2(m2.x - i2.x, m2.y - i2.y), w3);
+      yo[4 * s] = cmul(make_float2(m1.x - i1.x, m1.y - i1.y), w4);
+    }
   } else if (r == 2) {
     for (int b = threadIdx.x; b < nb; b += FFT_THREADS) {
       int p = b / s, q = b - p * s;
@@ -267,16 +313,18 @@ k_stft(const FftSeg *__restrict__ segs, const FftJob *__restrict__ jobs, const F
     float2 *Y = fft_run<+1>(spec, other, pl, tw);
 
     // ---- weighted overlap-add into the ring (frame A, then frame B) ----
-    const int oA = frame_out_start(pl, k);
+    const int oA = frame_out_start(pl, k) % ring;
     for (int i = threadIdx.x; i < N; i += FFT_THREADS) {
-      int slot = (oA + i) % ring;
+      int slot = oA + i;
+      if (slot >= ring) slot -= ring;
       ola[slot] += Y[i].x * ws[i];
     }
     __syncthreads();
     if (hasB) {
-      const int oB = frame_out_start(pl, k + 1);
+      const int oB = frame_out_start(pl, k + 1) % ring;
       for (int i = threadIdx.x; i < N; i += FFT_THREADS) {
-        int slot = (oB + i) % ring;
+        int slot = oB + i;
+        if (slot >= ring) slot -= ring;
         ola[slot] += Y[i].y * ws[i];
       }
       __syncthreads();
@@ -285,8 +333,10 @@ k_stft(const FftSeg *__restrict__ segs, const FftJob *__restrict__ jobs, const F
     int knext = k + 2;
     int done_to = (knext < sg.kb) ? frame_out_start(pl, knext) : ((sg.kb >= jb.nc) ? jb.xlen : frame_out_start(pl, sg.kb));
     if (knext >= sg.kb && sg.kb < jb.nc) done_to = flush_hi;
+    const int fbase = flushed % ring;
     for (int t = flushed + threadIdx.x; t < done_to; t += FFT_THREADS) {
-      int slot = t % ring;
+      int slot = fbase + (t - flushed);
+      if (slot >= ring) slot -= ring;
       float v = ola[slot];
       ola[slot] = 0.0f;
       if (t >= flush_lo && t < flush_hi) {
