@@ -35,9 +35,10 @@ void launch_envelope_f32(const EnvInst *, int, int, const sgb_envelope *, const 
 void launch_envelope_f64(const EnvInst *, int, int, const sgb_envelope *, const sgb_formant_ref *, const double *,
                          const double *, double *, cudaStream_t);
 size_t stft_smem_bytes(int n, double h_in, double h_out, int mode);
-cudaError_t launch_stft(int mode, int u_is_float, const FftSeg *, int, const FftJob *, const FftPlan *,
+cudaError_t launch_stft(int mode, int u_is_float, int spec, const FftSeg *, int, const FftJob *, const FftPlan *,
                         const float2 *, const float *, const float *, const void *, const float *, float *, int *,
                         size_t, cudaStream_t);
+int stft_spec_of(int n, const int *radix, int npass);
 void launch_noise_final(const sgb_noise *, int, const NoiseLayout *, const double *, const double *, const int *, int,
                         const float *, float *, int, cudaStream_t);
 void launch_sound_mix(const sgb_bout *, int, const BoutLayout *, const sgb_noise *, const NoiseLayout *,
@@ -436,22 +437,34 @@ struct PlanTable {
 };
 
 // segments: one CTA per sound when there are plenty of sounds, else split runs of frames
-static void make_segs(const std::vector<FftJob> &jobs, std::vector<FftSeg> &segs) {
+// `groups` receives, per compile-time FFT plan (spec), the [begin, end) range of its segments.
+struct SegGroup { int spec, begin, end; size_t smem; };
+static void make_segs(const std::vector<FftJob> &jobs, const std::vector<FftPlan> &plans, int mode,
+                      std::vector<FftSeg> &segs, std::vector<SegGroup> &groups) {
   const int target = 2 * 148;
   int per_job = 1;
   if ((int)jobs.size() < target && !jobs.empty()) per_job = (target + (int)jobs.size() - 1) / (int)jobs.size();
-  for (int j = 0; j < (int)jobs.size(); j++) {
-    int nc = jobs[j].nc;
-    int nseg = std::max(1, std::min(per_job, nc / 8));
-    int fr = (nc + nseg - 1) / nseg;
-    fr += fr & 1;   // keep pairs aligned
-    for (int ka = 0; ka < nc; ka += fr) {
-      FftSeg sg; sg.job = j; sg.ka = ka; sg.kb = std::min(nc, ka + fr); sg.pad = 0;
-      segs.push_back(sg);
+  std::vector<int> spec_of(plans.size());
+  for (size_t i = 0; i < plans.size(); i++) spec_of[i] = stft_spec_of(plans[i].n, plans[i].radix, plans[i].npass);
+  for (int sp = 0; sp < 7; sp++) {
+    SegGroup gr; gr.spec = sp; gr.begin = (int)segs.size(); gr.smem = 0;
+    for (int j = 0; j < (int)jobs.size(); j++) {
+      if (spec_of[jobs[j].plan] != sp) continue;
+      const FftPlan &pl = plans[jobs[j].plan];
+      gr.smem = std::max(gr.smem, stft_smem_bytes(pl.n, pl.h_in, pl.h_out, mode));
+      int nc = jobs[j].nc;
+      int nseg = std::max(1, std::min(per_job, nc / 8));
+      int fr = (nc + nseg - 1) / nseg;
+      fr += fr & 1;   // keep pairs aligned
+      for (int ka = 0; ka < nc; ka += fr) {
+        FftSeg sg; sg.job = j; sg.ka = ka; sg.kb = std::min(nc, ka + fr); sg.pad = 0;
+        segs.push_back(sg);
+      }
     }
+    gr.end = (int)segs.size();
+    if (gr.end > gr.begin) groups.push_back(gr);
   }
 }
-
 // matchLengths(x, len) geometry (R/utilities_math.R:413-444, padDir = 'central')
 static void match_lengths(int xlen, int len, int *pad, int *start0) {
   *pad = 0;
@@ -679,8 +692,9 @@ int sgb_batch_run(sgb_batch *b, sgb_run_info *info_out) {
   for (int c = 0; c < NC; c++) info.total_samples += b->call_len[c];
 
   std::vector<FftSeg> fsegs, nsegs;
-  make_segs(fjobs, fsegs);
-  make_segs(njobs, nsegs);
+  std::vector<SegGroup> fgroups, ngroups;
+  make_segs(fjobs, PT.plans, 0, fsegs, fgroups);
+  make_segs(njobs, PT.plans, 1, nsegs, ngroups);
 
   std::vector<FftPlan> &plans = PT.plans;
   std::vector<float2> &tw_host = PT.tw;
@@ -746,16 +760,18 @@ int sgb_batch_run(sgb_batch *b, sgb_run_info *info_out) {
   CK(cudaEventRecord(ev[6], st));
   // ---- K5 noise ----
   if (!nsegs.empty()) {
-    size_t smem = 0;
-    for (auto &J : njobs) smem = std::max(smem, stft_smem_bytes(plans[J.plan].n, plans[J.plan].h_in, plans[J.plan].h_out, 1));
-    if (smem > 226 * 1024) return fail(SGB_ERR_UNSUPPORTED, "noise window too long for shared memory (%zu bytes)", smem);
-    CK(launch_stft(1, b->u_is_float, b->d_nsegs.as<FftSeg>(), (int)nsegs.size(), b->d_njobs.as<FftJob>(),
-                   b->d_plans.as<FftPlan>(), b->d_tw.as<float2>(), b->d_win.as<float>(), nullptr, b->d_u.p,
-                   b->d_env.as<float>(), b->d_noise_raw.as<float>(), b->d_max.as<int>(), smem, st));
+    for (auto &gr : ngroups) {
+      if (gr.smem > 226 * 1024) return fail(SGB_ERR_UNSUPPORTED, "noise window too long for shared memory (%zu bytes)", gr.smem);
+      CK(launch_stft(1, b->u_is_float, gr.spec, b->d_nsegs.as<FftSeg>() + gr.begin, gr.end - gr.begin,
+                     b->d_njobs.as<FftJob>(), b->d_plans.as<FftPlan>(), b->d_tw.as<float2>(), b->d_win.as<float>(),
+                     nullptr, b->d_u.p, b->d_env.as<float>(), b->d_noise_raw.as<float>(), b->d_max.as<int>(),
+                     gr.smem, st));
+      launches++;
+    }
     launch_noise_final(b->d_noises.as<sgb_noise>(), NN, b->d_nl.as<NoiseLayout>(), b->d_anchors.as<double>(),
                        b->d_pre.as<double>(), b->d_max.as<int>(), NB, b->d_noise_raw.as<float>(),
                        b->d_noise_fin.as<float>(), 16, st);
-    launches += 2;
+    launches += 1;
   }
   CK(cudaEventRecord(ev[7], st));
   // ---- sound = voiced + breathing, global envelope ----
@@ -765,13 +781,11 @@ int sgb_batch_run(sgb_batch *b, sgb_run_info *info_out) {
   launches++;
   CK(cudaEventRecord(ev[8], st));
   // ---- K2 filter ----
-  if (!fsegs.empty()) {
-    size_t smem = 0;
-    for (auto &J : fjobs) smem = std::max(smem, stft_smem_bytes(plans[J.plan].n, plans[J.plan].h_in, plans[J.plan].h_out, 0));
-    if (smem > 226 * 1024) return fail(SGB_ERR_UNSUPPORTED, "window too long for shared memory (%zu bytes)", smem);
-    CK(launch_stft(0, 0, b->d_fsegs.as<FftSeg>(), (int)fsegs.size(), b->d_fjobs.as<FftJob>(),
+  for (auto &gr : fgroups) {
+    if (gr.smem > 226 * 1024) return fail(SGB_ERR_UNSUPPORTED, "window too long for shared memory (%zu bytes)", gr.smem);
+    CK(launch_stft(0, 0, gr.spec, b->d_fsegs.as<FftSeg>() + gr.begin, gr.end - gr.begin, b->d_fjobs.as<FftJob>(),
                    b->d_plans.as<FftPlan>(), b->d_tw.as<float2>(), b->d_win.as<float>(), b->d_sound.as<float>(),
-                   nullptr, b->d_env.as<float>(), b->d_filt.as<float>(), b->d_max.as<int>(), smem, st));
+                   nullptr, b->d_env.as<float>(), b->d_filt.as<float>(), b->d_max.as<int>(), gr.smem, st));
     launches++;
   }
   CK(cudaEventRecord(ev[9], st));
@@ -1055,7 +1069,8 @@ int sgb_filter(const double *sound, int64_t len, const double *envelope, int32_t
   J.out_len = (int32_t)xlen; J.shift = 0; J.max_slot = 0;
   std::vector<FftJob> jobs(1, J);
   std::vector<FftSeg> segs;
-  make_segs(jobs, segs);
+  std::vector<SegGroup> groups;
+  make_segs(jobs, PT.plans, 0, segs, groups);
   DBuf d64, dS, dE64, dE, dO, dPl, dTw, dWin, dJ, dSg, dMax, dO64;
   auto run = [&]() -> int {
     const size_t nenv = (size_t)nr * nInt;
@@ -1074,8 +1089,9 @@ int sgb_filter(const double *sound, int64_t len, const double *envelope, int32_t
     CK(cudaMemcpy(dJ.p, &J, sizeof J, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dSg.p, segs.data(), sizeof(FftSeg) * segs.size(), cudaMemcpyHostToDevice));
     k_fill_int<<<1, 32>>>(dMax.as<int>(), 4, ORDERED_NEG_INF);
-    CK(launch_stft(0, 0, dSg.as<FftSeg>(), (int)segs.size(), dJ.as<FftJob>(), dPl.as<FftPlan>(), dTw.as<float2>(),
-                   dWin.as<float>(), dS.as<float>(), nullptr, dE.as<float>(), dO.as<float>(), dMax.as<int>(), smem, 0));
+    CK(launch_stft(0, 0, groups[0].spec, dSg.as<FftSeg>(), (int)segs.size(), dJ.as<FftJob>(), dPl.as<FftPlan>(),
+                   dTw.as<float2>(), dWin.as<float>(), dS.as<float>(), nullptr, dE.as<float>(), dO.as<float>(),
+                   dMax.as<int>(), smem, 0));
     CK(cudaDeviceSynchronize());
     int mi;
     CK(cudaMemcpy(&mi, dMax.p, 4, cudaMemcpyDeviceToHost));

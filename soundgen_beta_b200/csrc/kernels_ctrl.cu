@@ -32,8 +32,33 @@ k_control(const sgb_syllable *syl, int S, const double *pitch, const double *anc
   __syncthreads();
   if (sh_status != SGB_OK) return;
   const int G = C.nGC, nH = C.nHarmonics;
-  for (int g = threadIdx.x; g < G; g += blockDim.x) A.colmax[g] = ctrl_colmax(sp, A, C, g);
-  for (int h = 1 + threadIdx.x; h <= nH; h += blockDim.x) A.rowmap[h - 1] = ctrl_rowkept(sp, A, C, h) ? 1 : 0;
+  __shared__ double lgt[1024];
+  const bool use_tab = nH <= 1024;
+  if (use_tab) for (int h = 1 + threadIdx.x; h <= nH; h += blockDim.x) lgt[h - 1] = log2((double)h);
+  __syncthreads();
+  const bool ao = C.any_oct != 0;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    if (!use_tab) { A.colmax[g] = ctrl_colmax(sp, A, C, g); continue; }
+    double m = -INFINITY;
+    const double pg = A.ppg[g], rog = A.ro[g], roctg = A.roct[g], rkg = A.rk[g];
+    for (int h = 1; h <= nH; h++) {
+      double r = rolloff_db_l(h, lgt[h - 1], pg, rog, roctg, rkg, ao, sp.rolloffParab, C.parab_harm, C.parab_a,
+                              C.parab_b, C.parab_c, 200.0, sp.throwaway, sp.samplingRate);
+      if (r > m) m = r;
+    }
+    A.colmax[g] = m;
+  }
+  for (int h = 1 + threadIdx.x; h <= nH; h += blockDim.x) {
+    if (!use_tab) { A.rowmap[h - 1] = ctrl_rowkept(sp, A, C, h) ? 1 : 0; continue; }
+    int kept = 0;
+    const double lh = lgt[h - 1];
+    for (int g = 0; g < G && !kept; g++) {
+      double r = rolloff_db_l(h, lh, A.ppg[g], A.ro[g], A.roct[g], A.rk[g], ao, sp.rolloffParab, C.parab_harm,
+                              C.parab_a, C.parab_b, C.parab_c, 200.0, sp.throwaway, sp.samplingRate);
+      if (r > -INFINITY) kept = 1;
+    }
+    A.rowmap[h - 1] = kept;
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     int kept = 0;
@@ -118,8 +143,8 @@ __global__ void k_build_tiles(const SylCtrl *ctrl, int S, const SylLayout *lay, 
 #define AMP_MAXH 1024
 #define AMP_MAXS 16
 #define AMP_CG 32
-#define AMP_RPT 8
-__global__ void __launch_bounds__(256)
+#define AMP_RPT 4
+__global__ void __launch_bounds__(256, 3)
 k_amp(const sgb_syllable *syl, int S, const SylCtrl *ctrl, const SylLayout *lay, Pools P, double *amp,
       float2 *amp32) {
   int s = blockIdx.x;
@@ -174,9 +199,24 @@ k_amp(const sgb_syllable *syl, int S, const SylCtrl *ctrl, const SylLayout *lay,
       // each thread owns rows j = rb + tid + i*256 and walks the columns, so that the FP32
       // {Y_g, Y_{g+1} - Y_g} table K1 consumes falls out of the same pass
       for (int rb = 0; rb < rows; rb += 256 * AMP_RPT) {
-        double prev[AMP_RPT];
+        double prev[AMP_RPT], lg[AMP_RPT];
+        int rk_[AMP_RPT], rs_[AMP_RPT], rh_[AMP_RPT];     // per owned row: f index k, sub index s, harmonic h
+#pragma unroll
+        for (int i = 0; i < AMP_RPT; i++) {
+          const int j = rb + i * 256 + (int)threadIdx.x + 1;
+          rk_[i] = 0; rs_[i] = 0; rh_[i] = 1; lg[i] = 0.0; prev[i] = 0.0;
+          if (j <= rows) {
+            rk_[i] = (n == 0) ? j : j / (n + 1);
+            rs_[i] = (n == 0) ? 0 : j % (n + 1);
+            if (rs_[i] == 0) { rh_[i] = A.rowmap[rk_[i] - 1]; lg[i] = log2((double)rh_[i]); }
+          }
+        }
         for (int g = ga; g < gx; g++) {
           const int gi = g - ga;
+          const double pg = A.ppg[g], rog = A.ro[g], roctg = A.roct[g], rkg = A.rk[g], cmg = A.colmax[g],
+                       shg = A.shimmer[g];
+          double *oc = oe + (int64_t)(g - g0) * rows;
+          float2 *oc32 = oe32 + (int64_t)(g - 1 - g0) * rows;
 #pragma unroll
           for (int i = 0; i < AMP_RPT; i++) {
             const int j = rb + i * 256 + (int)threadIdx.x + 1;
@@ -185,20 +225,18 @@ k_amp(const sgb_syllable *syl, int S, const SylCtrl *ctrl, const SylLayout *lay,
             if (!tabled) {
               v = ampl_exact(sp, A, C, e, j, g);
             } else {
-              int k = (n == 0) ? j : j / (n + 1), si = (n == 0) ? 0 : j % (n + 1);
-              if (si == 0) {
-                int h = A.rowmap[k - 1];
-                double r = rolloff_db(h, A.ppg[g], A.ro[g], A.roct[g], A.rk[g], C.any_oct != 0, sp.rolloffParab,
-                                      C.parab_harm, C.parab_a, C.parab_b, C.parab_c, 200.0, sp.throwaway,
-                                      sp.samplingRate);
-                v = exp2((r - A.colmax[g]) / 10.0) * A.shimmer[g];
+              if (rs_[i] == 0) {
+                double r = rolloff_db_l(rh_[i], lg[i], pg, rog, roctg, rkg, C.any_oct != 0, sp.rolloffParab,
+                                        C.parab_harm, C.parab_a, C.parab_b, C.parab_c, 200.0, sp.throwaway,
+                                        sp.samplingRate);
+                v = exp2((r - cmg) / 10.0) * shg;
               } else {
-                v = A0[k] * ML[(si - 1) * (AMP_CG + 1) + gi] + A0[k + 1] * MU[(si - 1) * (AMP_CG + 1) + gi];
+                v = A0[rk_[i]] * ML[(rs_[i] - 1) * (AMP_CG + 1) + gi] + A0[rk_[i] + 1] * MU[(rs_[i] - 1) * (AMP_CG + 1) + gi];
               }
               if (n > 0 && v < thr01) v = 0.0;
             }
-            if (g < gb) oe[(int64_t)(g - g0) * rows + (j - 1)] = v;
-            if (g > ga) oe32[(int64_t)(g - 1 - g0) * rows + (j - 1)] = make_float2((float)prev[i], (float)(v - prev[i]));
+            if (g < gb) oc[j - 1] = v;
+            if (g > ga) oc32[j - 1] = make_float2((float)prev[i], (float)(v - prev[i]));
             prev[i] = v;
           }
         }

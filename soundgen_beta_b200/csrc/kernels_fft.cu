@@ -44,8 +44,8 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
 // One Stockham pass (decimation in frequency): N points, stride s (product of the
 // radices already done), radix r.  DIR = -1 forward, +1 inverse (conjugated twiddles).
 template <int DIR>
-__device__ void fft_pass(const float2 *__restrict__ x, float2 *__restrict__ y, int N, int s, int r,
-                         const float2 *__restrict__ tw) {
+__device__ __forceinline__ void fft_pass(const float2 *__restrict__ x, float2 *__restrict__ y, int N, int s, int r,
+                                         const float2 *__restrict__ tw) {
   const int nb = N / r;             // butterflies
   const int m = nb / s;             // N / (s * r)
   if (r == 4) {
@@ -164,6 +164,28 @@ __device__ float2 *fft_run(float2 *a, float2 *b, const FftPlan &pl, const float2
   return src;
 }
 
+// Compile-time plans for soundgen's usual windows (50 ms at 16 / 22.05 / 24 / 44.1 / 48 kHz and the
+// 10 ms presets): with N, the strides and the radices known, every index division folds to a
+// multiply-shift and the radix dispatch disappears.  SPEC 0 = run-time plan (any even length).
+template <int DIR, int N, int S>
+__device__ __forceinline__ float2 *run_ct(float2 *a, float2 *, const float2 *) { return a; }
+template <int DIR, int N, int S, int R, int... Rest>
+__device__ __forceinline__ float2 *run_ct(float2 *a, float2 *b, const float2 *tw) {
+  fft_pass<DIR>(a, b, N, S, R, tw);
+  __syncthreads();
+  return run_ct<DIR, N, S * R, Rest...>(b, a, tw);
+}
+template <int DIR, int SPEC>
+__device__ __forceinline__ float2 *fft_any(float2 *a, float2 *b, const FftPlan &pl, const float2 *tw) {
+  if constexpr (SPEC == 1) return run_ct<DIR, 800, 1, 5, 5, 4, 4, 2>(a, b, tw);
+  else if constexpr (SPEC == 2) return run_ct<DIR, 1102, 1, 29, 19, 2>(a, b, tw);
+  else if constexpr (SPEC == 3) return run_ct<DIR, 1200, 1, 5, 5, 3, 4, 4>(a, b, tw);
+  else if constexpr (SPEC == 4) return run_ct<DIR, 2204, 1, 29, 19, 4>(a, b, tw);
+  else if constexpr (SPEC == 5) return run_ct<DIR, 2400, 1, 5, 5, 3, 4, 4, 2>(a, b, tw);
+  else if constexpr (SPEC == 6) return run_ct<DIR, 160, 1, 5, 4, 4, 2>(a, b, tw);
+  else return fft_run<DIR>(a, b, pl, tw);
+}
+
 __device__ __forceinline__ int frame_in_start(const FftPlan &pl, int k) {   // 0-based
   return (int)floor(1.0 + (double)k * pl.h_in) - 1;
 }
@@ -172,7 +194,7 @@ __device__ __forceinline__ int frame_out_start(const FftPlan &pl, int k) {
 }
 
 // MODE 0: filter (K2).  MODE 1: noise (K5), UT = uniform dtype.
-template <int MODE, typename UT>
+template <int MODE, typename UT, int SPEC>
 __global__ void __launch_bounds__(FFT_THREADS)
 k_stft(const FftSeg *__restrict__ segs, const FftJob *__restrict__ jobs, const FftPlan *__restrict__ plans,
        const float2 *__restrict__ twpool, const float *__restrict__ winpool,
@@ -263,7 +285,7 @@ k_stft(const FftSeg *__restrict__ segs, const FftJob *__restrict__ jobs, const F
       __syncthreads();
       // all generic-proxy reads of this staging buffer are done: make it safe for the next TMA write
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      float2 *Z = fft_run<-1>(bufA, bufB, pl, tw);
+      float2 *Z = fft_any<-1, SPEC>(bufA, bufB, pl, tw);
       // ---- split the two spectra, multiply by the envelope, rebuild Hermitian halves ----
       const float *eA = envpool + jb.env_off + (int64_t)((jb.nint > 1) ? k : 0) * nr;
       const float *eB = envpool + jb.env_off + (int64_t)((jb.nint > 1 && hasB) ? (k + 1) : 0) * nr;
@@ -310,7 +332,7 @@ k_stft(const FftSeg *__restrict__ segs, const FftJob *__restrict__ jobs, const F
       spec = bufA;
     }
     float2 *other = (spec == bufA) ? bufB : bufA;
-    float2 *Y = fft_run<+1>(spec, other, pl, tw);
+    float2 *Y = fft_any<+1, SPEC>(spec, other, pl, tw);
 
     // ---- weighted overlap-add into the ring (frame A, then frame B) ----
     const int oA = frame_out_start(pl, k) % ring;
@@ -371,34 +393,65 @@ size_t stft_smem_bytes(int n, double h_in, double h_out, int mode) {
   return floats * 4 + 64;
 }
 
-static size_t attr_smem[3] = {0, 0, 0};
+#define N_SPEC 7
+static size_t attr_smem[3][N_SPEC];
 
 template <typename K>
-static cudaError_t ensure_smem(K kf, int slot, size_t smem) {
-  if (smem <= 48 * 1024 || smem <= attr_smem[slot]) return cudaSuccess;
+static cudaError_t ensure_smem(K kf, size_t *slot, size_t smem) {
+  if (smem <= 48 * 1024 || smem <= *slot) return cudaSuccess;
   cudaError_t e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e == cudaSuccess) attr_smem[slot] = smem;
+  if (e == cudaSuccess) *slot = smem;
   return e;
 }
 
-cudaError_t launch_stft(int mode, int u_is_float, const FftSeg *segs, int n_segs, const FftJob *jobs,
+int stft_spec_of(int n, const int *radix, int npass) {
+  static const int sizes[N_SPEC] = {0, 800, 1102, 1200, 2204, 2400, 160};
+  static const int rad[N_SPEC][8] = {{0}, {5, 5, 4, 4, 2}, {29, 19, 2}, {5, 5, 3, 4, 4}, {29, 19, 4},
+                                     {5, 5, 3, 4, 4, 2}, {5, 4, 4, 2}};
+  for (int sp = 1; sp < N_SPEC; sp++) {
+    if (sizes[sp] != n) continue;
+    int np = 0;
+    while (np < 8 && rad[sp][np]) np++;
+    if (np != npass) continue;
+    bool same = true;
+    for (int i = 0; i < np; i++) if (rad[sp][i] != radix[i]) same = false;
+    if (same) return sp;
+  }
+  return 0;
+}
+
+template <int SPEC>
+static cudaError_t launch_spec(int mode, int u_is_float, const FftSeg *segs, int n_segs, const FftJob *jobs,
+                               const FftPlan *plans, const float2 *tw, const float *win, const float *in_f,
+                               const void *in_u, const float *env, float *out, int *maxpool, size_t smem,
+                               cudaStream_t st) {
+  cudaError_t e = cudaSuccess;
+  if (mode == 0) {
+    auto kf = k_stft<0, float, SPEC>;
+    if ((e = ensure_smem(kf, &attr_smem[0][SPEC], smem)) != cudaSuccess) return e;
+    kf<<<n_segs, FFT_THREADS, smem, st>>>(segs, jobs, plans, tw, win, in_f, nullptr, env, out, maxpool);
+  } else if (u_is_float) {
+    auto kf = k_stft<1, float, SPEC>;
+    if ((e = ensure_smem(kf, &attr_smem[1][SPEC], smem)) != cudaSuccess) return e;
+    kf<<<n_segs, FFT_THREADS, smem, st>>>(segs, jobs, plans, tw, win, nullptr, (const float *)in_u, env, out, maxpool);
+  } else {
+    auto kf = k_stft<1, double, SPEC>;
+    if ((e = ensure_smem(kf, &attr_smem[2][SPEC], smem)) != cudaSuccess) return e;
+    kf<<<n_segs, FFT_THREADS, smem, st>>>(segs, jobs, plans, tw, win, nullptr, (const double *)in_u, env, out, maxpool);
+  }
+  return cudaGetLastError();
+}
+
+// all segments of one launch share `spec` (0 = run-time plan)
+cudaError_t launch_stft(int mode, int u_is_float, int spec, const FftSeg *segs, int n_segs, const FftJob *jobs,
                         const FftPlan *plans, const float2 *tw, const float *win, const float *in_f,
                         const void *in_u, const float *env, float *out, int *maxpool, size_t smem,
                         cudaStream_t st) {
   if (n_segs <= 0) return cudaSuccess;
-  cudaError_t e = cudaSuccess;
-  if (mode == 0) {
-    auto kf = k_stft<0, float>;
-    if ((e = ensure_smem(kf, 0, smem)) != cudaSuccess) return e;
-    kf<<<n_segs, FFT_THREADS, smem, st>>>(segs, jobs, plans, tw, win, in_f, nullptr, env, out, maxpool);
-  } else if (u_is_float) {
-    auto kf = k_stft<1, float>;
-    if ((e = ensure_smem(kf, 1, smem)) != cudaSuccess) return e;
-    kf<<<n_segs, FFT_THREADS, smem, st>>>(segs, jobs, plans, tw, win, nullptr, (const float *)in_u, env, out, maxpool);
-  } else {
-    auto kf = k_stft<1, double>;
-    if ((e = ensure_smem(kf, 2, smem)) != cudaSuccess) return e;
-    kf<<<n_segs, FFT_THREADS, smem, st>>>(segs, jobs, plans, tw, win, nullptr, (const double *)in_u, env, out, maxpool);
+#define SGB_CASE(SP) case SP: return launch_spec<SP>(mode, u_is_float, segs, n_segs, jobs, plans, tw, win, in_f, in_u, env, out, maxpool, smem, st);
+  switch (spec) {
+    SGB_CASE(1) SGB_CASE(2) SGB_CASE(3) SGB_CASE(4) SGB_CASE(5) SGB_CASE(6)
+    default: return launch_spec<0>(mode, u_is_float, segs, n_segs, jobs, plans, tw, win, in_f, in_u, env, out, maxpool, smem, st);
   }
-  return cudaGetLastError();
+#undef SGB_CASE
 }
