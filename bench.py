@@ -155,7 +155,8 @@ def main():
     sizes = {0: 1, 1: 1024, 2: 4096, 3: 8192}
     n = args.batch or sizes[args.config]
     gen = workloads.CONFIGS[args.config]
-    calls = gen(n=n, seed=20260000 + args.config + 1000 * rank) if args.config != 0 else workloads.config0()
+    from soundgen_beta_b200 import sharding
+    calls = gen(n=n, seed=sharding.shard_seed(args.config, rank)) if args.config != 0 else workloads.config0()
     sr = workloads.SAMPLING_RATE[args.config]
     bb = sg.BatchBuilder(u_dtype=np.float32)   # uniforms travel as float32 (halves the PCIe bytes)
     for kw in calls:
@@ -208,17 +209,7 @@ def main():
     clocks = sampler.stop()
     stage_ms /= args.steps
 
-    if dist is not None:
-        import torch
-        t = torch.tensor([dt, dt_e2e, audio_s], dtype=torch.float64, device='cuda')
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone()
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        dt, dt_e2e = float(tmax[0]), float(tmax[1])
-        audio_total = float(tsum[2])
-    else:
-        audio_total = audio_s
+    dt, dt_e2e, audio_total = sharding.aggregate(dist, dt, dt_e2e, audio_s, device='cuda' if dist is not None else None)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()

@@ -1,0 +1,196 @@
+/*
+ * rshim.c -- .Call bindings of libsoundgen_b200 for the soundgen R package.
+ *
+ * Marshalling only: no arithmetic on samples happens here (BASELINE north_star: "no Rcpp-side
+ * math").  Every entry point converts R vectors to the POD structs of include/soundgen_b200.h,
+ * calls the C ABI and wraps the result in a fresh R vector.  Errors of the library become R
+ * errors AFTER all native resources are released (Rf_error long-jumps).
+ *
+ * Replaces (reference file:line):
+ *   sg_generate_harmonics   <- generateHarmonics        R/source.R:173-471
+ *   sg_generate_noise       <- generateNoise            R/source.R:57-138
+ *   sg_get_rolloff          <- getRolloff               R/sourceSpectrum.R:71-186
+ *   sg_get_spectral_envelope<- getSpectralEnvelope      R/sourceSpectrum.R:417-566 (deterministic part)
+ *   sg_filter               <- filter block of soundgen R/soundgen.R:743-807 (+ seewave stft/istft)
+ *
+ * Build: see src/Makevars (links against libsoundgen_b200.so built by __graft_entry__.build()).
+ */
+#include <R.h>
+#include <Rinternals.h>
+#include <R_ext/Rdynload.h>
+#include <string.h>
+#include <math.h>
+
+#include "soundgen_b200.h"
+
+static double num(SEXP list, const char *name, double dflt) {
+  SEXP names = Rf_getAttrib(list, R_NamesSymbol);
+  for (R_xlen_t i = 0; i < XLENGTH(list); i++)
+    if (strcmp(CHAR(STRING_ELT(names, i)), name) == 0) return Rf_asReal(VECTOR_ELT(list, i));
+  return dflt;
+}
+
+static void fail_if(int rc, sgb_batch *b) {
+  if (rc >= 0) return;
+  char msg[512];
+  strncpy(msg, sgb_last_error(), sizeof msg - 1);
+  msg[sizeof msg - 1] = 0;
+  if (b) sgb_batch_destroy(b);
+  if (rc == SGB_ERR_SYNTH) Rf_error("Failed to generate the new syllable!");   /* soundgen.R:624-626 */
+  Rf_error("soundgen_b200: %s", msg);
+}
+
+/* pars: named list of the numeric arguments of generateHarmonics (source.R:173-205);
+ * pitch: numeric contour; z: standard normals drawn by the caller (rnorm(cap));
+ * ampl: NULL or a 2-column numeric matrix (time, value).
+ * Returns list(waveform = numeric, z_used = integer, gc = integer, gc_upsampled = integer). */
+SEXP sg_generate_harmonics(SEXP pitch, SEXP pars, SEXP z, SEXP ampl) {
+  sgb_syllable s;
+  memset(&s, 0, sizeof s);
+  s.kind = 1;
+  s.pitch_len = (int32_t)XLENGTH(pitch);
+  s.z_cap = (int32_t)XLENGTH(z);
+#define P(f, d) s.f = num(pars, #f, d)
+  P(attackLen, 50); P(nonlinBalance, 0); P(jitterDep, 0); P(jitterLen, 1); P(vibratoFreq, 100);
+  P(vibratoDep, 0); P(shimmerDep, 0); P(rolloff, -18); P(rolloffOct, -2); P(rolloffKHz, -6);
+  P(rolloffParab, 0); P(rolloffParabHarm, 3); P(rolloff_perAmpl, 12); P(temperature, 0);
+  P(pitchDriftDep, .5); P(pitchDriftFreq, .125); P(randomWalk_trendStrength, .5); P(shortestEpoch, 300);
+  P(subFreq, 100); P(subDep, 0); P(samplingRate, 16000); P(pitchFloor, 75); P(pitchCeiling, 3500);
+  P(pitchSamplingRate, 3500); P(throwaway, -120);
+#undef P
+  double *anch = NULL;
+  int n_anch = 0;
+  if (!Rf_isNull(ampl)) {   /* column-major (time, value) matrix -> interleaved pairs */
+    n_anch = Rf_nrows(ampl);
+    anch = (double *)R_alloc(2 * (size_t)n_anch, sizeof(double));
+    for (int i = 0; i < n_anch; i++) { anch[2 * i] = REAL(ampl)[i]; anch[2 * i + 1] = REAL(ampl)[n_anch + i]; }
+    s.ampl_n = n_anch;
+  }
+  sgb_envelope env;
+  memset(&env, 0, sizeof env);
+  env.formantDep = 1; env.vocalTract = R_NaN; env.samplingRate = s.samplingRate; env.speedSound = 35400;
+  env.smoothLinearFactor = 1;
+  sgb_bout bout;
+  memset(&bout, 0, sizeof bout);
+  bout.syl_end = 1; bout.wl = (int32_t)(floor(50.0 / 1000 * s.samplingRate / 2) * 2);
+  bout.overlap = 75; bout.samplingRate = s.samplingRate; bout.throwaway = s.throwaway;
+  sgb_call call = {0, 1};
+  sgb_batch_desc d;
+  memset(&d, 0, sizeof d);
+  d.n_calls = d.n_bouts = d.n_syllables = d.n_envelopes = 1;
+  d.calls = &call; d.bouts = &bout; d.syllables = &s; d.envelopes = &env;
+  d.pitch = REAL(pitch); d.n_pitch = XLENGTH(pitch);
+  d.anchors = anch; d.n_anchors = n_anch;
+  d.z = REAL(z); d.n_z = XLENGTH(z);
+
+  sgb_batch *b = NULL;
+  fail_if(sgb_batch_create(&b), NULL);
+  fail_if(sgb_batch_upload(b, &d), b);
+  fail_if(sgb_batch_run(b, NULL), b);
+  sgb_syl_artefacts art;
+  fail_if(sgb_batch_artefacts(b, 0, &art), b);
+  fail_if(art.status, b);
+  int64_t len = 0;
+  fail_if(sgb_batch_syllable_len(b, 0, &len), b);
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 4));
+  SEXP w = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)len));
+  SEXP gc = PROTECT(Rf_allocVector(INTSXP, art.nGC));
+  SEXP gcu = PROTECT(Rf_allocVector(INTSXP, art.nGC + 1));
+  int rc = sgb_batch_syllable_fetch(b, 0, REAL(w), len);
+  if (rc >= 0) rc = sgb_batch_artefact_ints(b, 0, 0, INTEGER(gc), art.nGC);
+  if (rc >= 0) rc = sgb_batch_artefact_ints(b, 0, 1, INTEGER(gcu), art.nGC + 1);
+  if (rc < 0) { UNPROTECT(4); fail_if(rc, b); }
+  sgb_batch_destroy(b);
+  SET_VECTOR_ELT(out, 0, w);
+  SET_VECTOR_ELT(out, 1, Rf_ScalarInteger(art.z_used));
+  SET_VECTOR_ELT(out, 2, gc);
+  SET_VECTOR_ELT(out, 3, gcu);
+  SEXP nm = PROTECT(Rf_allocVector(STRSXP, 4));
+  SET_STRING_ELT(nm, 0, Rf_mkChar("waveform")); SET_STRING_ELT(nm, 1, Rf_mkChar("z_used"));
+  SET_STRING_ELT(nm, 2, Rf_mkChar("gc")); SET_STRING_ELT(nm, 3, Rf_mkChar("gc_upsampled"));
+  Rf_setAttrib(out, R_NamesSymbol, nm);
+  UNPROTECT(5);
+  return out;
+}
+
+/* getRolloff: returns a matrix rows x nGC with rownames 1..rows (used as times_f0, source.R:401) */
+SEXP sg_get_rolloff(SEXP pitch_per_gc, SEXP nHarmonics, SEXP rolloff, SEXP rolloffOct, SEXP rolloffKHz,
+                    SEXP rolloffParab, SEXP rolloffParabHarm, SEXP rolloffParabCeiling, SEXP baseline,
+                    SEXP throwaway, SEXP samplingRate) {
+  int G = (int)XLENGTH(pitch_per_gc), nH = Rf_asInteger(nHarmonics);
+  double *tmp = (double *)R_alloc((size_t)G * nH, sizeof(double));
+  int32_t rows = 0;
+  double ceil_ = Rf_isNull(rolloffParabCeiling) ? -1.0 : Rf_asReal(rolloffParabCeiling);
+  fail_if(sgb_get_rolloff(REAL(pitch_per_gc), G, nH, REAL(rolloff), (int)XLENGTH(rolloff), REAL(rolloffOct),
+                          (int)XLENGTH(rolloffOct), REAL(rolloffKHz), (int)XLENGTH(rolloffKHz),
+                          Rf_asReal(rolloffParab), Rf_asReal(rolloffParabHarm), ceil_, Rf_asReal(baseline),
+                          Rf_asReal(throwaway), Rf_asReal(samplingRate), tmp, &rows), NULL);
+  SEXP m = PROTECT(Rf_allocMatrix(REALSXP, rows, G));
+  for (int g = 0; g < G; g++) memcpy(REAL(m) + (size_t)g * rows, tmp + (size_t)g * nH, sizeof(double) * rows);
+  SEXP rn = PROTECT(Rf_allocVector(STRSXP, rows));
+  char buf[16];
+  for (int i = 0; i < rows; i++) { snprintf(buf, sizeof buf, "%d", i + 1); SET_STRING_ELT(rn, i, Rf_mkChar(buf)); }
+  SEXP dn = PROTECT(Rf_allocVector(VECSXP, 2));
+  SET_VECTOR_ELT(dn, 0, rn); SET_VECTOR_ELT(dn, 1, R_NilValue);
+  Rf_setAttrib(m, R_DimNamesSymbol, dn);
+  UNPROTECT(3);
+  return m;
+}
+
+/* getSpectralEnvelope, deterministic part.  formants: numeric matrix with 4 columns
+ * (time, freq, amp, width), the formants stacked row-wise; formant_n: rows per formant;
+ * mouth: NULL or 2-column matrix; pars: named list of scalars. */
+SEXP sg_get_spectral_envelope(SEXP nr, SEXP nc, SEXP formants, SEXP formant_n, SEXP tracks_given, SEXP mouth,
+                              SEXP pars) {
+  sgb_envelope e;
+  memset(&e, 0, sizeof e);
+  e.n_formants = Rf_isNull(formants) ? 0 : (int)XLENGTH(formant_n);
+  e.tracks_given = Rf_asLogical(tracks_given) ? 1 : 0;
+  e.formantDep = num(pars, "formantDep", 1); e.rolloffLip = num(pars, "rolloffLip", 6);
+  e.mouthOpenThres = num(pars, "mouthOpenThres", 0); e.openMouthBoost = num(pars, "openMouthBoost", 0);
+  e.vocalTract = num(pars, "vocalTract", R_NaN); e.samplingRate = num(pars, "samplingRate", 16000);
+  e.speedSound = num(pars, "speedSound", 35400); e.smoothLinearFactor = num(pars, "smoothLinearFactor", 1);
+  double *rows = NULL, *ma = NULL;
+  if (e.n_formants > 0) {   /* column-major R matrix -> row-major (time, freq, amp, width) */
+    int n = Rf_nrows(formants);
+    rows = (double *)R_alloc(4 * (size_t)n, sizeof(double));
+    for (int i = 0; i < n; i++) for (int j = 0; j < 4; j++) rows[4 * i + j] = REAL(formants)[(size_t)j * n + i];
+  }
+  if (!Rf_isNull(mouth)) {
+    int n = Rf_nrows(mouth);
+    ma = (double *)R_alloc(2 * (size_t)n, sizeof(double));
+    for (int i = 0; i < n; i++) { ma[2 * i] = REAL(mouth)[i]; ma[2 * i + 1] = REAL(mouth)[n + i]; }
+    e.mouth_n = n;
+  }
+  int NR = Rf_asInteger(nr), NC = Rf_asInteger(nc);
+  SEXP m = PROTECT(Rf_allocMatrix(REALSXP, NR, NC));
+  int rc = sgb_get_spectral_envelope(NR, NC, &e, rows, e.n_formants ? INTEGER(formant_n) : NULL, ma, REAL(m));
+  UNPROTECT(1);
+  fail_if(rc, NULL);
+  return m;
+}
+
+/* soundFiltered = istft(stft(sound) * envelope) / max  (soundgen.R:743-807) */
+SEXP sg_filter(SEXP sound, SEXP envelope, SEXP wl, SEXP overlap) {
+  int64_t len = XLENGTH(sound);
+  int nInt = Rf_isMatrix(envelope) ? Rf_ncols(envelope) : 1;
+  int64_t n = sgb_filter_len(len, Rf_asInteger(wl), Rf_asReal(overlap));
+  if (n < 0) Rf_error("soundgen_b200: sound too short to filter");
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)n));
+  int rc = sgb_filter(REAL(sound), len, REAL(envelope), nInt, Rf_asInteger(wl), Rf_asReal(overlap), REAL(out), n);
+  UNPROTECT(1);
+  fail_if(rc, NULL);
+  return out;
+}
+
+static const R_CallMethodDef call_methods[] = {
+    {"sg_generate_harmonics", (DL_FUNC)&sg_generate_harmonics, 4},
+    {"sg_get_rolloff", (DL_FUNC)&sg_get_rolloff, 11},
+    {"sg_get_spectral_envelope", (DL_FUNC)&sg_get_spectral_envelope, 7},
+    {"sg_filter", (DL_FUNC)&sg_filter, 4},
+    {NULL, NULL, 0}};
+
+void R_init_soundgen(DllInfo *dll) {
+  R_registerRoutines(dll, NULL, call_methods, NULL, NULL);
+  R_useDynamicSymbols(dll, FALSE);
+}
