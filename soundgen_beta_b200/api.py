@@ -587,6 +587,51 @@ def soundgen_batch(list_of_kwargs, out_dtype=np.float32, u_dtype=np.float64):
     return out, st
 
 
+class PipelinedBatches:
+    """Several sub-batches, each on its own handle / CUDA stream and host thread, so that the
+    H2D copy of one sub-batch and the D2H read of another overlap the kernels of a third
+    (ctypes releases the GIL during the library calls).  Independent sounds need no ordering."""
+
+    def __init__(self, descs):
+        self.descs = list(descs)
+        self.batches = [Batch() for _ in self.descs]
+        self.outs = [None] * len(self.descs)
+
+    def _one(self, i, dtype):
+        bt = self.batches[i]
+        bt.upload(self.descs[i])
+        bt.run()
+        if self.outs[i] is None:
+            n = int(bt.lengths().sum())
+            self.outs[i] = np.zeros(max(n, 1), dtype=dtype)
+            _abi.load().sgb_pin(self.outs[i].ctypes.data, self.outs[i].nbytes)
+        return bt.fetch(dtype, out=self.outs[i])
+
+    def step(self, dtype=np.float32):
+        """upload + run + fetch of every sub-batch; returns the per-call waveforms in order."""
+        import threading
+        res = [None] * len(self.descs)
+        err = []
+
+        def work(i):
+            try:
+                res[i] = self._one(i, dtype)
+            except Exception as e:   # surfaced to the caller below
+                err.append(e)
+        th = [threading.Thread(target=work, args=(i,)) for i in range(len(self.descs))]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        if err:
+            raise err[0]
+        return [w for r in res for w in r]
+
+    def close(self):
+        for b in self.batches:
+            b.close()
+
+
 def generateHarmonics(pitch, attackLen=50, nonlinBalance=0, nonlinDep=0, jitterDep=0, jitterLen=1,
                       vibratoFreq=100, vibratoDep=0, shimmerDep=0, creakyBreathy=0, rolloff=-18,
                       rolloffOct=-2, rolloffKHz=-6, rolloffParab=0, rolloffParabHarm=3, rolloffLip=6,

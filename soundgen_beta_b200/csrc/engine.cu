@@ -684,7 +684,7 @@ int sgb_batch_run(sgb_batch *b, sgb_run_info *info_out) {
       }
     }
     b->call_len[c] = clen;
-    out_total += align4(clen);
+    out_total += clen;          // outputs are packed back to back: one D2H copy fetches them all
     if (b->call_status[c] != SGB_OK) n_failed++;
   }
   b->total_out = out_total;
@@ -846,13 +846,7 @@ static int fetch_common(sgb_batch *b, void *out, int64_t n, bool f64) {
     if (m > 0) k_f32_to_f64<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(b->d_out.as<float>(), b->d_out64.as<double>(), m);
     src = b->d_out64.p; esz = 8;
   }
-  int64_t pos = 0;
-  for (size_t c = 0; c < b->call_len.size(); c++) {
-    if (b->call_len[c] > 0)
-      CK(cudaMemcpyAsync((char *)out + pos * esz, (const char *)src + b->call_off[c] * esz, (size_t)b->call_len[c] * esz,
-                         cudaMemcpyDeviceToHost, st));
-    pos += b->call_len[c];
-  }
+  if (need > 0) CK(cudaMemcpyAsync(out, src, (size_t)need * esz, cudaMemcpyDeviceToHost, st));
   CK(cudaEventRecord(b->ev[SGB_T_COUNT + 1], st));
   CK(cudaStreamSynchronize(st));
   CK(cudaEventElapsedTime(&b->info.ms[SGB_T_D2H], b->ev[SGB_T_COUNT], b->ev[SGB_T_COUNT + 1]));

@@ -7,7 +7,7 @@
 #define SYNTH_SPT 4                         // samples per thread
 #define SYNTH_TILE (SYNTH_THREADS * SYNTH_SPT)
 #define SYNTH_KBLOCK 64                     // rows per Clenshaw block
-#define SYNTH_NI_CAP 12                     // amplitude intervals staged in smem per tile
+#define SYNTH_NI_CAP 8                     // amplitude intervals staged in smem per tile
 
 // Pooled per-glottal-cycle scratch: syllable s owns [gc_off[s], gc_off[s+1]) of every array.
 struct Pools {

@@ -16,6 +16,9 @@
 
 #define KPAD (SYNTH_KBLOCK + 1)
 
+#ifndef SYNTH_MIN_CTAS
+#define SYNTH_MIN_CTAS 5
+#endif
 #define SYNTH_NI_FAST 4      // cycles per tile handled by the double-buffered (prefetching) path
 #define SYNTH_TAB 32         // spline pieces / cycle starts cached per tile
 #define SYNTH_SB (2 * SYNTH_KBLOCK)   // rows per super-block: two Clenshaw blocks run interleaved
@@ -23,13 +26,14 @@
 
 struct SynthFix { double x; float w; int gi; int k; int pad; };   // a sample whose pair straddles a cycle
 
-__global__ void __launch_bounds__(SYNTH_THREADS)
+__global__ void __launch_bounds__(SYNTH_THREADS, SYNTH_MIN_CTAS)
 k_synth(const SynthTile *__restrict__ tiles, const sgb_syllable *__restrict__ syl,
         const SylCtrl *__restrict__ ctrl, const SylLayout *__restrict__ lay, Pools P,
         const float2 *__restrict__ amp, float *__restrict__ wave, int *__restrict__ epmax) {
   // [cycle][half][row] {Y_g, Y_g, dY, dY}: one LDS.128 yields both packed operands of a pair
   __shared__ float4 sA[2 * SYNTH_NI_FAST * SBPAD];
-  __shared__ float4 sBig[SYNTH_NI_CAP * SBPAD];
+  float4 *sBig = sA;   // the single-buffered path for up to SYNTH_NI_CAP cycles reuses the same storage
+  static_assert(SYNTH_NI_CAP <= 2 * SYNTH_NI_FAST, "sBig aliases sA");
   __shared__ int sh_rng[4];
   __shared__ int t_gc[SYNTH_TAB + 2];
   __shared__ double t_rcp[SYNTH_TAB + 1];
