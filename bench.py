@@ -131,7 +131,7 @@ def main():
     ap.add_argument('--config', type=int, default=3)
     ap.add_argument('--batch', type=int, default=0, help='calls per GPU per step (default: the config size)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--pipeline', type=int, default=4,
+    ap.add_argument('--pipeline', type=int, default=8,
                     help='sub-batches (host threads / CUDA streams) of the end-to-end measurement')
     args = ap.parse_args()
     rank, world, local = env_int('RANK', 0), env_int('WORLD_SIZE', 1), env_int('LOCAL_RANK', 0)
@@ -248,11 +248,18 @@ def main():
     ms_synth = float(stage_ms[_abi.T_NAMES.index('synth')])
     ms_filter = float(stage_ms[_abi.T_NAMES.index('filter')])
     ms_noise = float(stage_ms[_abi.T_NAMES.index('noise')])
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')))
+        key = 'cfg%d_%d' % (args.config, len(calls))
+        traffic = tj.get(key, {}).get('k_synth', {}).get('dram_bytes_per_launch')
+    except Exception:
+        pass
     roofline = None
     if ms_synth > 0 and info.synth_partials > 0:
         ach = 6.0 * info.synth_partials / (ms_synth * 1e-3) / 1e12
         roofline = {'kernel': 'k_synth', 'bound': 'fp32', 'achieved': ach, 'peak': fp32.value,
-                    'unit': 'TFLOP/s', 'frac': ach / fp32.value if fp32.value else None, 'traffic': None,
+                    'unit': 'TFLOP/s', 'frac': ach / fp32.value if fp32.value else None, 'traffic': traffic,
                     'peak_source': 'measured in this run: sgb_measure_fp32_peak (FFMA2 chains)',
                     'algorithmic': '6 flop per partial-sample x %d partial-samples per launch' % info.synth_partials}
     hbm = peaks.get('hbm_gbs', 6650.0)
