@@ -95,7 +95,8 @@ SGB_HD bool random_walk(int len, double rw_range, double rw_smoothing, bool tren
   } else {
     for (int i = 0; i < n; i++) w1[i] = (double)(i + 1);
     fmm_coef(n, w1, w0, w2, w3, w4);
-    for (int k = 0; k < len; k++) out[k] = r_spline_at(n, w1, w0, w2, w3, w4, len, k);
+    const double by = r_seq_by_step(w1[0], w1[n - 1], len);
+    for (int k = 0; k < len; k++) out[k] = r_spline_at_by(n, w1, w0, w2, w3, w4, by, len, k);
   }
   double mn = out[0];
   for (int i = 1; i < len; i++) mn = fmin(mn, out[i]);
@@ -260,8 +261,10 @@ SGB_HD void ctrl_sequential(const sgb_syllable &sp, const double *anchors, const
     A.jidx[nj++] = 1;
     double i = 1.0;
     long guard = 0;
+    double *ratio_g = A.t3;      // ratio = pitch_per_gc * jitterLen / 1000, one division per cycle
+    for (int g = 0; g < G; g++) ratio_g[g] = A.ppg[g] * sp.jitterLen / 1000.0;
     while (i < (double)G) {
-      double ratio = A.ppg[(int)i - 1] * sp.jitterLen / 1000.0;
+      double ratio = ratio_g[(int)i - 1];
       i = cur + ratio;
       cur = i;
       double r = rint(i);
@@ -283,8 +286,9 @@ SGB_HD void ctrl_sequential(const sgb_syllable &sp, const double *anchors, const
     }
     zi += nj;
     fmm_coef(nj, jx, jy, A.sb, A.sc, A.sd);
+    const double jby = r_seq_by_step(jx[0], jx[nj - 1], G);
     for (int g = 0; g < G; g++) {
-      double jg = r_spline_at(nj, jx, jy, A.sb, A.sc, A.sd, G, g);
+      double jg = r_spline_at_by(nj, jx, jy, A.sb, A.sc, A.sd, jby, G, g);
       A.ppg[g] = A.ppg[g] * jg;
     }
   }
@@ -319,7 +323,7 @@ SGB_HD void ctrl_sequential(const sgb_syllable &sp, const double *anchors, const
   // per-gc arguments of getRolloff (source.R:331-341)
   C.any_oct = 0;
   for (int g = 0; g < G; g++) {
-    double rw3 = pow(A.rw[g], 3.0);
+    double rw3 = (A.rw[g] == 1.0) ? 1.0 : pow(A.rw[g], 3.0);
     A.ro[g] = (sp.rolloff + rolloffAmpl[g]) * rw3;
     A.roct[g] = sp.rolloffOct * rw3;
     A.rk[g] = sp.rolloffKHz * A.rw[g];
@@ -353,7 +357,7 @@ SGB_HD void ctrl_sequential(const sgb_syllable &sp, const double *anchors, const
   int maxsub = 0;
   if (fry) {
     for (int g = 0; g < G; g++) {
-      double rw4 = pow(A.rw[g], 4.0);
+      double rw4 = (A.rw[g] == 1.0) ? 1.0 : pow(A.rw[g], 4.0);
       double subFreq = sp.subFreq * rw4;
       A.subdep[g] = sp.subDep * rw4 * vf_on[g];
       double ns = rint(A.ppg[g] / subFreq) - 1.0;

@@ -9,7 +9,7 @@
 // re-evaluated in FP64 with the reference's own formula (exact_epoch_sample).
 #include "engine.cuh"
 
-#define COMPOSE_THREADS 256
+#define COMPOSE_THREADS 512
 #define ZC_REL_TOL 2e-4f
 
 struct SylView {

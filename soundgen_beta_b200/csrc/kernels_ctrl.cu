@@ -4,7 +4,9 @@
 // One CTA per syllable.  Parallel: vibrato, column maxima, row pruning.
 // Sequential (thread 0): glottal cycles, random walks, jitter, drift, epochs,
 // upsampling knots -- R/source.R:206-385.
-__global__ void __launch_bounds__(128)
+#define CTRL_THREADS 32   // one warp per syllable: the stage is bound by the latency of its sequential
+                          // part, so what matters is how many syllables are resident per SM
+__global__ void __launch_bounds__(CTRL_THREADS, 16)
 k_control(const sgb_syllable *syl, int S, const double *pitch, const double *anchors, const double *z,
           Pools P, SylCtrl *ctrl) {
   int s = blockIdx.x;
@@ -296,7 +298,7 @@ k_rolloff_api(const double *p, int G, int nH, const double *ro, int n_ro, const 
 // ---- host launchers (kernels stay private to this translation unit) ----
 void launch_control(const sgb_syllable *syl, int S, const double *pitch, const double *anchors, const double *z,
                     const Pools &P, SylCtrl *ctrl, SylLayout *lay, int64_t *totals, cudaStream_t st) {
-  k_control<<<S, 128, 0, st>>>(syl, S, pitch, anchors, z, P, ctrl);
+  k_control<<<S, CTRL_THREADS, 0, st>>>(syl, S, pitch, anchors, z, P, ctrl);
   k_scan_sizes<<<1, 1024, 0, st>>>(ctrl, S, lay, totals);
 }
 void launch_tiles_amp(const sgb_syllable *syl, int S, const SylCtrl *ctrl, const SylLayout *lay, const Pools &P,

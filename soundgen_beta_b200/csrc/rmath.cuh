@@ -12,6 +12,14 @@ SGB_HD double r_seq_at(double from, double to, int n, int k) {
   return from + (double)k * by;
 }
 
+// the same with the step by = (to - from) / (n - 1) computed once by the caller
+SGB_HD double r_seq_by_step(double from, double to, int n) { return (n > 1) ? (to - from) / (double)(n - 1) : 0.0; }
+SGB_HD double r_seq_at_by(double from, double to, double by, int n, int k) {
+  if (n <= 1 || k <= 0) return from;
+  if (k >= n - 1) return to;
+  return from + (double)k * by;
+}
+
 // Forsythe-Malcolm-Moler cubic spline coefficients (R `spline`, method "fmm").
 // x,y: n knots; b,c,d: outputs (also used as workspace).  n >= 2.
 SGB_HD void fmm_coef(int n, const double *x, const double *y, double *b, double *c, double *d) {
@@ -83,6 +91,13 @@ SGB_HD double r_spline_at(int n, const double *x, const double *y, const double 
                           const double *d, int nout, int k) {
   if (n == 1) return y[0];
   double u = r_seq_at(x[0], x[n - 1], nout, k);
+  return fmm_eval(n, x, y, b, c, d, u);
+}
+
+SGB_HD double r_spline_at_by(int n, const double *x, const double *y, const double *b, const double *c,
+                             const double *d, double by, int nout, int k) {
+  if (n == 1) return y[0];
+  double u = r_seq_at_by(x[0], x[n - 1], by, nout, k);
   return fmm_eval(n, x, y, b, c, d, u);
 }
 
