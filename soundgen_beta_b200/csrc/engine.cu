@@ -19,13 +19,13 @@
 void launch_control(const sgb_syllable *, int, const double *, const double *, const double *, const Pools &,
                     SylCtrl *, SylLayout *, int64_t *, cudaStream_t);
 void launch_tiles_amp(const sgb_syllable *, int, const SylCtrl *, const SylLayout *, const Pools &, SynthTile *,
-                      int64_t *, double *, float2 *, cudaStream_t);
+                      int64_t *, double *, float4 *, cudaStream_t);
 void launch_rolloff_api(const double *, int, int, const double *, int, const double *, int, const double *, int,
                         double, double, double, double, double, double, double *, int *, double *, int *);
 void launch_fp32_peak(float2 *, int, int, int);
 #define ENV_MAXK_HOST 64
 void launch_synth(const SynthTile *, int, const sgb_syllable *, const SylCtrl *, const SylLayout *, const Pools &,
-                  const float2 *, float *, int *, cudaStream_t);
+                  const float4 *, float *, int *, cudaStream_t);
 void launch_compose(const sgb_syllable *, int, SylCtrl *, const SylLayout *, const Pools &, const double *,
                     const float *, float *, const double *, const double *, const int *, cudaStream_t);
 void launch_place_voiced(const sgb_syllable *, int, const SylCtrl *, const SylLayout *, const SylPlace *,
@@ -125,7 +125,7 @@ struct sgb_batch {
   // device copies
   DBuf d_bouts, d_syls, d_noises, d_envs, d_frefs, d_pitch, d_anchors, d_formants, d_z, d_u, d_pre;
   DBuf d_gc_off, d_h_off, d_ctrl, d_lay, d_totals, d_summary, d_tiles, d_epmax;
-  DBuf p_pitch_w, p_i32[6], p_f64[19];
+  DBuf p_pitch_w, p_i32[6], p_f64[19], p_pc;
   DBuf d_amp, d_amp32, d_wave, d_raw, d_sound, d_voiced, d_filt, d_noise_raw, d_noise_fin, d_env, d_out, d_out64;
   DBuf d_bl, d_place, d_nl, d_envinst, d_plans, d_tw, d_win, d_fjobs, d_njobs, d_fsegs, d_nsegs, d_max;
   Pools pools;
@@ -224,6 +224,7 @@ void sgb_batch_destroy(sgb_batch *b) {
   for (auto d : all) d->release();
   for (auto &d : b->p_i32) d.release();
   for (auto &d : b->p_f64) d.release();
+  b->p_pc.release();
   for (auto &e : b->ev) cudaEventDestroy(e);
   cudaStreamDestroy(b->st);
   delete b;
@@ -350,6 +351,7 @@ int sgb_batch_upload(sgb_batch *b, const sgb_batch_desc *D) {
   for (int i = 0; i < 5; i++) CK(b->p_i32[i].ensure(4 * (size_t)g));
   CK(b->p_i32[5].ensure(4 * (size_t)h));
   for (auto &d : b->p_f64) CK(d.ensure(8 * (size_t)g));
+  CK(b->p_pc.ensure(8 * (size_t)g * SYNTH_PC));
   Pools &P = b->pools;
   P.pitch_w = b->p_pitch_w.as<double>();
   P.gc = b->p_i32[0].as<int32_t>(); P.nsub = b->p_i32[1].as<int32_t>(); P.rwbin = b->p_i32[2].as<int32_t>();
@@ -357,6 +359,7 @@ int sgb_batch_upload(sgb_batch *b, const sgb_batch_desc *D) {
   double **dp[] = {&P.ppg, &P.rw, &P.ro, &P.roct, &P.rk, &P.shimmer, &P.drift, &P.subdep, &P.colmax, &P.kt,
                    &P.sb, &P.sc, &P.sd, &P.phi, &P.t1, &P.t2, &P.t3, &P.t4};
   for (int i = 0; i < 18; i++) *dp[i] = b->p_f64[i].as<double>();
+  P.pc = b->p_pc.as<double>();
   P.gc_off = b->d_gc_off.as<int64_t>();
   P.h_off = b->d_h_off.as<int64_t>();
   CK(b->d_ctrl.ensure(sizeof(SylCtrl) * (size_t)S));
@@ -508,19 +511,19 @@ int sgb_batch_run(sgb_batch *b, sgb_run_info *info_out) {
   const int64_t amp_total = tot[0], wave_total = tot[1], n_tiles = tot[2], raw_total = tot[3];
   if (n_tiles > 2000000000LL) return fail(SGB_ERR_UNSUPPORTED, "batch too large: %lld synthesis tiles", (long long)n_tiles);
   CK(b->d_amp.ensure(8 * (size_t)std::max<int64_t>(amp_total, 1)));
-  CK(b->d_amp32.ensure(8 * (size_t)std::max<int64_t>(amp_total, 1)));
+  CK(b->d_amp32.ensure(16 * (size_t)std::max<int64_t>(amp_total, 1)));
   CK(b->d_wave.ensure(4 * (size_t)std::max<int64_t>(wave_total, 4)));
   CK(b->d_raw.ensure(4 * (size_t)std::max<int64_t>(raw_total, 4)));
   CK(b->d_tiles.ensure(sizeof(SynthTile) * (size_t)std::max<int64_t>(n_tiles, 1)));
 
   // ---- K3 amplitude matrices ----
   launch_tiles_amp(d_syl, S, d_ctrl, d_lay, P, b->d_tiles.as<SynthTile>(), d_tot, b->d_amp.as<double>(),
-                   b->d_amp32.as<float2>(), st);
+                   b->d_amp32.as<float4>(), st);
   launches += 2;
   CK(cudaEventRecord(ev[2], st));
   // ---- K1 synthesis ----
   CK(cudaMemsetAsync(b->d_epmax.p, 0, 4 * (size_t)S * SGB_MAX_EPOCHS, st));
-  launch_synth(b->d_tiles.as<SynthTile>(), (int)n_tiles, d_syl, d_ctrl, d_lay, P, b->d_amp32.as<float2>(),
+  launch_synth(b->d_tiles.as<SynthTile>(), (int)n_tiles, d_syl, d_ctrl, d_lay, P, b->d_amp32.as<float4>(),
                b->d_wave.as<float>(), b->d_epmax.as<int>(), st);
   if (n_tiles > 0) launches++;
   CK(cudaEventRecord(ev[3], st));

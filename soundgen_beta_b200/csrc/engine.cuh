@@ -6,8 +6,9 @@
 #define SYNTH_THREADS 128
 #define SYNTH_SPT 4                         // samples per thread
 #define SYNTH_TILE (SYNTH_THREADS * SYNTH_SPT)
-#define SYNTH_KBLOCK 64                     // rows per Clenshaw block
-#define SYNTH_NI_CAP 8                     // amplitude intervals staged in smem per tile
+#define SYNTH_KMAX 128                      // rows per Clenshaw block when a warp sees one glottal cycle
+#define SYNTH_STAGE 128                     // float4 entries per warp stage: columns x rows per block
+#define SYNTH_PC 6                          // doubles per spline piece {kt, c0..c4}
 
 // Pooled per-glottal-cycle scratch: syllable s owns [gc_off[s], gc_off[s+1]) of every array.
 struct Pools {
@@ -15,6 +16,7 @@ struct Pools {
   int32_t *gc, *nsub, *rwbin, *jidx, *gcup, *rowmap;
   double *ppg, *rw, *ro, *roct, *rk, *shimmer, *drift, *subdep, *colmax, *kt, *sb, *sc, *sd, *phi,
       *t1, *t2, *t3, *t4;
+  double *pc;              // [6 * cap] per spline piece: knot, quartic phase polynomial (K1)
   const int64_t *gc_off;   // [S+1] prefix of (cap+1)
   const int64_t *h_off;    // [S+1] prefix of hcap
 };
@@ -43,7 +45,9 @@ struct SylLayout {
   int32_t pad;
 };
 
-struct SynthTile { int32_t syl; int32_t epoch; int32_t k0; int32_t pad; };
+// One K1 tile: SYNTH_TILE samples of one epoch.  gi_lo / a_lo are the amplitude interval and the
+// spline piece of the tile's first sample (the warps scan forward from there).
+struct SynthTile { int32_t syl; int32_t epoch; int32_t k0; int32_t gi_lo; int32_t a_lo; int32_t pad[3]; };
 
 // Host-computed layout of one bout (after syllable lengths are known).
 struct BoutLayout {

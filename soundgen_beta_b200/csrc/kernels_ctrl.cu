@@ -34,6 +34,20 @@ k_control(const sgb_syllable *syl, int S, const double *pitch, const double *anc
   __syncthreads();
   if (sh_status != SGB_OK) return;
   const int G = C.nGC, nH = C.nHarmonics;
+  // K1's view of pitch_upsampled: per spline piece the knot and the quartic in M = u - kt of
+  //   sum_{v <= u} pitch_upsampled[v] = phi + y (M+1) + b S1(M) + c S2(M) + d S3(M)   (Faulhaber sums)
+  {
+    double *pc = P.pc + SYNTH_PC * P.gc_off[s];
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+      const double y = A.ppg[g], b = A.sb[g], c = A.sc[g], d = A.sd[g];
+      pc[SYNTH_PC * g + 0] = A.kt[g];
+      pc[SYNTH_PC * g + 1] = A.phi[g] + y;
+      pc[SYNTH_PC * g + 2] = y + b / 2.0 + c / 6.0;
+      pc[SYNTH_PC * g + 3] = b / 2.0 + c / 2.0 + d / 4.0;
+      pc[SYNTH_PC * g + 4] = c / 3.0 + d / 2.0;
+      pc[SYNTH_PC * g + 5] = d / 4.0;
+    }
+  }
   __shared__ double lgt[1024];
   const bool use_tab = nH <= 1024;
   if (use_tab) for (int h = 1 + threadIdx.x; h <= nH; h += blockDim.x) lgt[h - 1] = log2((double)h);
@@ -120,14 +134,29 @@ __global__ void k_build_tiles(const SylCtrl *ctrl, int S, const SylLayout *lay, 
   const SylCtrl &C = ctrl[s];
   if (C.status != SGB_OK || C.nGC == 0) return;
   const int32_t *gcup = P.gcup + P.gc_off[s];
+  const double *kt = P.kt + P.gc_off[s];
+  const int G = C.nGC;
   int t = lay[s].tile_off;
   int64_t partials = 0, samples = 0;
+  int a = 0;                                    // spline piece: largest a with kt[a] <= u (monotone over the syllable)
   for (int e = 0; e < C.nEpochs; e++) {
-    int Ne = gcup[C.ep_end[e]] - gcup[C.ep_start[e] - 1] + 1;
+    const int g_first = C.ep_start[e] - 1, g_last = C.ep_end[e] - 1;
+    const int x_first_i = gcup[g_first];
+    const double x_first = (double)x_first_i, x_last = (double)gcup[g_last];
+    const int Ne = gcup[C.ep_end[e]] - x_first_i + 1;
+    const double by = (x_last - x_first) / (double)(Ne - 1);
+    const int nknots = g_last - g_first + 1;
+    int lo = 0;                                 // amplitude interval of approx(): largest lo <= nknots-2 with knot <= v
     for (int k0 = 0; k0 < Ne; k0 += SYNTH_TILE) {
-      SynthTile T; T.syl = s; T.epoch = e; T.k0 = k0; T.pad = 0;
+      const double v = (k0 >= Ne - 1) ? x_last : (x_first + (double)k0 * by);
+      while (lo < nknots - 2 && v >= (double)gcup[g_first + lo + 1]) lo++;
+      const double u = (double)(x_first_i + k0);
+      while (a < G - 1 && u >= kt[a + 1]) a++;
+      SynthTile T; T.syl = s; T.epoch = e; T.k0 = k0; T.gi_lo = lo; T.a_lo = a; T.pad[0] = T.pad[1] = T.pad[2] = 0;
       tiles[t++] = T;
     }
+    // epochs overlap by one cycle (the next one starts at this one's last cycle): rewind the piece index
+    while (a > 0 && (double)gcup[g_last] < kt[a]) a--;
     partials += (int64_t)Ne * C.ep_rows[e];
     samples += Ne;
   }
@@ -148,7 +177,7 @@ __global__ void k_build_tiles(const SylCtrl *ctrl, int S, const SylLayout *lay, 
 #define AMP_RPT 4
 __global__ void __launch_bounds__(256, 3)
 k_amp(const sgb_syllable *syl, int S, const SylCtrl *ctrl, const SylLayout *lay, Pools P, double *amp,
-      float2 *amp32) {
+      float4 *amp32) {
   int s = blockIdx.x;
   if (s >= S) return;
   const SylCtrl &C = ctrl[s];
@@ -156,7 +185,7 @@ k_amp(const sgb_syllable *syl, int S, const SylCtrl *ctrl, const SylLayout *lay,
   const sgb_syllable sp = syl[s];
   SylArrays A = make_arrays(P, sp, s);
   double *out = amp + lay[s].amp_off;
-  float2 *out32 = amp32 + lay[s].amp_off;
+  float4 *out32 = amp32 + lay[s].amp_off;
   __shared__ double A0[AMP_MAXH + 2];
   __shared__ double ML[AMP_MAXS * (AMP_CG + 1)], MU[AMP_MAXS * (AMP_CG + 1)];
   const int G = C.nGC, Hk = C.rows_kept;
@@ -171,7 +200,7 @@ k_amp(const sgb_syllable *syl, int S, const SylCtrl *ctrl, const SylLayout *lay,
       const int rows = C.ep_rows[e];
       const int g0 = C.ep_start[e] - 1;
       double *oe = out + C.ep_amp_off[e];
-      float2 *oe32 = out32 + C.ep_amp_off[e];
+      float4 *oe32 = out32 + C.ep_amp_off[e];
       const bool tabled = (n == 0) || (Hk <= AMP_MAXH && n <= AMP_MAXS);
       __syncthreads();
       if (tabled && n > 0) {
@@ -218,7 +247,7 @@ k_amp(const sgb_syllable *syl, int S, const SylCtrl *ctrl, const SylLayout *lay,
           const double pg = A.ppg[g], rog = A.ro[g], roctg = A.roct[g], rkg = A.rk[g], cmg = A.colmax[g],
                        shg = A.shimmer[g];
           double *oc = oe + (int64_t)(g - g0) * rows;
-          float2 *oc32 = oe32 + (int64_t)(g - 1 - g0) * rows;
+          float4 *oc32 = oe32 + (int64_t)(g - 1 - g0) * rows;
 #pragma unroll
           for (int i = 0; i < AMP_RPT; i++) {
             const int j = rb + i * 256 + (int)threadIdx.x + 1;
@@ -238,7 +267,10 @@ k_amp(const sgb_syllable *syl, int S, const SylCtrl *ctrl, const SylLayout *lay,
               if (n > 0 && v < thr01) v = 0.0;
             }
             if (g < gb) oc[j - 1] = v;
-            if (g > ga) oc32[j - 1] = make_float2((float)prev[i], (float)(v - prev[i]));
+            if (g > ga) {   // {Y, Y, dY, dY}: one 16-byte load gives K1 both packed FFMA2 operands
+              const float y = (float)prev[i], dy = (float)(v - prev[i]);
+              oc32[j - 1] = make_float4(y, y, dy, dy);
+            }
             prev[i] = v;
           }
         }
@@ -302,7 +334,7 @@ void launch_control(const sgb_syllable *syl, int S, const double *pitch, const d
   k_scan_sizes<<<1, 1024, 0, st>>>(ctrl, S, lay, totals);
 }
 void launch_tiles_amp(const sgb_syllable *syl, int S, const SylCtrl *ctrl, const SylLayout *lay, const Pools &P,
-                      SynthTile *tiles, int64_t *totals, double *amp, float2 *amp32, cudaStream_t st) {
+                      SynthTile *tiles, int64_t *totals, double *amp, float4 *amp32, cudaStream_t st) {
   k_build_tiles<<<(S + 127) / 128, 128, 0, st>>>(ctrl, S, lay, P, tiles, totals);
   dim3 g(S, S >= 2048 ? 1 : (S >= 256 ? 4 : 16));
   k_amp<<<g, 256, 0, st>>>(syl, S, ctrl, lay, P, amp, amp32);

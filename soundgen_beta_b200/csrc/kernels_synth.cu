@@ -1,351 +1,311 @@
 // K1: glottal-cycle additive synthesis -- the harmonic loop of generateHarmonics
 // (R/source.R:389-419): waveform_epoch[k] = sum_rows sin(2*pi*integr[k]*times_f0) * am_upsampled[k].
 //
-// One CTA per (syllable, epoch, 512-sample tile).  Per sample, once:
-//   * phase in FP64: integr = (phi_i + closed-form sum of the cubic piece of
-//     pitch_upsampled) / samplingRate, re-anchored at every spline knot (one per
-//     glottal cycle), so no error accumulates along the syllable;
+// One CTA per (syllable, epoch, 512-sample tile); its four warps are AUTONOMOUS: each owns 128
+// consecutive samples (4 per lane = 2 packed pairs), stages its own amplitude rows and never meets
+// a CTA barrier, so a warp that waits (set-up, copies) never holds up another warp's FMA stream.
+// Per sample, once:
+//   * phase in FP64: integr = (closed-form sum of the cubic piece of pitch_upsampled) / samplingRate,
+//     a quartic in the offset from the spline knot (coefficients from K0), re-anchored at every knot
+//     (one per glottal cycle), so no error accumulates along the syllable;
 //   * the stretched amplitude coordinate of approx() (source.R:403-405) -> (cycle, weight).
 // Per (sample, row): rows are integer multiples j of theta' = 2*pi*integr/(nSubharm+1), so
-// sum_j a_j sin(j theta') is evaluated with a blocked Clenshaw recurrence in Reinsch's
-// stable form (4 FP32 FMAs per partial-sample, no sincos in the loop); every block of
-// SYNTH_KBLOCK rows gets its base rotation e^{i j0 theta'} from a per-sample rotator whose
-// step e^{i K theta'} is reduced in FP64 (no sincos in the loop).  The amplitude columns of
-// the next row block are prefetched into registers while the current block computes.
+// sum_j a_j sin(j theta') is evaluated with a blocked Clenshaw recurrence in Reinsch's stable form
+// (4 packed FP32 FMAs per pair of partial-samples, no sincos in the loop); every block of K rows
+// gets its base rotation e^{i j0 theta'} from a per-sample rotator whose step e^{i K theta'} is
+// reduced in FP64.  The {Y, Y, dY, dY} amplitude rows of the next block travel global -> shared
+// memory with cp.async (16 B per lane, L1-allocating: the four warps of a tile read the same lines)
+// into a per-warp double buffer while the current block computes; one broadcast LDS.128 per row
+// feeds both packed operands of both pairs.  K = 128 / (cycles the warp touches, rounded up to a
+// power of two) so that a stage always fits SYNTH_STAGE entries.
 #include "engine.cuh"
 
-#define KPAD (SYNTH_KBLOCK + 1)
-
 #ifndef SYNTH_MIN_CTAS
-#define SYNTH_MIN_CTAS 5
+#define SYNTH_MIN_CTAS 6
 #endif
-#define SYNTH_NI_FAST 4      // cycles per tile handled by the double-buffered (prefetching) path
-#define SYNTH_TAB 32         // spline pieces / cycle starts cached per tile
-#define SYNTH_SB (2 * SYNTH_KBLOCK)   // rows per super-block: two Clenshaw blocks run interleaved
-#define SBPAD (2 * KPAD)
+#define SYNTH_WARPS (SYNTH_THREADS / 32)
+#define SYNTH_WSAMP (32 * SYNTH_SPT)      // samples per warp
+#define SYNTH_KFALL 64                    // block length of the direct (no staging) path
+#define FULLMASK 0xffffffffu
 
-struct SynthFix { double x; float w; int gi; int k; int pad; };   // a sample whose pair straddles a cycle
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+// Row recurrences for one packed pair (two samples).  The FMA pipe is limited by register-file reads
+// (measured, scripts/micro/rf_model.cu: an FFMA2 with three fresh register pairs takes 3.1 cycles, with
+// two 2.3, an FADD2 2.1), so each warp picks the cheapest form that is safe for ALL its lanes:
+//   mode 3  standard Clenshaw  b <- c2 b1 - b2 + a            (3 ops) every lane at least 0.057 cycles
+//           (20 degrees) away from theta = 0 and pi, where 2 cos(theta) carries the angle accurately;
+//   mode 1/2 Reinsch, sigma = +1 / -1 for the whole warp       (4 ops, two of them adds): every lane
+//           within 3/8 cycle of the pole the form is built around;
+//   mode 0  Reinsch with a per-lane sigma                      (4 FMAs) anything else (a warp that spans
+//           more than a quarter cycle of phase: high pitch).
+#define SYNTH_LERP(CH, Q) __ffma2_rn(w2[CH], make_float2(Q.z, Q.w), make_float2(Q.x, Q.y))
+#define SYNTH_STEP0(CH, Q)                                                                        \
+  {                                                                                               \
+    const float2 a_ = SYNTH_LERP(CH, Q);                                                          \
+    s1[CH] = __ffma2_rn(k0[CH], s0[CH], __ffma2_rn(k1[CH], s1[CH], a_));                           \
+    s0[CH] = __ffma2_rn(k1[CH], s0[CH], s1[CH]);                                                  \
+  }
+#define SYNTH_STEP1(CH, Q)                                                                        \
+  {                                                                                               \
+    const float2 a_ = SYNTH_LERP(CH, Q);                                                          \
+    s1[CH] = __ffma2_rn(k0[CH], s0[CH], __fadd2_rn(s1[CH], a_));                                   \
+    s0[CH] = __fadd2_rn(s0[CH], s1[CH]);                                                          \
+  }
+#define SYNTH_STEP2(CH, Q)                                                                        \
+  {                                                                                               \
+    const float2 a_ = SYNTH_LERP(CH, Q);                                                          \
+    s1[CH] = __ffma2_rn(k0[CH], s0[CH], __fadd2_rn(a_, make_float2(-s1[CH].x, -s1[CH].y)));        \
+    s0[CH] = __fadd2_rn(s1[CH], make_float2(-s0[CH].x, -s0[CH].y));                               \
+  }
+#define SYNTH_STEP3(CH, Q)                                                                        \
+  {                                                                                               \
+    const float2 a_ = SYNTH_LERP(CH, Q);                                                          \
+    const float2 nb = __fadd2_rn(__ffma2_rn(k0[CH], s0[CH], a_), make_float2(-s1[CH].x, -s1[CH].y)); \
+    s1[CH] = s0[CH]; s0[CH] = nb;                                                                 \
+  }
+// one block of mk rows for both pairs of a lane; r0 / r1: the pairs' amplitude columns in the stage
+#define SYNTH_ROWS(STEP, UNR)                                                                     \
+  if (one_col) {                                                                                  \
+    _Pragma(UNR) for (int m = mk - 1; m >= 0; m--) { const float4 q = r0[m]; STEP(0, q) STEP(1, q) } \
+  } else {                                                                                        \
+    _Pragma(UNR) for (int m = mk - 1; m >= 0; m--) { const float4 q0 = r0[m], q1 = r1[m]; STEP(0, q0) STEP(1, q1) } \
+  }
 
 __global__ void __launch_bounds__(SYNTH_THREADS, SYNTH_MIN_CTAS)
 k_synth(const SynthTile *__restrict__ tiles, const sgb_syllable *__restrict__ syl,
         const SylCtrl *__restrict__ ctrl, const SylLayout *__restrict__ lay, Pools P,
-        const float2 *__restrict__ amp, float *__restrict__ wave, int *__restrict__ epmax) {
-  // [cycle][half][row] {Y_g, Y_g, dY, dY}: one LDS.128 yields both packed operands of a pair
-  __shared__ float4 sA[2 * SYNTH_NI_FAST * SBPAD];
-  float4 *sBig = sA;   // the single-buffered path for up to SYNTH_NI_CAP cycles reuses the same storage
-  static_assert(SYNTH_NI_CAP <= 2 * SYNTH_NI_FAST, "sBig aliases sA");
-  __shared__ int sh_rng[4];
-  __shared__ int t_gc[SYNTH_TAB + 2];
-  __shared__ double t_rcp[SYNTH_TAB + 1];
-  __shared__ double t_kt[SYNTH_TAB + 2], t_phi[SYNTH_TAB + 1], t_py[SYNTH_TAB + 1], t_sb[SYNTH_TAB + 1],
-      t_sc[SYNTH_TAB + 1], t_sd[SYNTH_TAB + 1];
-  __shared__ SynthFix fixl[SYNTH_TAB];
-  __shared__ int n_fix;
-  __shared__ float fix_red[SYNTH_THREADS / 32];
-
+        const float4 *__restrict__ amp, float *__restrict__ wave, int *__restrict__ epmax) {
+  __shared__ float4 sStage[SYNTH_WARPS][2][SYNTH_STAGE];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const SynthTile T = tiles[blockIdx.x];
-  const int s = T.syl, e = T.epoch, k0 = T.k0;
+  const int s = T.syl, e = T.epoch;
   const SylCtrl &C = ctrl[s];
-  const double sr = syl[s].samplingRate;
   const int64_t o = P.gc_off[s];
   const int32_t *__restrict__ gcup = P.gcup + o;
-  const double *__restrict__ kt = P.kt + o;
+  const double *__restrict__ pcs = P.pc + SYNTH_PC * o;
   const int G = C.nGC;
   const int g_first = C.ep_start[e] - 1;       // first gc of the epoch (0-based)
   const int g_lastStart = C.ep_end[e] - 1;     // last gc of the epoch
+  const int x_first_i = gcup[g_first];
+  const int Ne = gcup[C.ep_end[e]] - x_first_i + 1;
+  const int kw = T.k0 + SYNTH_WSAMP * wid;     // the warp's first sample
+  if (kw >= Ne) return;                        // no CTA-wide barrier below
   const int nsub = C.vf_active ? C.ep_nsub[e] : 0;
   const int J = C.ep_rows[e];
-  const int x_first_i = gcup[g_first];
   const double x_first = (double)x_first_i, x_last = (double)gcup[g_lastStart];
-  const int Ne = gcup[C.ep_end[e]] - x_first_i + 1;
   const double by = (x_last - x_first) / (double)(Ne - 1);
   const int nknots_e = g_lastStart - g_first + 1;   // knots of approx(): gc starts of the epoch
-  const float2 *__restrict__ ampE = amp + lay[s].amp_off + C.ep_amp_off[e];   // {Y_g, Y_{g+1} - Y_g}
-  const double inv_sr_np1 = 1.0 / (sr * (double)(nsub + 1));
-  const int klast_tile = min(k0 + SYNTH_TILE, Ne) - 1;
+  const float4 *__restrict__ ampE = amp + lay[s].amp_off + C.ep_amp_off[e];   // {Y_g, Y_g, dY, dY}
+  const double inv_sr_np1 = 1.0 / (syl[s].samplingRate * (double)(nsub + 1));
 
-  // ---- tile tables: which cycles / spline pieces the tile touches (two threads search) ----
-  if (threadIdx.x == 0) n_fix = 0;
-  if (threadIdx.x < 2) {
-    int k = threadIdx.x ? klast_tile : k0;
-    double v = (k >= Ne - 1) ? x_last : (x_first + (double)k * by);
-    int lo = 0, hi = nknots_e - 1;
-    while (hi > lo + 1) {
-      int mid = (lo + hi) >> 1;
-      if (v < (double)gcup[g_first + mid]) hi = mid; else lo = mid;
-    }
-    sh_rng[threadIdx.x] = lo;
-  } else if (threadIdx.x >= 32 && threadIdx.x < 34) {
-    int k = (threadIdx.x & 1) ? klast_tile : k0;
-    double u = (double)(x_first_i + k);
-    int a = 0, b = G;
-    while (b > a + 1) {
-      int mid = (a + b) >> 1;
-      if (u < kt[mid]) b = mid; else a = mid;
-    }
-    sh_rng[2 + (threadIdx.x & 1)] = a;
+  // ---- where the warp starts: amplitude interval and spline piece (forward scans from the tile's) ----
+  int lo_w = T.gi_lo, a_w = T.a_lo;
+  {
+    const double v = (kw >= Ne - 1) ? x_last : (x_first + (double)kw * by);
+    while (lo_w < nknots_e - 2 && v >= (double)gcup[g_first + lo_w + 1]) lo_w++;
+    const double u = (double)(x_first_i + kw);
+    while (a_w < G - 1 && u >= pcs[SYNTH_PC * (a_w + 1)]) a_w++;
   }
-  __syncthreads();
-  const int gi_lo = sh_rng[0], n_int = sh_rng[1] - sh_rng[0] + 1;
-  const int a_lo = sh_rng[2], n_pc = sh_rng[3] - sh_rng[2] + 1;
-  const bool tab_ok = (n_int <= SYNTH_TAB) && (n_pc <= SYNTH_TAB);
-  if (tab_ok) {
-    for (int i = threadIdx.x; i <= n_int; i += SYNTH_THREADS) {
-      int g0v = gcup[g_first + gi_lo + i];
-      t_gc[i] = g0v;
-      if (i < n_int) t_rcp[i] = 1.0 / (double)(gcup[g_first + gi_lo + i + 1] - g0v);
-    }
-    for (int i = threadIdx.x; i < n_pc; i += SYNTH_THREADS) {
-      int a = a_lo + i;
-      t_kt[i] = kt[a]; t_phi[i] = P.phi[o + a]; t_py[i] = P.ppg[o + a];
-      t_sb[i] = P.sb[o + a]; t_sc[i] = P.sc[o + a]; t_sd[i] = P.sd[o + a];
-    }
-    if (threadIdx.x == 0) t_kt[n_pc] = (a_lo + n_pc < G) ? kt[a_lo + n_pc] : 1.0e300;
-  }
-  __syncthreads();
 
-  // ---- per-sample set-up (4 consecutive samples per thread = 2 packed pairs) ----
-  float w[SYNTH_SPT], delta[SYNTH_SPT], sigma[SYNTH_SPT], sint[SYNTH_SPT], rotc[SYNTH_SPT], rots[SYNTH_SPT];
+  // ---- per-sample set-up (4 consecutive samples per lane = 2 packed pairs) ----
+  float w[SYNTH_SPT];
   int gi[SYNTH_SPT];
   double xph[SYNTH_SPT];
-  const int kbase = k0 + SYNTH_SPT * threadIdx.x;
+  const int kbase = kw + SYNTH_SPT * lane;
+  {
+    int lo = lo_w, a = a_w;
 #pragma unroll
-  for (int i = 0; i < SYNTH_SPT; i++) {
-    int k = kbase + i;
-    if (k >= Ne) k = Ne - 1;
-    // amplitude coordinate: seq(x_first, x_last, length.out = Ne)[k]
-    double v = (k >= Ne - 1) ? x_last : (x_first + (double)k * by);
-    double u = (double)(x_first_i + k);
-    int lo, a;
-    double xg, rcp, M, f_phi, f_py, f_sb, f_sc, f_sd;
-    if (tab_ok) {
-      lo = 0;
-      while (lo < n_int - 1 && v >= (double)t_gc[lo + 1]) lo++;
-      xg = (double)t_gc[lo]; rcp = t_rcp[lo];
-      a = 0;
-      while (a < n_pc - 1 && u >= t_kt[a + 1]) a++;
-      M = u - t_kt[a];
-      f_phi = t_phi[a]; f_py = t_py[a]; f_sb = t_sb[a]; f_sc = t_sc[a]; f_sd = t_sd[a];
-    } else {
-      int l2 = 0, hi = nknots_e - 1;
-      while (hi > l2 + 1) {
-        int mid = (l2 + hi) >> 1;
-        if (v < (double)gcup[g_first + mid]) hi = mid; else l2 = mid;
-      }
-      xg = (double)gcup[g_first + l2]; rcp = 1.0 / ((double)gcup[g_first + l2 + 1] - xg);
-      lo = l2 - gi_lo;
-      int a2 = 0, b = G;
-      while (b > a2 + 1) {
-        int mid = (a2 + b) >> 1;
-        if (u < kt[mid]) b = mid; else a2 = mid;
-      }
-      M = u - kt[a2];
-      f_phi = P.phi[o + a2]; f_py = P.ppg[o + a2]; f_sb = P.sb[o + a2]; f_sc = P.sc[o + a2]; f_sd = P.sd[o + a2];
+    for (int i = 0; i < SYNTH_SPT; i++) {
+      int k = kbase + i;
+      if (k >= Ne) k = Ne - 1;
+      // amplitude coordinate: seq(x_first, x_last, length.out = Ne)[k]
+      const double v = (k >= Ne - 1) ? x_last : (x_first + (double)k * by);
+      const double u = (double)(x_first_i + k);
+      while (lo < nknots_e - 2 && v >= (double)gcup[g_first + lo + 1]) lo++;
+      while (a < G - 1 && u >= pcs[SYNTH_PC * (a + 1)]) a++;
+      const int xg = gcup[g_first + lo], xn = gcup[g_first + lo + 1];
+      w[i] = (float)(v - (double)xg) * __frcp_rn((float)(xn - xg));
+      gi[i] = lo - lo_w;
+      // phase (cycles) of sample u of the syllable: quartic in the offset from the knot
+      const double *pp = pcs + SYNTH_PC * a;
+      const double M = u - pp[0];
+      const double ph = fma(fma(fma(fma(pp[5], M, pp[4]), M, pp[3]), M, pp[2]), M, pp[1]);
+      double x = ph * inv_sr_np1;               // integr / (nSubharm + 1)
+      x -= floor(x);
+      xph[i] = x;
     }
-    w[i] = (float)((v - xg) * rcp);
-    gi[i] = lo;
-    // phase (cycles) of sample u of the syllable: closed-form sum of the cubic spline piece
-    double s1 = M * (M + 1.0) * 0.5;
-    double s2 = M * (M + 1.0) * (2.0 * M + 1.0) / 6.0;
-    double s3 = s1 * s1;
-    double x = (f_phi + f_py * (M + 1.0) + f_sb * s1 + f_sc * s2 + f_sd * s3) * inv_sr_np1;   // integr / (n+1)
-    x -= floor(x);
-    xph[i] = x;
-    double q = rint(2.0 * x);
-    float xr = (float)(x - 0.5 * q);                    // in [-0.25, 0.25]
-    float sg = (((int)q) & 1) ? -1.0f : 1.0f;
-    float sh, ch;
-    sincospif(xr, &sh, &ch);
-    sigma[i] = sg;
-    delta[i] = -sg * 4.0f * sh * sh;                    // 2cos(theta) - 2 sigma
-    sint[i] = sg * 2.0f * sh * ch;                      // sin(theta)
-    // e^{i K theta}: rotation between the bases of consecutive row blocks (FP64-reduced)
-    double xk = (double)SYNTH_KBLOCK * x;
-    xk -= rint(xk);
-    sincospif(2.0f * (float)xk, &rots[i], &rotc[i]);
   }
-  const bool use_smem = (n_int <= SYNTH_NI_CAP);
-  const bool fast = (n_int <= SYNTH_NI_FAST);
-  // A pair takes the amplitude column of its FIRST sample.  If the second sample already lies in
-  // the next cycle its sum is recomputed after the main loop (at most n_int - 1 samples per tile).
+  const int ncolw = __shfl_sync(FULLMASK, gi[SYNTH_SPT - 1], 31) + 1;   // cycles the warp touches
+  const bool staged = (ncolw <= 16);
+  int kshift = 7;                                                      // K = 128 >> ceil(log2(ncolw))
+  if (staged) { for (int cap = 1; cap < ncolw; cap <<= 1) kshift--; }
+  else kshift = 31 - __clz(SYNTH_KFALL);
+  if ((1 << kshift) > SYNTH_KMAX) kshift = 31 - __clz(SYNTH_KMAX);
+  const int K = 1 << kshift;
+
+  // which recurrence is safe for every lane of the warp (distances in cycles from theta = 0 / pi)
+  int mode;
+  {
+    bool okA = true, okP = true, okM = true;
+#pragma unroll
+    for (int i = 0; i < SYNTH_SPT; i++) {
+      const float xf = (float)xph[i];
+      const float d0 = fminf(xf, 1.0f - xf), dpi = fabsf(xf - 0.5f);
+      okA = okA && (d0 >= 0.057f) && (dpi >= 0.057f);
+      okP = okP && (d0 <= 0.375f);
+      okM = okM && (dpi <= 0.375f);
+    }
+    okA = __all_sync(FULLMASK, okA); okP = __all_sync(FULLMASK, okP); okM = __all_sync(FULLMASK, okM);
+    mode = okA ? 3 : (okP ? 1 : (okM ? 2 : 0));
+  }
+  // k0: delta = 2cos(theta) - 2 sigma (Reinsch) or 2cos(theta) (standard); k1: sigma; ec/es: cos, sin(theta)
+  float2 w2[2], k0[2], k1[2], ec2[2], es2[2], rotc2[2], rots2[2];
 #pragma unroll
   for (int p = 0; p < 2; p++) {
-    if (gi[2 * p + 1] != gi[2 * p] && kbase + 2 * p + 1 < Ne && use_smem) {
-      int slot = atomicAdd(&n_fix, 1);
-      if (slot < SYNTH_TAB) {
-        SynthFix f; f.x = xph[2 * p + 1]; f.w = w[2 * p + 1]; f.gi = gi[2 * p + 1];
-        f.k = SYNTH_SPT * threadIdx.x + 2 * p + 1; f.pad = 0;
-        fixl[slot] = f;
-      }
+    float kk[2], sg[2], co[2], si[2], rc[2], rs[2];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const double x = xph[2 * p + h];
+      const double q = rint(2.0 * x);
+      const float xr = (float)(x - 0.5 * q);              // in [-0.25, 0.25]
+      float sgn = (((int)q) & 1) ? -1.0f : 1.0f;          // the nearer pole
+      float sh, ch;
+      sincospif(xr, &sh, &ch);
+      si[h] = sgn * 2.0f * sh * ch;                       // sin(theta)
+      co[h] = sgn * fmaf(-2.0f * sh, sh, 1.0f);           // cos(theta)
+      float dl = -sgn * 4.0f * sh * sh;                   // 2cos(theta) - 2 sgn, accurate near the pole sgn
+      if (mode == 1 && sgn < 0.0f) { dl = -4.0f * ch * ch; sgn = 1.0f; }   // 2cos(theta) - 2: form built around theta = 0
+      if (mode == 2 && sgn > 0.0f) { dl = 4.0f * ch * ch; sgn = -1.0f; }   // 2cos(theta) + 2: ... around theta = pi
+      kk[h] = (mode == 3) ? 2.0f * co[h] : dl;
+      sg[h] = sgn;
+      double xk = (double)K * x;                          // e^{i K theta}: base rotation between row blocks
+      xk -= rint(xk);
+      sincospif(2.0f * (float)xk, &rs[h], &rc[h]);
     }
+    w2[p] = make_float2(w[2 * p], w[2 * p + 1]);
+    k0[p] = make_float2(kk[0], kk[1]); k1[p] = make_float2(sg[0], sg[1]);
+    ec2[p] = make_float2(co[0], co[1]); es2[p] = make_float2(si[0], si[1]);
+    rotc2[p] = make_float2(rc[0], rc[1]); rots2[p] = make_float2(rs[0], rs[1]);
   }
-  const int gp0 = gi[0], gp1 = gi[2];
-  const bool one_col = __all_sync(0xffffffffu, gp0 == gp1);
 
-  float2 w2[2], delta2[2], sigma2[2];
-  w2[0] = make_float2(w[0], w[1]); w2[1] = make_float2(w[2], w[3]);
-  delta2[0] = make_float2(delta[0], delta[1]); delta2[1] = make_float2(delta[2], delta[3]);
-  sigma2[0] = make_float2(sigma[0], sigma[1]); sigma2[1] = make_float2(sigma[2], sigma[3]);
-
-  float acc[SYNTH_SPT], basec[SYNTH_SPT], bases[SYNTH_SPT];
+  // ---- a pair takes the amplitude column of its FIRST sample; if the second sample already lies in
+  //      the next cycle its sum is evaluated directly, by the whole warp, before the main loop ----
+  float fixv[2] = {0.0f, 0.0f};
+  bool need[2];
 #pragma unroll
-  for (int i = 0; i < SYNTH_SPT; i++) { acc[i] = 0.0f; basec[i] = 1.0f; bases[i] = 0.0f; }
-
-  // prefetch registers of the double-buffered path: up to 4 elements per thread per super-block
-  float2 pf[4];
-  auto pf_load = [&](int j0) {
-    const int mk = min(SYNTH_SB, J - j0);
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-      int idx = threadIdx.x + r * SYNTH_THREADS;
-      if (idx < n_int * SYNTH_SB) {
-        int ii = idx / SYNTH_SB, m = idx - ii * SYNTH_SB;
-        pf[r] = (m < mk) ? ampE[(int64_t)(gi_lo + ii) * J + j0 + m] : make_float2(0.0f, 0.0f);
+  for (int p = 0; p < 2; p++) {
+    need[p] = staged && (gi[2 * p + 1] != gi[2 * p]) && (kbase + 2 * p + 1 < Ne);
+    unsigned msk = __ballot_sync(FULLMASK, need[p]);
+    while (msk) {
+      const int src = __ffs(msk) - 1;
+      msk &= msk - 1;
+      const double xs = __shfl_sync(FULLMASK, xph[2 * p + 1], src);
+      const float ws = __shfl_sync(FULLMASK, w[2 * p + 1], src);
+      const int gs = __shfl_sync(FULLMASK, gi[2 * p + 1], src);
+      const float4 *col = ampE + (int64_t)(lo_w + gs) * J;
+      float part = 0.0f;
+      for (int j = 1 + lane; j <= J; j += 32) {
+        const float4 q = col[j - 1];
+        const float a_ = fmaf(ws, q.z, q.x);
+        double xj = (double)j * xs;
+        xj -= rint(xj);
+        part = fmaf(a_, sinpif(2.0f * (float)xj), part);
       }
-    }
-  };
-  auto pf_store = [&](float4 *dst) {
 #pragma unroll
-    for (int r = 0; r < 4; r++) {
-      int idx = threadIdx.x + r * SYNTH_THREADS;
-      if (idx < n_int * SYNTH_SB) {
-        int ii = idx / SYNTH_SB, m = idx - ii * SYNTH_SB;
-        int half = m / SYNTH_KBLOCK, mm = m - half * SYNTH_KBLOCK;
-        dst[ii * SBPAD + half * KPAD + mm] = make_float4(pf[r].x, pf[r].x, pf[r].y, pf[r].y);
-      }
-    }
-  };
-  if (fast) pf_load(0);
-
-  int blk = 0;
-  for (int j0 = 0; j0 < J; j0 += SYNTH_SB, blk++) {
-    const int mk = min(SYNTH_SB, J - j0);
-    const float4 *tab;
-    if (fast) {
-      float4 *dst = sA + (blk & 1) * (SYNTH_NI_FAST * SBPAD);
-      pf_store(dst);
-      __syncthreads();
-      if (j0 + SYNTH_SB < J) pf_load(j0 + SYNTH_SB);   // in flight while this super-block computes
-      tab = dst;
-    } else if (use_smem) {
-      __syncthreads();
-      for (int idx = threadIdx.x; idx < n_int * SYNTH_SB; idx += SYNTH_THREADS) {
-        int ii = idx / SYNTH_SB, m = idx - ii * SYNTH_SB;
-        float2 q = (m < mk) ? ampE[(int64_t)(gi_lo + ii) * J + j0 + m] : make_float2(0.0f, 0.0f);
-        int half = m / SYNTH_KBLOCK, mm = m - half * SYNTH_KBLOCK;
-        sBig[ii * SBPAD + half * KPAD + mm] = make_float4(q.x, q.x, q.y, q.y);
-      }
-      __syncthreads();
-      tab = sBig;
-    } else {
-      tab = sBig;
-    }
-    // two Clenshaw blocks (rows j0+1..j0+64 and j0+65..j0+128) x two pairs = 4 independent chains
-    float2 bb2[4], dd2[4];
-#pragma unroll
-    for (int c = 0; c < 4; c++) { bb2[c] = make_float2(0.0f, 0.0f); dd2[c] = make_float2(0.0f, 0.0f); }
-    const int mtop = min(mk, SYNTH_KBLOCK);
-    if (use_smem && one_col) {   // every thread of the warp has both pairs in one cycle: 2 loads per row pair
-      const float4 *r0 = tab + gp0 * SBPAD;
-#pragma unroll 4
-      for (int m = mtop - 1; m >= 0; m--) {
-        const float4 a0 = r0[m], b0 = r0[KPAD + m];
-#define STEPY(CH, PR, Q)                                                                   \
-        {                                                                                  \
-          float2 a_ = __ffma2_rn(w2[PR], make_float2(Q.z, Q.w), make_float2(Q.x, Q.y));     \
-          dd2[CH] = __ffma2_rn(delta2[PR], bb2[CH], __ffma2_rn(sigma2[PR], dd2[CH], a_));   \
-          bb2[CH] = __ffma2_rn(sigma2[PR], bb2[CH], dd2[CH]);                              \
-        }
-        STEPY(0, 0, a0) STEPY(1, 1, a0) STEPY(2, 0, b0) STEPY(3, 1, b0)
-      }
-    } else if (use_smem) {
-      const float4 *r0 = tab + gp0 * SBPAD, *r1 = tab + gp1 * SBPAD;
-#pragma unroll 4
-      for (int m = mtop - 1; m >= 0; m--) {
-        const float4 a0 = r0[m], a1 = r1[m], b0 = r0[KPAD + m], b1 = r1[KPAD + m];
-#define STEPX(CH, PR, Q)                                                                   \
-        {                                                                                  \
-          float2 a_ = __ffma2_rn(w2[PR], make_float2(Q.z, Q.w), make_float2(Q.x, Q.y));     \
-          dd2[CH] = __ffma2_rn(delta2[PR], bb2[CH], __ffma2_rn(sigma2[PR], dd2[CH], a_));   \
-          bb2[CH] = __ffma2_rn(sigma2[PR], bb2[CH], dd2[CH]);                              \
-        }
-        STEPX(0, 0, a0) STEPX(1, 1, a1) STEPX(2, 0, b0) STEPX(3, 1, b1)
-      }
-    } else {   // very high pitch: more cycles per tile than fit in shared memory, read L2 directly
-      for (int m = mtop - 1; m >= 0; m--) {
-#pragma unroll
-        for (int hf = 0; hf < 2; hf++) {
-          float ya[SYNTH_SPT], da[SYNTH_SPT];
-#pragma unroll
-          for (int i = 0; i < SYNTH_SPT; i++) {
-            int row = j0 + hf * SYNTH_KBLOCK + m;
-            ya[i] = 0.0f; da[i] = 0.0f;
-            if (row < J) {
-              float2 q = ampE[(int64_t)(gi_lo + gi[i]) * J + row];
-              ya[i] = q.x; da[i] = q.y;
-            }
-          }
-#pragma unroll
-          for (int pr = 0; pr < 2; pr++) {
-            int ch = 2 * hf + pr;
-            float2 a_ = __ffma2_rn(w2[pr], make_float2(da[2 * pr], da[2 * pr + 1]), make_float2(ya[2 * pr], ya[2 * pr + 1]));
-            dd2[ch] = __ffma2_rn(delta2[pr], bb2[ch], __ffma2_rn(sigma2[pr], dd2[ch], a_));
-            bb2[ch] = __ffma2_rn(sigma2[pr], bb2[ch], dd2[ch]);
-          }
-        }
-      }
-    }
-    // block sums: S = b1 sin(theta), C = b1 delta/2 + sigma d1; contribution Im(e^{i j0 theta} (C + iS))
-#pragma unroll
-    for (int hf = 0; hf < 2; hf++) {
-      const float bbs[SYNTH_SPT] = {bb2[2 * hf].x, bb2[2 * hf].y, bb2[2 * hf + 1].x, bb2[2 * hf + 1].y};
-      const float dds[SYNTH_SPT] = {dd2[2 * hf].x, dd2[2 * hf].y, dd2[2 * hf + 1].x, dd2[2 * hf + 1].y};
-#pragma unroll
-      for (int i = 0; i < SYNTH_SPT; i++) {
-        float Ss = bbs[i] * sint[i];
-        float Cs = fmaf(bbs[i], 0.5f * delta[i], sigma[i] * dds[i]);
-        acc[i] += fmaf(bases[i], Cs, basec[i] * Ss);
-        float nc = fmaf(basec[i], rotc[i], -bases[i] * rots[i]);
-        float ns = fmaf(basec[i], rots[i], bases[i] * rotc[i]);
-        basec[i] = nc; bases[i] = ns;
-      }
+      for (int of = 16; of > 0; of >>= 1) part += __shfl_xor_sync(FULLMASK, part, of);
+      if (lane == src) fixv[p] = part;
     }
   }
 
-  // ---- samples whose pair straddled a cycle boundary: direct cooperative evaluation ----
-  __syncthreads();
-  const int nfx = min(n_fix, SYNTH_TAB);
-  for (int f = 0; f < nfx; f++) {
-    const SynthFix F = fixl[f];
-    const float2 *col = ampE + (int64_t)(gi_lo + F.gi) * J;
-    float part = 0.0f;
-    for (int j = 1 + threadIdx.x; j <= J; j += SYNTH_THREADS) {
-      float2 q = col[j - 1];
-      float a_ = fmaf(F.w, q.y, q.x);
-      double xj = (double)j * F.x;
-      xj -= rint(xj);
-      part = fmaf(a_, sinpif(2.0f * (float)xj), part);
-    }
-    for (int of = 16; of > 0; of >>= 1) part += __shfl_xor_sync(0xffffffffu, part, of);
-    if ((threadIdx.x & 31) == 0) fix_red[threadIdx.x >> 5] = part;
-    __syncthreads();
-    if (F.k / SYNTH_SPT == (int)threadIdx.x) {
-      float tot = 0.0f;
-      for (int i = 0; i < SYNTH_THREADS / 32; i++) tot += fix_red[i];
-      const int slot = F.k % SYNTH_SPT;
+  float2 acc2[2], basec2[2], bases2[2];
 #pragma unroll
-      for (int i = 0; i < SYNTH_SPT; i++) if (i == slot) acc[i] = tot;
-    }
-    __syncthreads();
+  for (int p = 0; p < 2; p++) {
+    acc2[p] = make_float2(0.0f, 0.0f); basec2[p] = make_float2(1.0f, 1.0f); bases2[p] = make_float2(0.0f, 0.0f);
+  }
+  // block sums over local rows r = 1..mk: S = sum a_r sin(r theta) = b1 sin(theta); C = sum a_r cos(r theta)
+  //   = b1 cos(theta) - b2 (standard) = b1 (cos(theta) - sigma) + sigma d1 (Reinsch, d1 = b1 - sigma b2);
+  // contribution Im(e^{i j0 theta} (C + iS)); then the base advances by e^{i K theta}
+#define SYNTH_EPILOGUE()                                                                              \
+  _Pragma("unroll") for (int p = 0; p < 2; p++) {                                                     \
+    const float2 Ss = __fmul2_rn(s0[p], es2[p]);                                                      \
+    float2 Cs;                                                                                        \
+    if (mode == 3) Cs = __ffma2_rn(s0[p], ec2[p], make_float2(-s1[p].x, -s1[p].y));                   \
+    else Cs = __ffma2_rn(s0[p], __fmul2_rn(k0[p], make_float2(0.5f, 0.5f)), __fmul2_rn(k1[p], s1[p])); \
+    acc2[p] = __ffma2_rn(bases2[p], Cs, __ffma2_rn(basec2[p], Ss, acc2[p]));                          \
+    const float2 nb = make_float2(-bases2[p].x, -bases2[p].y);                                        \
+    const float2 nc = __ffma2_rn(basec2[p], rotc2[p], __fmul2_rn(nb, rots2[p]));                      \
+    const float2 ns = __ffma2_rn(basec2[p], rots2[p], __fmul2_rn(bases2[p], rotc2[p]));               \
+    basec2[p] = nc; bases2[p] = ns;                                                                   \
   }
 
+  if (staged) {
+    float4(*stage)[SYNTH_STAGE] = sStage[wid];
+    auto issue = [&](int buf, int j0) {
+      float4 *dst = stage[buf];
+#pragma unroll
+      for (int r = 0; r < SYNTH_STAGE / 32; r++) {
+        const int idx = lane + 32 * r;
+        const int c = idx >> kshift, m = idx & (K - 1);
+        if (c < ncolw && j0 + m < J) cp_async16(dst + idx, ampE + (int64_t)(lo_w + c) * J + j0 + m);
+      }
+      cp_async_commit();
+    };
+    issue(0, 0);
+    const int c0 = gi[0] << kshift, c1 = gi[2] << kshift;
+    const bool one_col = __all_sync(FULLMASK, c0 == c1);
+    int blk = 0;
+    for (int j0 = 0; j0 < J; j0 += K, blk++) {
+      const int mk = min(K, J - j0);
+      if (j0 + K < J) { issue((blk + 1) & 1, j0 + K); cp_async_wait<1>(); }   // next block in flight
+      else cp_async_wait<0>();
+      __syncwarp();
+      const float4 *tab = stage[blk & 1];
+      const float4 *r0 = tab + c0, *r1 = tab + c1;
+      float2 s0[2], s1[2];
+      s0[0] = s0[1] = s1[0] = s1[1] = make_float2(0.0f, 0.0f);
+      if (mode == 3) { SYNTH_ROWS(SYNTH_STEP3, "unroll 8") }
+      else if (mode == 1) { SYNTH_ROWS(SYNTH_STEP1, "unroll 8") }
+      else if (mode == 2) { SYNTH_ROWS(SYNTH_STEP2, "unroll 8") }
+      else { SYNTH_ROWS(SYNTH_STEP0, "unroll 4") }
+      SYNTH_EPILOGUE()
+      __syncwarp();      // the stage is rewritten by the copy issued in the next iteration
+    }
+  } else {
+    // very high pitch (more than 16 cycles in 128 samples): every sample reads its own column from L1/L2
+    const float4 *colp[SYNTH_SPT];
+#pragma unroll
+    for (int i = 0; i < SYNTH_SPT; i++) colp[i] = ampE + (int64_t)(lo_w + gi[i]) * J;
+    for (int j0 = 0; j0 < J; j0 += K) {
+      const int mk = min(K, J - j0);
+      float2 s0[2], s1[2];
+      s0[0] = s0[1] = s1[0] = s1[1] = make_float2(0.0f, 0.0f);
+      for (int m = mk - 1; m >= 0; m--) {
+        const float4 q0 = colp[0][j0 + m], q1 = colp[1][j0 + m], q2 = colp[2][j0 + m], q3 = colp[3][j0 + m];
+        const float4 qa = make_float4(q0.x, q1.x, q0.z, q1.z), qb = make_float4(q2.x, q3.x, q2.z, q3.z);
+        if (mode == 3) { SYNTH_STEP3(0, qa) SYNTH_STEP3(1, qb) }
+        else { SYNTH_STEP0(0, qa) SYNTH_STEP0(1, qb) }
+      }
+      SYNTH_EPILOGUE()
+    }
+  }
+
+  float acc[SYNTH_SPT] = {acc2[0].x, need[0] ? fixv[0] : acc2[0].y, acc2[1].x, need[1] ? fixv[1] : acc2[1].y};
   // max |w| of the epoch (tolerance of the zero-crossing searches in K6)
   {
     float m = 0.0f;
 #pragma unroll
     for (int i = 0; i < SYNTH_SPT; i++) if (kbase + i < Ne) m = fmaxf(m, fabsf(acc[i]));
-    for (int of = 16; of > 0; of >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, of));
-    if ((threadIdx.x & 31) == 0) atomicMax(&epmax[(int64_t)s * SGB_MAX_EPOCHS + e], float_to_ordered(m));
+#pragma unroll
+    for (int of = 16; of > 0; of >>= 1) m = fmaxf(m, __shfl_xor_sync(FULLMASK, m, of));
+    if (lane == 0) atomicMax(&epmax[(int64_t)s * SGB_MAX_EPOCHS + e], float_to_ordered(m));
   }
   float *out = wave + lay[s].wave_off + C.ep_wave_off[e];
   if (kbase + SYNTH_SPT <= Ne) {
@@ -357,7 +317,7 @@ k_synth(const SynthTile *__restrict__ tiles, const sgb_syllable *__restrict__ sy
 }
 
 void launch_synth(const SynthTile *tiles, int n_tiles, const sgb_syllable *syl, const SylCtrl *ctrl,
-                  const SylLayout *lay, const Pools &P, const float2 *amp, float *wave, int *epmax,
+                  const SylLayout *lay, const Pools &P, const float4 *amp, float *wave, int *epmax,
                   cudaStream_t st) {
   if (n_tiles <= 0) return;
   k_synth<<<n_tiles, SYNTH_THREADS, 0, st>>>(tiles, syl, ctrl, lay, P, amp, wave, epmax);
