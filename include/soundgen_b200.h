@@ -202,6 +202,9 @@ int sgb_batch_artefacts(sgb_batch *b, int32_t syl, sgb_syl_artefacts *out);
  *        (2*nEpochs: zc1, zc2; 0 = NA) */
 int sgb_batch_artefact_ints(sgb_batch *b, int32_t syl, int which, int32_t *out, int32_t cap);
 int sgb_batch_pitch_per_gc(sgb_batch *b, int32_t syl, double *out, int32_t cap);
+/* Diagnostic: nine position-weighted checksums of the last run's intermediates (see engine.cu);
+ * identical inputs must give identical checksums on every run. */
+int sgb_batch_checksums(sgb_batch *b, uint64_t *out, int32_t cap);
 
 /* ------------------------------------------------------------------------- */
 /* Single-call interfaces                                                     */

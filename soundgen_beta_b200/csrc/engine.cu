@@ -139,9 +139,19 @@ struct sgb_batch {
   std::vector<int64_t> call_len, call_off;
   std::vector<int32_t> call_status;
   int64_t total_out = 0;
+  int64_t last_amp = 0, last_wave = 0, last_raw = 0, last_tiles = 0, last_sound = 0;
   bool keep_voiced = false;
   sgb_run_info info;
 };
+
+// position-weighted checksum of a word array (diagnostics)
+__global__ void k_checksum(const uint32_t *p, size_t n, unsigned long long *out) {
+  unsigned long long a = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    a += (unsigned long long)p[i] * (unsigned long long)((i % 1000003u) + 1u);
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, a);
+}
 
 extern "C" {
 
@@ -509,6 +519,7 @@ int sgb_batch_run(sgb_batch *b, sgb_run_info *info_out) {
   CK(cudaStreamSynchronize(st));
   CK(cudaGetLastError());
   const int64_t amp_total = tot[0], wave_total = tot[1], n_tiles = tot[2], raw_total = tot[3];
+  b->last_amp = amp_total; b->last_wave = wave_total; b->last_raw = raw_total; b->last_tiles = n_tiles;
   if (n_tiles > 2000000000LL) return fail(SGB_ERR_UNSUPPORTED, "batch too large: %lld synthesis tiles", (long long)n_tiles);
   CK(b->d_amp.ensure(8 * (size_t)std::max<int64_t>(amp_total, 1)));
   CK(b->d_amp32.ensure(16 * (size_t)std::max<int64_t>(amp_total, 1)));
@@ -737,6 +748,7 @@ int sgb_batch_run(sgb_batch *b, sgb_run_info *info_out) {
   CK(up(b->d_njobs, njobs.data(), sizeof(FftJob) * njobs.size()));
   CK(up(b->d_fsegs, fsegs.data(), sizeof(FftSeg) * fsegs.size()));
   CK(up(b->d_nsegs, nsegs.data(), sizeof(FftSeg) * nsegs.size()));
+  b->last_sound = sound_total;
   CK(cudaMemsetAsync(b->d_sound.p, 0, 4 * (size_t)(sound_total + 64), st));
   CK(cudaMemsetAsync(b->d_out.p, 0, 4 * (size_t)(out_total + 64), st));
   if (noise_total) CK(cudaMemsetAsync(b->d_noise_raw.p, 0, 4 * (size_t)(noise_total + 64), st));
@@ -857,6 +869,39 @@ static int fetch_common(sgb_batch *b, void *out, int64_t n, bool f64) {
 }
 int sgb_batch_fetch_f32(sgb_batch *b, float *out, int64_t n) { return fetch_common(b, out, n, false); }
 int sgb_batch_fetch_f64(sgb_batch *b, double *out, int64_t n) { return fetch_common(b, out, n, true); }
+
+// Diagnostic: position-weighted 64-bit checksums of the intermediates of the last run
+// (0 control pools, 1 spline pieces, 2 tiles, 3 FP32 amplitude table, 4 FP64 amplitude matrices,
+//  5 epoch waveforms, 6 composed syllables, 7 bout sounds, 8 output).  Used by the determinism tests.
+int sgb_batch_checksums(sgb_batch *b, uint64_t *out, int32_t cap) {
+  if (!b || !out || cap < 9) return fail(SGB_ERR_INVALID, "bad argument");
+  if (!b->have_run) return fail(SGB_ERR_STATE, "no completed run");
+  CK(cudaSetDevice(b->device));
+  DBuf d;
+  CK(d.ensure(8 * 16));
+  CK(cudaMemsetAsync(d.p, 0, 8 * 16, b->st));
+  unsigned long long *acc = d.as<unsigned long long>();
+  auto sum = [&](int slot, const void *p, size_t bytes) {
+    size_t n = bytes / 4;
+    if (!p || n == 0) return;
+    k_checksum<<<1024, 256, 0, b->st>>>((const uint32_t *)p, n, acc + slot);
+  };
+  const size_t g = (size_t)b->gc_total;
+  sum(0, b->pools.gcup, 4 * g); sum(0, b->pools.kt, 8 * g); sum(0, b->pools.ppg, 8 * g); sum(0, b->pools.phi, 8 * g);
+  sum(1, b->pools.pc, 8 * g * SYNTH_PC);
+  sum(2, b->d_tiles.p, sizeof(SynthTile) * (size_t)b->last_tiles);
+  sum(2, b->d_epmax.p, 4 * b->syls.size() * SGB_MAX_EPOCHS);
+  sum(3, b->d_amp32.p, 16 * (size_t)b->last_amp);
+  sum(4, b->d_amp.p, 8 * (size_t)b->last_amp);
+  sum(5, b->d_wave.p, 4 * (size_t)b->last_wave);
+  sum(6, b->d_raw.p, 4 * (size_t)b->last_raw);
+  sum(7, b->d_sound.p, 4 * (size_t)b->last_sound);
+  sum(8, b->d_out.p, 4 * (size_t)b->total_out);
+  CK(cudaMemcpyAsync(out, d.p, 8 * 9, cudaMemcpyDeviceToHost, b->st));
+  CK(cudaStreamSynchronize(b->st));
+  d.release();
+  return SGB_OK;
+}
 
 int sgb_batch_syllable_len(sgb_batch *b, int32_t syl, int64_t *out_len) {
   if (!b || !out_len) return fail(SGB_ERR_INVALID, "null argument");

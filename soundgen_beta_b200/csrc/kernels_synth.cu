@@ -19,6 +19,7 @@
 // feeds both packed operands of both pairs.  K = 128 / (cycles the warp touches, rounded up to a
 // power of two) so that a stage always fits SYNTH_STAGE entries.
 #include "engine.cuh"
+#include <cstdlib>
 
 #ifndef SYNTH_MIN_CTAS
 #define SYNTH_MIN_CTAS 6
@@ -82,7 +83,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
 __global__ void __launch_bounds__(SYNTH_THREADS, SYNTH_MIN_CTAS)
 k_synth(const SynthTile *__restrict__ tiles, const sgb_syllable *__restrict__ syl,
         const SylCtrl *__restrict__ ctrl, const SylLayout *__restrict__ lay, Pools P,
-        const float4 *__restrict__ amp, float *__restrict__ wave, int *__restrict__ epmax) {
+        const float4 *__restrict__ amp, float *__restrict__ wave, int *__restrict__ epmax, int force_mode) {
   __shared__ float4 sStage[SYNTH_WARPS][2][SYNTH_STAGE];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const SynthTile T = tiles[blockIdx.x];
@@ -165,6 +166,7 @@ k_synth(const SynthTile *__restrict__ tiles, const sgb_syllable *__restrict__ sy
     }
     okA = __all_sync(FULLMASK, okA); okP = __all_sync(FULLMASK, okP); okM = __all_sync(FULLMASK, okM);
     mode = okA ? 3 : (okP ? 1 : (okM ? 2 : 0));
+    if (force_mode >= 0) mode = force_mode;   // test hook (SGB_SYNTH_MODE): 0 is valid for every warp
   }
   // k0: delta = 2cos(theta) - 2 sigma (Reinsch) or 2cos(theta) (standard); k1: sigma; ec/es: cos, sin(theta)
   float2 w2[2], k0[2], k1[2], ec2[2], es2[2], rotc2[2], rots2[2];
@@ -320,7 +322,8 @@ void launch_synth(const SynthTile *tiles, int n_tiles, const sgb_syllable *syl, 
                   const SylLayout *lay, const Pools &P, const float4 *amp, float *wave, int *epmax,
                   cudaStream_t st) {
   if (n_tiles <= 0) return;
-  k_synth<<<n_tiles, SYNTH_THREADS, 0, st>>>(tiles, syl, ctrl, lay, P, amp, wave, epmax);
+  static const int force_mode = [] { const char *e = getenv("SGB_SYNTH_MODE"); return e ? atoi(e) : -1; }();
+  k_synth<<<n_tiles, SYNTH_THREADS, 0, st>>>(tiles, syl, ctrl, lay, P, amp, wave, epmax, force_mode == 0 ? 0 : -1);
 }
 
 // FP32 pipe peak: 8 independent FFMA2 dependency chains per thread.
