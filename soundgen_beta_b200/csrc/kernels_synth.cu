@@ -41,8 +41,8 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
 // Row recurrences for one packed pair (two samples).  The FMA pipe is limited by register-file reads
 // (measured, scripts/micro/rf_model.cu: an FFMA2 with three fresh register pairs takes 3.1 cycles, with
 // two 2.3, an FADD2 2.1), so each warp picks the cheapest form that is safe for ALL its lanes:
-//   mode 3  standard Clenshaw  b <- c2 b1 - b2 + a            (3 ops) every lane at least 0.057 cycles
-//           (20 degrees) away from theta = 0 and pi, where 2 cos(theta) carries the angle accurately;
+//   mode 3  standard Clenshaw  b <- c2 b1 - b2 + a            (3 ops) every lane at least 0.03 cycles
+//           (11 degrees) away from theta = 0 and pi, where 2 cos(theta) carries the angle accurately;
 //   mode 1/2 Reinsch, sigma = +1 / -1 for the whole warp       (4 ops, two of them adds): every lane
 //           within 3/8 cycle of the pole the form is built around;
 //   mode 0  Reinsch with a per-lane sigma                      (4 FMAs) anything else (a warp that spans
@@ -160,7 +160,7 @@ k_synth(const SynthTile *__restrict__ tiles, const sgb_syllable *__restrict__ sy
     for (int i = 0; i < SYNTH_SPT; i++) {
       const float xf = (float)xph[i];
       const float d0 = fminf(xf, 1.0f - xf), dpi = fabsf(xf - 0.5f);
-      okA = okA && (d0 >= 0.057f) && (dpi >= 0.057f);
+      okA = okA && (d0 >= 0.03f) && (dpi >= 0.03f);
       okP = okP && (d0 <= 0.375f);
       okM = okM && (dpi <= 0.375f);
     }
@@ -213,13 +213,22 @@ k_synth(const SynthTile *__restrict__ tiles, const sgb_syllable *__restrict__ sy
       const float ws = __shfl_sync(FULLMASK, w[2 * p + 1], src);
       const int gs = __shfl_sync(FULLMASK, gi[2 * p + 1], src);
       const float4 *col = ampE + (int64_t)(lo_w + gs) * J;
+      // every lane sums a contiguous run of rows with a float rotator started from an FP64-reduced phase
+      const int chunk = (J + 31) >> 5;
+      const int ja = lane * chunk + 1, jb = min(J, ja + chunk - 1);
       float part = 0.0f;
-      for (int j = 1 + lane; j <= J; j += 32) {
-        const float4 q = col[j - 1];
-        const float a_ = fmaf(ws, q.z, q.x);
-        double xj = (double)j * xs;
-        xj -= rint(xj);
-        part = fmaf(a_, sinpif(2.0f * (float)xj), part);
+      if (ja <= jb) {
+        float s1, c1, sj, cj;
+        sincospif(2.0f * (float)(xs - rint(xs)), &s1, &c1);     // e^{i theta}
+        double xa = (double)ja * xs;
+        xa -= rint(xa);
+        sincospif(2.0f * (float)xa, &sj, &cj);                  // e^{i ja theta}
+        for (int j = ja; j <= jb; j++) {
+          const float4 q = col[j - 1];
+          part = fmaf(fmaf(ws, q.z, q.x), sj, part);
+          const float cn = fmaf(cj, c1, -sj * s1), sn = fmaf(sj, c1, cj * s1);
+          cj = cn; sj = sn;
+        }
       }
 #pragma unroll
       for (int of = 16; of > 0; of >>= 1) part += __shfl_xor_sync(FULLMASK, part, of);
