@@ -14,6 +14,7 @@ One JSON line is printed by rank 0.
 from __future__ import annotations
 
 import argparse
+import faulthandler
 import json
 import os
 import subprocess
@@ -123,6 +124,7 @@ def run_reference(args, rank, world):
 
 
 def main():
+    faulthandler.dump_traceback_later(1500, exit=True)   # a stuck run reports where, instead of hanging the box
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=5)
@@ -132,7 +134,9 @@ def main():
     ap.add_argument('--batch', type=int, default=0, help='calls per GPU per step (default: the config size)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--pipeline', type=int, default=8,
-                    help='sub-batches (host threads / CUDA streams) of the end-to-end measurement')
+                    help='sub-batches (handles / CUDA streams) of the end-to-end measurement')
+    ap.add_argument('--runners', type=int, default=3,
+                    help='host threads that run kernels in the end-to-end pipeline (plus one uploader, one fetcher)')
     args = ap.parse_args()
     rank, world, local = env_int('RANK', 0), env_int('WORLD_SIZE', 1), env_int('LOCAL_RANK', 0)
     if args.impl == 'reference':
@@ -164,10 +168,7 @@ def main():
     for kw in calls:
         bb.add_soundgen(**kw)
     desc = bb.build()
-    for k in ('pitch', 'anchors', 'formants', 'z', 'u', 'pre'):   # pin the host pools
-        a = desc._keep[k]
-        if a.size:
-            L.sgb_pin(a.ctypes.data, a.nbytes)
+    sg.pin_desc(desc)   # page-lock the host pools
     bt = sg.Batch()
     bt.upload(desc)
 
@@ -200,8 +201,9 @@ def main():
     barrier()
     dt = time.perf_counter() - t0
     # ---- timed: end to end through the public batch API (H2D + run + D2H of every waveform) ----
-    # the batch is cut into `--pipeline` sub-batches driven by host threads on their own streams,
-    # so transfers of one sub-batch overlap the kernels of another (no work is skipped)
+    # the batch is cut into `--pipeline` sub-batches that flow through an upload / run / fetch software
+    # pipeline (one uploader, `--runners` kernel threads, one fetcher), so the transfers of one
+    # sub-batch overlap the kernels of others (no work is skipped)
     npipe = max(1, min(args.pipeline, len(calls)))
     subs = []
     for i in range(npipe):
@@ -210,18 +212,13 @@ def main():
         for kw in calls[lo:hi]:
             sb.add_soundgen(**kw)
         sd = sb.build()
-        for k in ('pitch', 'anchors', 'formants', 'z', 'u', 'pre'):
-            a = sd._keep[k]
-            if a.size:
-                L.sgb_pin(a.ctypes.data, a.nbytes)
+        sg.pin_desc(sd)
         subs.append(sd)
-    pipe = sg.PipelinedBatches(subs)
-    pipe.step()          # warm-up: sizes the pools of every handle, pins the outputs
-    pipe.step()
+    pipe = sg.PipelinedBatches(subs, runners=args.runners)
+    pipe.run_steps(2)    # warm-up: sizes the pools of every handle, pins the outputs
     barrier()
     t1 = time.perf_counter()
-    for _ in range(args.steps):
-        pipe.step()
+    pipe.run_steps(args.steps)
     barrier()
     dt_e2e = time.perf_counter() - t1
     d2h_bytes = sum(o.nbytes for o in pipe.outs)
@@ -291,7 +288,7 @@ def main():
                        'uniforms': 'float32'},
             'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': int(bb.h2d_bytes()),
                     'd2h_bytes_per_step': int(d2h_bytes), 'ms_per_step': dt_e2e / args.steps * 1e3,
-                    'pipeline': npipe},
+                    'pipeline': npipe, 'runners': args.runners},
             'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline,
             'roofline_filter': roof_filter, 'cpu_baseline': cpu,
             'stage_ms': {nm: float(v) for nm, v in zip(_abi.T_NAMES, stage_ms)},

@@ -2,7 +2,7 @@
 reference's own function names.  All compute goes through libsoundgen_b200.so (CUDA,
 sm_100a); importing this package never falls back to a CPU implementation."""
 from .api import (Batch, BatchBuilder, PipelinedBatches, SoundgenError, filter_sound, generateHarmonics, generateNoise,
-                  getRolloff, getSpectralEnvelope, soundgen, soundgen_batch)
+                  getRolloff, getSpectralEnvelope, pin_desc, soundgen, soundgen_batch)
 
 __all__ = ['Batch', 'BatchBuilder', 'PipelinedBatches', 'SoundgenError', 'filter_sound', 'generateHarmonics', 'generateNoise',
-           'getRolloff', 'getSpectralEnvelope', 'soundgen', 'soundgen_batch']
+           'getRolloff', 'getSpectralEnvelope', 'pin_desc', 'soundgen', 'soundgen_batch']

@@ -588,48 +588,129 @@ def soundgen_batch(list_of_kwargs, out_dtype=np.float32, u_dtype=np.float64):
 
 
 class PipelinedBatches:
-    """Several sub-batches, each on its own handle / CUDA stream and host thread, so that the
-    H2D copy of one sub-batch and the D2H read of another overlap the kernels of a third
-    (ctypes releases the GIL during the library calls).  Independent sounds need no ordering."""
+    """Several sub-batches, each with its own handle / CUDA stream, driven as a three-stage software
+    pipeline: one thread uploads (H2D copy engine), `runners` threads run the kernels (two, so that the
+    latency-bound control / joining stages of one sub-batch overlap the FMA-bound synthesis of another
+    and the host-side layout of one overlaps the kernels of the other), one thread fetches (D2H copy
+    engine).  ctypes releases the GIL during the library calls.  Independent sounds need no ordering,
+    so no work is skipped and nothing is shared between the sub-batches."""
 
-    def __init__(self, descs):
+    def __init__(self, descs, runners=2):
         self.descs = list(descs)
         self.batches = [Batch() for _ in self.descs]
         self.outs = [None] * len(self.descs)
+        self.runners = max(1, int(runners))
+        self.results = [None] * len(self.descs)
 
-    def _one(self, i, dtype):
+    def _fetch(self, i, dtype):
         bt = self.batches[i]
-        bt.upload(self.descs[i])
-        bt.run()
-        if self.outs[i] is None:
+        if self.outs[i] is None or self.outs[i].dtype != np.dtype(dtype):
             n = int(bt.lengths().sum())
             self.outs[i] = np.zeros(max(n, 1), dtype=dtype)
             _abi.load().sgb_pin(self.outs[i].ctypes.data, self.outs[i].nbytes)
         return bt.fetch(dtype, out=self.outs[i])
 
-    def step(self, dtype=np.float32):
-        """upload + run + fetch of every sub-batch; returns the per-call waveforms in order."""
+    def run_steps(self, nsteps=1, dtype=np.float32, transfer=True):
+        """`nsteps` passes over all sub-batches.  transfer=True: every pass uploads the inputs and
+        fetches every waveform (end to end); False: inputs stay resident, outputs stay on the device.
+        A sub-batch is re-uploaded for the next pass only after its previous results were fetched."""
+        import queue
         import threading
-        res = [None] * len(self.descs)
+        n = len(self.descs)
+        q_run, q_fetch = queue.Queue(), queue.Queue()
+        free = [threading.Semaphore(1) for _ in range(n)]     # handle i is idle
         err = []
+        abort = threading.Event()
 
-        def work(i):
-            try:
-                res[i] = self._one(i, dtype)
-            except Exception as e:   # surfaced to the caller below
-                err.append(e)
-        th = [threading.Thread(target=work, args=(i,)) for i in range(len(self.descs))]
+        class _Abort(Exception):
+            pass
+
+        def q_get(q):
+            while True:
+                try:
+                    return q.get(timeout=0.2)
+                except queue.Empty:
+                    if abort.is_set():
+                        raise _Abort()
+
+        def acquire(sem):
+            while not sem.acquire(timeout=0.2):
+                if abort.is_set():
+                    raise _Abort()
+
+        def guard(f):
+            def g():
+                try:
+                    f()
+                except _Abort:
+                    pass
+                except Exception as e:   # surfaced to the caller below; the other stages stop waiting
+                    err.append(e)
+                    abort.set()
+            return g
+
+        def uploader():
+            for s in range(nsteps):
+                for i in range(n):
+                    acquire(free[i])
+                    if transfer or self.batches[i].desc is None:
+                        self.batches[i].upload(self.descs[i])
+                    q_run.put(i)
+            for _ in range(self.runners):
+                q_run.put(None)
+
+        def runner():
+            while True:
+                i = q_get(q_run)
+                if i is None:
+                    q_fetch.put(None)
+                    return
+                self.batches[i].run()
+                q_fetch.put(i)
+
+        def fetcher():
+            done = 0
+            while done < self.runners:
+                i = q_get(q_fetch)
+                if i is None:
+                    done += 1
+                    continue
+                if transfer:
+                    self.results[i] = self._fetch(i, dtype)
+                free[i].release()
+
+        th = [threading.Thread(target=guard(uploader))] + \
+             [threading.Thread(target=guard(runner)) for _ in range(self.runners)] + \
+             [threading.Thread(target=guard(fetcher))]
         for t in th:
             t.start()
         for t in th:
             t.join()
         if err:
             raise err[0]
-        return [w for r in res for w in r]
+
+    def step(self, dtype=np.float32):
+        """upload + run + fetch of every sub-batch; returns the per-call waveforms in order."""
+        self.run_steps(1, dtype=dtype, transfer=True)
+        return [w for r in self.results for w in r]
 
     def close(self):
         for b in self.batches:
             b.close()
+        for o in self.outs:            # a registration must not outlive the array it covers
+            if o is not None:
+                _abi.load().sgb_unpin(o.ctypes.data)
+        self.outs = [None] * len(self.descs)
+
+
+def pin_desc(desc, pin=True):
+    """Page-locks (or releases) the host pools of a built batch description so that its uploads are
+    truly asynchronous.  Unpin before the description is garbage-collected."""
+    L = _abi.load()
+    for k in ('pitch', 'anchors', 'formants', 'z', 'u', 'pre'):
+        a = desc._keep[k]
+        if a.size:
+            _check(L.sgb_pin(a.ctypes.data, a.nbytes) if pin else L.sgb_unpin(a.ctypes.data))
 
 
 def generateHarmonics(pitch, attackLen=50, nonlinBalance=0, nonlinDep=0, jitterDep=0, jitterLen=1,

@@ -60,8 +60,10 @@ static int fail(int code, const char *fmt, ...) {
 #define CK(call)                                                                               \
   do {                                                                                         \
     cudaError_t e_ = (call);                                                                   \
-    if (e_ != cudaSuccess)                                                                     \
+    if (e_ != cudaSuccess) {                                                                   \
+      cudaGetLastError();   /* a reported error must not resurface in a later, unrelated call */ \
       return fail(SGB_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); \
+    }                                                                                          \
   } while (0)
 
 struct SylSummary { int32_t status, out_len, n_up, nGC; };
@@ -170,7 +172,9 @@ int sgb_set_device(int device) {
 
 int sgb_pin(void *ptr, int64_t bytes) {
   if (!ptr || bytes <= 0) return fail(SGB_ERR_INVALID, "bad buffer");
-  CK(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault));
+  cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return SGB_OK; }   // pinning is idempotent
+  CK(e);
   return SGB_OK;
 }
 int sgb_unpin(void *ptr) {
