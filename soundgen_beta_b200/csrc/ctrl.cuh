@@ -108,13 +108,15 @@ SGB_HD bool random_walk(int len, double rw_range, double rw_smoothing, bool tren
 
 // r[h, g] of getRolloff before normalisation (R/sourceSpectrum.R:84-143), in dB;
 // -INFINITY for discarded entries.  h is the ORIGINAL harmonic number (1-based).
-SGB_HD double rolloff_db_l(int h, double lg2h, double p, double ro, double roct, double rk, bool any_oct,
+// rolloff_db_l with the per-cycle slope (ro + rk * (p - baseline) / 1000) supplied by the caller
+// (K3 evaluates it once per column): the same operations in the same order.
+SGB_HD double rolloff_db_s(int h, double lg2h, double p, double slope, double roct, bool any_oct,
                            double rolloffParab, int parab_harm, double pa, double pb, double pc,
                            double baseline, double throwaway, double samplingRate) {
   double hd = (double)h;
   double delta = 0.0;
   if (any_oct && h >= 2) delta = roct * (p * hd - baseline) / 1000.0;
-  double r = ((ro + rk * (p - baseline) / 1000.0) * lg2h) + delta;
+  double r = (slope * lg2h) + delta;
   if (hd * p >= samplingRate / 2.0) r = -INFINITY;
   if (rolloffParab != 0.0) {
     if (parab_harm < 3) {
@@ -125,6 +127,12 @@ SGB_HD double rolloff_db_l(int h, double lg2h, double p, double ro, double roct,
   }
   if (r < throwaway) r = -INFINITY;
   return r;
+}
+SGB_HD double rolloff_db_l(int h, double lg2h, double p, double ro, double roct, double rk, bool any_oct,
+                           double rolloffParab, int parab_harm, double pa, double pb, double pc,
+                           double baseline, double throwaway, double samplingRate) {
+  return rolloff_db_s(h, lg2h, p, ro + rk * (p - baseline) / 1000.0, roct, any_oct, rolloffParab, parab_harm,
+                      pa, pb, pc, baseline, throwaway, samplingRate);
 }
 
 SGB_HD double rolloff_db(int h, double p, double ro, double roct, double rk, bool any_oct,

@@ -55,12 +55,30 @@ k_control(const sgb_syllable *syl, int S, const double *pitch, const double *anc
   const bool ao = C.any_oct != 0;
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
     if (!use_tab) { A.colmax[g] = ctrl_colmax(sp, A, C, g); continue; }
+    // max over h of r(h, g) (sourceSpectrum.R:146).  Past the parabola r is slope*log2(h) + oct*h + const:
+    // monotone or with a single stationary point, so the maximum sits at the first harmonics, at the
+    // last harmonic below Nyquist or next to the stationary point; those candidates are evaluated
+    // with the exact expression (dead entries are -Inf and never win).
     double m = -INFINITY;
     const double pg = A.ppg[g], rog = A.ro[g], roctg = A.roct[g], rkg = A.rk[g];
-    for (int h = 1; h <= nH; h++) {
+    auto probe = [&](int h) {
+      if (h < 1 || h > nH) return;
       double r = rolloff_db_l(h, lgt[h - 1], pg, rog, roctg, rkg, ao, sp.rolloffParab, C.parab_harm, C.parab_a,
                               C.parab_b, C.parab_c, 200.0, sp.throwaway, sp.samplingRate);
       if (r > m) m = r;
+    };
+    const int hhead = min(nH, max(C.parab_harm, 2) + 1);
+    for (int h = 1; h <= hhead; h++) probe(h);
+    int hl = (int)fmin((double)nH, floor(sp.samplingRate / 2.0 / pg)) + 1;      // last harmonic below Nyquist
+    while (hl > 1 && (double)hl * pg >= sp.samplingRate / 2.0) hl--;
+    probe(hl); probe(hl - 1);
+    if (ao && roctg != 0.0) {
+      const double slope = rog + rkg * (pg - 200.0) / 1000.0;
+      const double hs = -slope * 1000.0 / (roctg * pg * 0.6931471805599453);    // d/dh = 0
+      if (hs > 1.0 && hs < (double)nH + 1.0) {
+        const int h0 = (int)floor(hs);
+        for (int h = h0 - 1; h <= h0 + 2; h++) probe(h);
+      }
     }
     A.colmax[g] = m;
   }
@@ -244,8 +262,8 @@ k_amp(const sgb_syllable *syl, int S, const SylCtrl *ctrl, const SylLayout *lay,
         }
         for (int g = ga; g < gx; g++) {
           const int gi = g - ga;
-          const double pg = A.ppg[g], rog = A.ro[g], roctg = A.roct[g], rkg = A.rk[g], cmg = A.colmax[g],
-                       shg = A.shimmer[g];
+          const double pg = A.ppg[g], roctg = A.roct[g], cmg = A.colmax[g], shg = A.shimmer[g];
+          const double slope = A.ro[g] + A.rk[g] * (pg - 200.0) / 1000.0;   // column term of rolloff_db_l
           double *oc = oe + (int64_t)(g - g0) * rows;
           float4 *oc32 = oe32 + (int64_t)(g - 1 - g0) * rows;
 #pragma unroll
@@ -257,7 +275,7 @@ k_amp(const sgb_syllable *syl, int S, const SylCtrl *ctrl, const SylLayout *lay,
               v = ampl_exact(sp, A, C, e, j, g);
             } else {
               if (rs_[i] == 0) {
-                double r = rolloff_db_l(rh_[i], lg[i], pg, rog, roctg, rkg, C.any_oct != 0, sp.rolloffParab,
+                double r = rolloff_db_s(rh_[i], lg[i], pg, slope, roctg, C.any_oct != 0, sp.rolloffParab,
                                         C.parab_harm, C.parab_a, C.parab_b, C.parab_c, 200.0, sp.throwaway,
                                         sp.samplingRate);
                 v = exp2((r - cmg) / 10.0) * shg;
