@@ -88,6 +88,9 @@ def oracle_one(kw):
     kw = dict(kw)
     z = kw.pop('z', None)
     u = kw.pop('u', None)
+    if 'seed' in kw:      # cfg4: generous per-call streams (the oracle consumes what it needs)
+        r = np.random.default_rng(kw.pop('seed'))
+        z, u = [r.standard_normal(200000)], [r.random(6000000)]
     rng = so.RStream(z=np.concatenate(z) if z else None, u=np.concatenate(u) if u else None)
     y = osg(rng=rng, **kw)
     return y.size / float(kw.get('samplingRate', 16000))
@@ -101,6 +104,8 @@ def run_reference(args, rank, world):
     from soundgen_beta_b200 import workloads
     cores = os.cpu_count() or 1
     per_step = max(cores, 2 * cores if args.config in (1,) else cores)
+    if args.config == 4:
+        per_step = max(per_step, 33)
     calls = workloads.CONFIGS[args.config](n=per_step) if args.config != 0 else workloads.config0() * per_step
     with mp.Pool(cores) as pool:
         for _ in range(args.warmup):
@@ -158,15 +163,24 @@ def main():
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     assert L.sgb_set_device(local) == 0
 
-    sizes = {0: 1, 1: 1024, 2: 4096, 3: 8192}
+    sizes = {0: 1, 1: 1024, 2: 4096, 3: 8192, 4: max(1, 65536 // world)}   # cfg4: one sweep shared by the ranks
     n = args.batch or sizes[args.config]
     gen = workloads.CONFIGS[args.config]
     from soundgen_beta_b200 import sharding
     calls = gen(n=n, seed=sharding.shard_seed(args.config, rank)) if args.config != 0 else workloads.config0()
-    sr = workloads.SAMPLING_RATE[args.config]
+    srs = np.array([float(kw.get('samplingRate', 16000)) for kw in calls])
+
+    def add_calls(builder, some):
+        for kw in some:
+            if 'seed' in kw:     # cfg4: the call's random streams are drawn on demand from its own seed
+                kw = dict(kw)
+                z, u = workloads.streams(kw.pop('seed'), np.float32)
+                builder.add_soundgen(z=z, u=u, **kw)
+            else:
+                builder.add_soundgen(**kw)
+
     bb = sg.BatchBuilder(u_dtype=np.float32)   # uniforms travel as float32 (halves the PCIe bytes)
-    for kw in calls:
-        bb.add_soundgen(**kw)
+    add_calls(bb, calls)
     desc = bb.build()
     sg.pin_desc(desc)   # page-lock the host pools
     bt = sg.Batch()
@@ -181,7 +195,7 @@ def main():
     for _ in range(max(args.warmup, 1)):
         info = bt.run()
     lens = bt.lengths()
-    audio_s = float(lens.sum()) / sr
+    audio_s = float(np.sum(lens / srs))
     out = np.zeros(int(lens.sum()), dtype=np.float32)
     L.sgb_pin(out.ctypes.data, out.nbytes)
     bt.fetch(np.float32, out=out)
@@ -212,8 +226,7 @@ def main():
     for i in range(npipe):
         lo, hi = sharding.shard_range(len(calls), i, npipe)
         sb = sg.BatchBuilder(u_dtype=np.float32)
-        for kw in calls[lo:hi]:
-            sb.add_soundgen(**kw)
+        add_calls(sb, calls[lo:hi])
         sd = sb.build()
         sg.pin_desc(sd)
         subs.append(sd)
@@ -275,7 +288,7 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        m = {0: 8, 1: 24, 2: 4, 3: 6}[args.config]
+        m = {0: 8, 1: 24, 2: 4, 3: 6, 4: 33}[args.config]
         sample = (calls * m)[:m]
         tc = time.perf_counter()
         a = sum(oracle_one(kw) for kw in sample)

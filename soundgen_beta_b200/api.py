@@ -113,7 +113,7 @@ class BatchBuilder:
 
     def add_envelope(self, formants, formantDep=1, rolloffLip=6, mouthAnchors=None, mouthOpenThres=0,
                      openMouthBoost=0, vocalTract=None, samplingRate=16000, speedSound=35400,
-                     smoothLinearFactor=1, nc_fixed=0, tracks=None):
+                     smoothLinearFactor=1, nc_fixed=0, tracks=None, contour_method='loess'):
         """Registers one getSpectralEnvelope() specification; resolves the vocalTract /
         schwa defaults of R/sourceSpectrum.R:294-315 (argument munging, host side)."""
         fl = _formant_list(formants)
@@ -144,8 +144,9 @@ class BatchBuilder:
                 self.n_formants += f.shape[0]
         ma = host.as_anchors(mouthAnchors)
         if ma is not None and not np.any(np.isnan(ma[1])):
-            if 3 <= ma[0].size <= 10:
-                raise NotImplementedError('mouthAnchors with 3-10 anchors use loess in the reference')
+            if 3 <= ma[0].size <= 10 and contour_method != 'spline':
+                raise NotImplementedError('mouthAnchors with 3-10 anchors use loess in the reference '
+                                          "(pass contour_method='spline')")
             e.mouth_off, e.mouth_n = self._add_anchors(ma)
         else:
             e.mouth_n = 0
@@ -194,7 +195,8 @@ class BatchBuilder:
         return len(self.syls) - 1
 
     def add_noise(self, length, noiseAnchors, u, rolloffNoise=-6, attackLen=10, windowLength_points=1024,
-                  samplingRate=16000, overlap=75, env_id=-1, insertion=1, mix=0, strength=None):
+                  samplingRate=16000, overlap=75, env_id=-1, insertion=1, mix=0, strength=None,
+                  contour_method='loess'):
         n = Noise()
         n.len = int(length)
         n.insertion = int(insertion)
@@ -207,9 +209,9 @@ class BatchBuilder:
             n.strength_pre_off = self._add_pre(strength)
             n.anchor_n = 0
         else:
-            if 3 <= an[0].size <= 10:
-                raise NotImplementedError('noiseAnchors with 3-10 anchors use loess in the reference: '
-                                          'pass a pre-evaluated `strength` contour')
+            if 3 <= an[0].size <= 10 and contour_method != 'spline':
+                raise NotImplementedError('noiseAnchors with 3-10 anchors use loess in the reference: pass a '
+                                          "pre-evaluated `strength` contour or contour_method='spline'")
             n.anchor_off, n.anchor_n = self._add_anchors(an)
         n.env_id = int(env_id)
         n.rolloffNoise, n.attackLen = float(rolloffNoise), float(attackLen)
@@ -329,8 +331,10 @@ class BatchBuilder:
                 t = t / np.max(t)
             pitchAnchors = (t, pitchAnchors[1])
         has_noise = noiseAnchors is not None and np.sum(noiseAnchors[1] > throwaway) > 0
-        z = list(z) if isinstance(z, (list, tuple)) else ([z] if z is not None else [])
-        u = list(u) if isinstance(u, (list, tuple)) else ([u] if u is not None else [])
+        z_fn = z if callable(z) else None    # z(n) / u(n): draw n values when a syllable / noise segment needs them
+        u_fn = u if callable(u) else None
+        z = [] if z_fn else (list(z) if isinstance(z, (list, tuple)) else ([z] if z is not None else []))
+        u = [] if u_fn else (list(u) if isinstance(u, (list, tuple)) else ([u] if u is not None else []))
         zi = ui = si = 0
         # main vocal-tract filter (soundgen.R:751-775)
         moving = formants is not None and max(f.shape[0] for f in formants) > 1
@@ -338,9 +342,10 @@ class BatchBuilder:
             moving = True
         env_main = self.add_envelope(formants, formantDep=formantDep, rolloffLip=rolloffLip,
                                      mouthAnchors=mouthAnchors, vocalTract=vocalTract,
-                                     samplingRate=samplingRate)
-        if amplAnchorsGlobal is not None and 3 <= amplAnchorsGlobal[0].size <= 10:
-            raise NotImplementedError('amplAnchorsGlobal with 3-10 anchors use loess in the reference')
+                                     samplingRate=samplingRate, contour_method=contour_method)
+        if amplAnchorsGlobal is not None and 3 <= amplAnchorsGlobal[0].size <= 10 and contour_method != 'spline':
+            raise NotImplementedError('amplAnchorsGlobal with 3-10 anchors use loess in the reference '
+                                      "(pass contour_method='spline')")
         bout0 = len(self.bouts)
         n_sil = int(host.rint(samplingRate / 1000 * addSilence)) if addSilence is not None else 0
         for b in range(repeatBout):   # :482
@@ -380,7 +385,7 @@ class BatchBuilder:
                                                  thisIsPitch=True, method=contour_method,
                                                  valueFloor=pitchFloor, valueCeiling=pitchCeiling)
                     pc = pc * pitchDeltas[s]
-                    zs = z[zi] if zi < len(z) else None
+                    zs = z_fn(2 * pc.size + 64) if z_fn else (z[zi] if zi < len(z) else None)
                     zi += 1
                     self.add_syllable(pc, z=zs, amplAnchors=amplAnchors, pause_after=pause,
                                       contour_method=contour_method, **pars)
@@ -395,13 +400,18 @@ class BatchBuilder:
                         nInt = int(host.rint(rng_t / 10))   # :662-666 (always "moving", see oracle note)
                         env_n = self.add_envelope(formantsNoise, formantDep=formantDep, rolloffLip=rolloffLip,
                                                   mouthAnchors=mouthAnchors, vocalTract=vocalTract,
-                                                  samplingRate=samplingRate, nc_fixed=nInt)
-                    if ui >= len(u):
+                                                  samplingRate=samplingRate, nc_fixed=nInt,
+                                                  contour_method=contour_method)
+                    if u_fn:
+                        u_seg = u_fn(self.noise_uniform_count(ulen, wl_points, overlap))
+                    elif ui >= len(u):
                         raise ValueError('soundgen(): a uniform buffer `u` is needed for each noise segment')
-                    self.add_noise(ulen, (t, noiseAnchors[1]), u[ui], rolloffNoise=rolloffNoise,
+                    else:
+                        u_seg = u[ui]
+                    self.add_noise(ulen, (t, noiseAnchors[1]), u_seg, rolloffNoise=rolloffNoise,
                                    attackLen=attackLen, windowLength_points=wl_points, samplingRate=samplingRate,
                                    overlap=overlap, env_id=env_n, insertion=int(startIdx[s]),
-                                   mix=0 if formantsNoise is None else 1)
+                                   mix=0 if formantsNoise is None else 1, contour_method=contour_method)
                     ui += 1
             ag = None
             if amplAnchorsGlobal is not None and np.sum(amplAnchorsGlobal[1] < -throwaway) > 0:   # :721-724

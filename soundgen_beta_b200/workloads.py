@@ -98,9 +98,34 @@ def config3(n=8192, seed=20260003):
     return out
 
 
-CONFIGS = {0: config0, 1: config1, 2: config2, 3: config3}
+def config4(n=65536, seed=20260004):
+    """datagen sweep: call i uses preset (i mod 33) in the order of R/presets.R.  In the reference each
+    call runs with its preset's own temperature under set.seed(i); that host-side stochastic stage needs
+    R's RNG, so here temperature = 0 and the anchors with 3-10 points are evaluated with the FMM spline
+    instead of loess (contour_method='spline').  What still varies from call to call are the random
+    streams (jitter / shimmer normals, noise uniforms), drawn per call from PCG64(seed + i)."""
+    from . import presets
+    ps = presets.load()
+    out = []
+    for i in range(n):
+        _, _, kw = ps[i % len(ps)]
+        kw = dict(kw)
+        kw.update(temperature=0, contour_method='spline', seed=seed + i)
+        out.append(kw)
+    return out
+
+
+def streams(seed, dtype=np.float64):
+    """(z, u) callables for soundgen(): independent PCG64 streams of normals and uniforms."""
+    rz = np.random.default_rng([seed, 1])
+    ru = np.random.default_rng([seed, 2])
+    return (lambda n: rz.standard_normal(n)), (lambda n: ru.random(n).astype(dtype, copy=False))
+
+
+CONFIGS = {0: config0, 1: config1, 2: config2, 3: config3, 4: config4}
 NAMES = {0: 'cfg0 soundgen() defaults, 1 x 1000 ms @ 16 kHz',
          1: 'cfg1 voiced batch, 1024 x 500 ms @ 44.1 kHz',
          2: 'cfg2 noise-heavy batch, 4096 x 2 s @ 22.05 kHz',
-         3: 'cfg3 harmonic-rich batch, 8192 x 1 s @ 48 kHz'}
-SAMPLING_RATE = {0: 16000, 1: 44100, 2: 22050, 3: 48000}
+         3: 'cfg3 harmonic-rich batch, 8192 x 1 s @ 48 kHz',
+         4: 'cfg4 datagen sweep over the 33 bundled presets (temperature 0, spline contours)'}
+SAMPLING_RATE = {0: 16000, 1: 44100, 2: 22050, 3: 48000, 4: None}   # cfg4: per call
