@@ -27,6 +27,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+T_START = time.perf_counter()
 METRIC = 'audio_seconds_synthesised_per_second'
 UNIT = 'audio-s/s'
 
@@ -129,7 +130,6 @@ def run_reference(args, rank, world):
 
 
 def main():
-    faulthandler.dump_traceback_later(1500, exit=True)   # a stuck run reports where, instead of hanging the box
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=5)
@@ -142,7 +142,9 @@ def main():
                     help='sub-batches (handles / CUDA streams) of the end-to-end measurement')
     ap.add_argument('--runners', type=int, default=3,
                     help='host threads that run kernels in the end-to-end pipeline (plus one uploader, one fetcher)')
+    ap.add_argument('--watchdog', type=int, default=1500, help='seconds after which a stuck run dumps its stacks and exits')
     args = ap.parse_args()
+    faulthandler.dump_traceback_later(args.watchdog, exit=True)   # a stuck run reports where, instead of hanging the box
     rank, world, local = env_int('RANK', 0), env_int('WORLD_SIZE', 1), env_int('LOCAL_RANK', 0)
     if args.impl == 'reference':
         run_reference(args, rank, world)
@@ -231,12 +233,22 @@ def main():
         sg.pin_desc(sd)
         subs.append(sd)
     pipe = sg.PipelinedBatches(subs, runners=args.runners)
+
+    def report_stuck():   # fires shortly before the watchdog: where is every handle waiting?
+        for i, hb in enumerate([bt] + pipe.batches):
+            st = np.zeros(12, dtype=np.int32)
+            L.sgb_batch_debug_state(hb.h, st.ctypes.data, 12)
+            print('handle %d: wait %d, stage events done %s' % (i, st[0], st[1:].tolist()), file=sys.stderr, flush=True)
+    stuck = threading.Timer(max(3, args.watchdog - 8 - (time.perf_counter() - T_START)), report_stuck)
+    stuck.daemon = True
+    stuck.start()
     pipe.run_steps(2)    # warm-up: sizes the pools of every handle, pins the outputs
     barrier()
     t1 = time.perf_counter()
     pipe.run_steps(args.steps)
     barrier()
     dt_e2e = time.perf_counter() - t1
+    stuck.cancel()
     d2h_bytes = sum(o.nbytes for o in pipe.outs)
     clocks = sampler.stop()
     stage_ms /= args.steps

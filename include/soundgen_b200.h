@@ -205,6 +205,9 @@ int sgb_batch_pitch_per_gc(sgb_batch *b, int32_t syl, double *out, int32_t cap);
 /* Diagnostic: nine position-weighted checksums of the last run's intermediates (see engine.cu);
  * identical inputs must give identical checksums on every run. */
 int sgb_batch_checksums(sgb_batch *b, uint64_t *out, int32_t cap);
+/* Diagnostic for a stuck run, callable from another thread: out[0] = the wait the handle's host thread is
+ * in, out[1..11] = completion of the stage events of the current run (see engine.cu). */
+int sgb_batch_debug_state(sgb_batch *b, int32_t *out, int32_t cap);
 
 /* ------------------------------------------------------------------------- */
 /* Single-call interfaces                                                     */

@@ -89,7 +89,7 @@ EXPORTS = ['sgb_version', 'sgb_last_error', 'sgb_device_count', 'sgb_set_device'
            'sgb_batch_create', 'sgb_batch_destroy', 'sgb_batch_upload', 'sgb_batch_run',
            'sgb_batch_lengths', 'sgb_batch_fetch_f32', 'sgb_batch_fetch_f64', 'sgb_batch_status',
            'sgb_batch_syllable_len', 'sgb_batch_syllable_fetch', 'sgb_batch_noise_fetch',
-           'sgb_batch_artefacts', 'sgb_batch_artefact_ints', 'sgb_batch_pitch_per_gc', 'sgb_batch_checksums',
+           'sgb_batch_artefacts', 'sgb_batch_artefact_ints', 'sgb_batch_pitch_per_gc', 'sgb_batch_checksums', 'sgb_batch_debug_state',
            'sgb_get_rolloff', 'sgb_get_spectral_envelope', 'sgb_filter_len', 'sgb_filter']
 
 
@@ -136,6 +136,7 @@ def load():
     L.sgb_batch_artefact_ints.argtypes = [vp, i32, C.c_int, vp, i32]
     L.sgb_batch_pitch_per_gc.argtypes = [vp, i32, vp, i32]
     L.sgb_batch_checksums.argtypes = [vp, vp, i32]
+    L.sgb_batch_debug_state.argtypes = [vp, vp, i32]
     L.sgb_get_rolloff.argtypes = [vp, i32, i32, vp, i32, vp, i32, vp, i32, f64, f64, f64, f64,
                                   f64, f64, vp, C.POINTER(i32)]
     L.sgb_get_spectral_envelope.argtypes = [i32, i32, C.POINTER(Envelope), vp, vp, vp, vp]

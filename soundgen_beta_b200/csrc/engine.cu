@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "engine.cuh"
+#include <cstdlib>
 
 // ---- kernel launchers defined in the other translation units ----
 void launch_control(const sgb_syllable *, int, const double *, const double *, const double *, const Pools &,
@@ -46,6 +47,8 @@ void launch_sound_mix(const sgb_bout *, int, const BoutLayout *, const sgb_noise
 void launch_finalize(int, const sgb_bout *, int, const BoutLayout *, const sgb_noise *, const NoiseLayout *,
                      const float *, const float *, const float *, const int *, void *, int, cudaStream_t);
 
+int stft_timeout_flag();
+int *compose_debug_buffer();
 // ------------------------------------------------------------------ errors ---
 static thread_local std::string g_err;
 static int fail(int code, const char *fmt, ...) {
@@ -55,6 +58,20 @@ static int fail(int code, const char *fmt, ...) {
   vsnprintf(buf, sizeof buf, fmt, ap);
   va_end(ap);
   g_err = buf;
+  if (code == SGB_ERR_CUDA) {   // a trapped search left its diagnostics in mapped host memory
+    int *d = compose_debug_buffer();
+    if (d && d[0] > 0) {
+      char t[160];
+      int n = d[0] < 400 ? d[0] : 400;
+      snprintf(t, sizeof t, " | k_compose diagnostics: %d records", d[0]);
+      g_err += t;
+      for (int i = 0; i < n && i < 24; i++) {
+        int *r = d + 8 + i * 10;
+        snprintf(t, sizeof t, " [loop %d syl %d ep %d tid %d: %d %d %d %d %d]", r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7], r[8]);
+        g_err += t;
+      }
+    }
+  }
   return code;
 }
 #define CK(call)                                                                               \
@@ -142,9 +159,21 @@ struct sgb_batch {
   std::vector<int32_t> call_status;
   int64_t total_out = 0;
   int64_t last_amp = 0, last_wave = 0, last_raw = 0, last_tiles = 0, last_sound = 0;
+  volatile int where = 0;   // progress marker for sgb_batch_debug_state: which wait the host thread is in
+  volatile int reached[16] = {0};   // SGB_TRACE=1: stage events the stream has passed (set by host callbacks)
+  struct Mark { volatile int *dst; } marks[16];
   bool keep_voiced = false;
   sgb_run_info info;
 };
+
+// SGB_TRACE=1: a host callback after every stage records how far the stream got, readable without any
+// CUDA call (sgb_batch_debug_state) when a run is stuck.
+static const bool g_trace = getenv("SGB_TRACE") != nullptr;
+static void CUDART_CB trace_cb(void *p) { *reinterpret_cast<volatile int *>(p) = 1; }
+static void trace_mark(sgb_batch *b, int i) {
+  if (!g_trace) return;
+  cudaLaunchHostFunc(b->st, trace_cb, (void *)&b->reached[i]);
+}
 
 // position-weighted checksum of a word array (diagnostics)
 __global__ void k_checksum(const uint32_t *p, size_t n, unsigned long long *out) {
@@ -212,6 +241,7 @@ int sgb_measure_fp32_peak(double *out_tflops) {
 }
 
 int sgb_batch_create(sgb_batch **out) {
+  compose_debug_buffer();
   if (!out) return fail(SGB_ERR_INVALID, "null out pointer");
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n < 1)
@@ -358,7 +388,9 @@ int sgb_batch_upload(sgb_batch *b, const sgb_batch_desc *D) {
   if ((rc = upload_array(b, b->d_gc_off, gc_off.data(), 8 * (size_t)(S + 1)))) return rc;
   if ((rc = upload_array(b, b->d_h_off, h_off.data(), 8 * (size_t)(S + 1)))) return rc;
   CK(cudaEventRecord(b->ev[SGB_T_COUNT + 1], b->st));
+  b->where = 10;
   CK(cudaStreamSynchronize(b->st));   // gc_off / h_off are stack vectors
+  b->where = 0;
   CK(cudaEventElapsedTime(&b->info.ms[SGB_T_H2D], b->ev[SGB_T_COUNT], b->ev[SGB_T_COUNT + 1]));
 
   CK(b->p_pitch_w.ensure(8 * (size_t)std::max<int64_t>(1, D->n_pitch)));
@@ -510,7 +542,8 @@ int sgb_batch_run(sgb_batch *b, sgb_run_info *info_out) {
   int64_t *d_tot = b->d_totals.as<int64_t>();
   cudaEvent_t *ev = b->ev;
   // events: e[0] start, then one after each stage
-  CK(cudaEventRecord(ev[0], st));
+  if (g_trace) for (int i = 0; i < 16; i++) b->reached[i] = 0;
+  CK(cudaEventRecord(ev[0], st)); trace_mark(b, 0);
 
   // ---- K0 control + size scan ----
   CK(cudaMemsetAsync(d_tot, 0, 64, st));
@@ -519,8 +552,10 @@ int sgb_batch_run(sgb_batch *b, sgb_run_info *info_out) {
   launches += 2;
   int64_t tot[8];
   CK(cudaMemcpyAsync(tot, d_tot, 64, cudaMemcpyDeviceToHost, st));
-  CK(cudaEventRecord(ev[1], st));
+  CK(cudaEventRecord(ev[1], st)); trace_mark(b, 1);
+  b->where = 1;
   CK(cudaStreamSynchronize(st));
+  b->where = 0;
   CK(cudaGetLastError());
   const int64_t amp_total = tot[0], wave_total = tot[1], n_tiles = tot[2], raw_total = tot[3];
   b->last_amp = amp_total; b->last_wave = wave_total; b->last_raw = raw_total; b->last_tiles = n_tiles;
@@ -535,13 +570,13 @@ int sgb_batch_run(sgb_batch *b, sgb_run_info *info_out) {
   launch_tiles_amp(d_syl, S, d_ctrl, d_lay, P, b->d_tiles.as<SynthTile>(), d_tot, b->d_amp.as<double>(),
                    b->d_amp32.as<float4>(), st);
   launches += 2;
-  CK(cudaEventRecord(ev[2], st));
+  CK(cudaEventRecord(ev[2], st)); trace_mark(b, 2);
   // ---- K1 synthesis ----
   CK(cudaMemsetAsync(b->d_epmax.p, 0, 4 * (size_t)S * SGB_MAX_EPOCHS, st));
   launch_synth(b->d_tiles.as<SynthTile>(), (int)n_tiles, d_syl, d_ctrl, d_lay, P, b->d_amp32.as<float4>(),
                b->d_wave.as<float>(), b->d_epmax.as<int>(), st);
   if (n_tiles > 0) launches++;
-  CK(cudaEventRecord(ev[3], st));
+  CK(cudaEventRecord(ev[3], st)); trace_mark(b, 3);
   // ---- K6 compose ----
   launch_compose(d_syl, S, d_ctrl, d_lay, P, b->d_amp.as<double>(), b->d_wave.as<float>(), b->d_raw.as<float>(),
                  b->d_anchors.as<double>(), b->d_pitch.as<double>(), b->d_epmax.as<int>(), st);
@@ -552,8 +587,10 @@ int sgb_batch_run(sgb_batch *b, sgb_run_info *info_out) {
   CK(cudaMemcpyAsync(b->summary.data(), b->d_summary.p, sizeof(SylSummary) * (size_t)S, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(b->lay_host.data(), d_lay, sizeof(SylLayout) * (size_t)S, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(tot, d_tot, 64, cudaMemcpyDeviceToHost, st));
-  CK(cudaEventRecord(ev[4], st));
+  CK(cudaEventRecord(ev[4], st)); trace_mark(b, 4);
+  b->where = 2;
   CK(cudaStreamSynchronize(st));
+  b->where = 0;
   CK(cudaGetLastError());
   info.synth_partials = tot[4];
   info.synth_samples = tot[5];
@@ -768,7 +805,7 @@ int sgb_batch_run(sgb_batch *b, sgb_run_info *info_out) {
     CK(b->d_voiced.ensure(4 * (size_t)(sound_total + 64)));
     CK(cudaMemcpyAsync(b->d_voiced.p, b->d_sound.p, 4 * (size_t)(sound_total + 64), cudaMemcpyDeviceToDevice, st));
   }
-  CK(cudaEventRecord(ev[5], st));   // assemble (part 1)
+  CK(cudaEventRecord(ev[5], st)); trace_mark(b, 5);   // assemble (part 1)
   // ---- K4 envelopes (bouts + noises) ----
   int max_nc = 0;
   for (auto &I : envinst) max_nc = std::max(max_nc, I.nc);
@@ -776,7 +813,7 @@ int sgb_batch_run(sgb_batch *b, sgb_run_info *info_out) {
                       b->d_frefs.as<sgb_formant_ref>(), b->d_formants.as<double>(), b->d_anchors.as<double>(),
                       b->d_env.as<float>(), st);
   if (!envinst.empty()) launches++;
-  CK(cudaEventRecord(ev[6], st));
+  CK(cudaEventRecord(ev[6], st)); trace_mark(b, 6);
   // ---- K5 noise ----
   if (!nsegs.empty()) {
     for (auto &gr : ngroups) {
@@ -792,13 +829,13 @@ int sgb_batch_run(sgb_batch *b, sgb_run_info *info_out) {
                        b->d_noise_fin.as<float>(), 16, st);
     launches += 1;
   }
-  CK(cudaEventRecord(ev[7], st));
+  CK(cudaEventRecord(ev[7], st)); trace_mark(b, 7);
   // ---- sound = voiced + breathing, global envelope ----
   launch_sound_mix(b->d_bouts.as<sgb_bout>(), NB, b->d_bl.as<BoutLayout>(), b->d_noises.as<sgb_noise>(),
                    b->d_nl.as<NoiseLayout>(), b->d_anchors.as<double>(), b->d_noise_fin.as<float>(),
                    b->d_sound.as<float>(), chunks, st);
   launches++;
-  CK(cudaEventRecord(ev[8], st));
+  CK(cudaEventRecord(ev[8], st)); trace_mark(b, 8);
   // ---- K2 filter ----
   for (auto &gr : fgroups) {
     if (gr.smem > 226 * 1024) return fail(SGB_ERR_UNSUPPORTED, "window too long for shared memory (%zu bytes)", gr.smem);
@@ -807,15 +844,18 @@ int sgb_batch_run(sgb_batch *b, sgb_run_info *info_out) {
                    nullptr, b->d_env.as<float>(), b->d_filt.as<float>(), b->d_max.as<int>(), gr.smem, st));
     launches++;
   }
-  CK(cudaEventRecord(ev[9], st));
+  CK(cudaEventRecord(ev[9], st)); trace_mark(b, 9);
   // ---- normalise, post-filter noise, AM, silences ----
   launch_finalize(0, b->d_bouts.as<sgb_bout>(), NB, b->d_bl.as<BoutLayout>(), b->d_noises.as<sgb_noise>(),
                   b->d_nl.as<NoiseLayout>(), b->d_sound.as<float>(), b->d_filt.as<float>(),
                   b->d_noise_fin.as<float>(), b->d_max.as<int>(), b->d_out.p, chunks, st);
   launches++;
-  CK(cudaEventRecord(ev[10], st));
+  CK(cudaEventRecord(ev[10], st)); trace_mark(b, 10);
+  b->where = 3;
   CK(cudaStreamSynchronize(st));
+  b->where = 0;
   CK(cudaGetLastError());
+  if (stft_timeout_flag()) return fail(SGB_ERR_CUDA, "k_stft: a staged (TMA) frame load did not complete");
   info.kernel_launches = launches;
   float ms;
   CK(cudaEventElapsedTime(&ms, ev[0], ev[1])); info.ms[SGB_T_CONTROL] = ms;
@@ -873,6 +913,17 @@ static int fetch_common(sgb_batch *b, void *out, int64_t n, bool f64) {
 }
 int sgb_batch_fetch_f32(sgb_batch *b, float *out, int64_t n) { return fetch_common(b, out, n, false); }
 int sgb_batch_fetch_f64(sgb_batch *b, double *out, int64_t n) { return fetch_common(b, out, n, true); }
+
+// Diagnostic for a stuck run (callable from another thread): out[0] = which wait the handle's host thread
+// is in (0 none, 10 upload, 1 after control, 2 after compose, 3 end of run), out[1 + i] = 1 if stage event i
+// of the current run has been passed by the stream (needs SGB_TRACE=1; events: start, control, ampl, synth, compose, assemble,
+// envelope, noise, filter, finalize, end).
+int sgb_batch_debug_state(sgb_batch *b, int32_t *out, int32_t cap) {
+  if (!b || !out || cap < 12) return fail(SGB_ERR_INVALID, "bad argument");
+  out[0] = b->where;
+  for (int i = 0; i <= 10; i++) out[1 + i] = b->reached[i];   // no CUDA call here: the driver may be wedged
+  return SGB_OK;
+}
 
 // Diagnostic: position-weighted 64-bit checksums of the intermediates of the last run
 // (0 control pools, 1 spline pieces, 2 tiles, 3 FP32 amplitude table, 4 FP64 amplitude matrices,

@@ -8,12 +8,37 @@
 // trusted when |w| is well above their error bound; samples closer to zero are
 // re-evaluated in FP64 with the reference's own formula (exact_epoch_sample).
 #include "engine.cuh"
+#include <cstring>
+#include <cstdio>
 
-// 256, not more: with 512-thread CTAs and eight batches in flight on their own streams the composed
-// syllables were occasionally not reproducible run to run (scripts/dbg_pipe.py); 256 is clean over
-// hundreds of repetitions (tests/test_gpu_determinism.py keeps watching it).
+// (512-thread CTAs are no faster.  They did expose, as rare irreproducible joins and hangs with several
+// batches in flight, the write-after-read race that the barrier after the zc1 search now closes;
+// tests/test_gpu_determinism.py keeps watching.)
 #define COMPOSE_THREADS 256
 #define ZC_REL_TOL 2e-4f
+
+// Diagnostics of a non-terminating search: records land in mapped host memory, readable after a trap.
+__device__ int *g_dbg = nullptr;
+static int *h_dbg = nullptr;
+int *compose_debug_buffer() {
+  if (!h_dbg) {
+    if (cudaHostAlloc((void **)&h_dbg, 4096 * sizeof(int), cudaHostAllocMapped) != cudaSuccess) return nullptr;
+    memset(h_dbg, 0, 4096 * sizeof(int));
+    int *d = nullptr;
+    cudaHostGetDevicePointer((void **)&d, h_dbg, 0);
+    cudaMemcpyToSymbol(g_dbg, &d, sizeof d);
+  }
+  return h_dbg;
+}
+__device__ __noinline__ void dbg_record(int loop, int s, int e, int a, int b, int c, int d2, int e2) {
+  if (!g_dbg) return;
+  int slot = atomicAdd(&g_dbg[0], 1);
+  if (slot < 400) {
+    int *r = g_dbg + 8 + slot * 10;
+    r[0] = loop; r[1] = s; r[2] = e; r[3] = (int)threadIdx.x; r[4] = a; r[5] = b; r[6] = c; r[7] = d2; r[8] = e2; r[9] = 1;
+  }
+  __threadfence_system();
+}
 
 struct SylView {
   const int32_t *gcup;
@@ -132,7 +157,9 @@ k_compose(const sgb_syllable *__restrict__ syl, int S, SylCtrl *__restrict__ ctr
       // settled in FP64.  Only samples of the tail epoch (not yet cross-faded) are re-evaluated.
       int found = -1;
       int top = Lc - 2;
+      int guard1 = 0;
       while (top >= 0 && found < 0) {
+        if (++guard1 > (1 << 22)) { dbg_record(1, s, e, top, found, Lc, tail_start, sh_found); __trap(); }
         int p = top - (int)threadIdx.x;
         int hit = -1;
         if (p >= 0) {
@@ -162,6 +189,10 @@ k_compose(const sgb_syllable *__restrict__ syl, int S, SylCtrl *__restrict__ ctr
         else ok1 = v1 > 0.0f;
         if (ok0 && ok1) found = cand; else top = cand - 1;
       }
+      // every thread has read comp[cand], comp[cand + 1] for its own copy of the decision: only now may
+      // the sample after the crossing be overwritten (without this barrier a slow warp could read the
+      // new zero, reject the crossing the others accepted, and search on alone, forever)
+      __syncthreads();
       if (found >= 0) {
         zc1 = found + 1;
         Lc1 = found + 2;
@@ -176,7 +207,9 @@ k_compose(const sgb_syllable *__restrict__ syl, int S, SylCtrl *__restrict__ ctr
     {
       int found = -1;
       int base = 0;
+      int guard2 = 0;
       while (base <= Ne - 3 && found < 0) {
+        if (++guard2 > (1 << 22)) { dbg_record(2, s, e, base, found, Ne, Lc, sh_found); __trap(); }
         int p = base + (int)threadIdx.x;
         int hit = 0x7fffffff;
         if (p <= Ne - 3) {

@@ -10,6 +10,7 @@
 // mbarrier) into a double buffer while the previous pair is transformed; the weighted
 // overlap-add lives in a shared-memory ring and every output sample is written once.
 #include "engine.cuh"
+#include <cstdio>
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -26,15 +27,23 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+__device__ int g_stft_timeout = 0;   // set when a staged frame load never completed (checked by the host)
+int stft_timeout_flag() { int v = 0; cudaMemcpyFromSymbol(&v, g_stft_timeout, sizeof v); return v; }
+__device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity) {
   uint32_t ok = 0;
+  unsigned long long polls = 0;
   while (!ok) {
     asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
                  " selp.b32 %0, 1, 0, p;\n}\n"
                  : "=r"(ok)
                  : "r"(smem_u32(bar)), "r"(parity)
                  : "memory");
+    if (!ok && ++polls > (1ull << 26)) {   // seconds: a staged load that never lands must fail loudly, not hang
+      g_stft_timeout = 1;
+      return false;
+    }
   }
+  return true;
 }
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
@@ -268,7 +277,7 @@ k_stft(const FftSeg *__restrict__ segs, const FftJob *__restrict__ jobs, const F
     float2 *spec;
     if (MODE == 0) {
       // ---- wait for the staged input, prefetch the next pair ----
-      mbar_wait(&bars[cur], phase[cur]);
+      if (!mbar_wait(&bars[cur], phase[cur])) return;   // the host reports it (stft_timeout_flag)
       phase[cur] ^= 1u;
       if (threadIdx.x == 0 && k + 2 < sg.kb) issue_load(k + 2, cur ^ 1);
       const float *st = cur ? stage1 : stage0;

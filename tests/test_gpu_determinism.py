@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 NAMES = ['ctrl', 'pieces', 'tiles', 'amp32', 'amp64', 'wave', 'raw', 'sound', 'out']
 
 
-@pytest.mark.parametrize('cfg,n,npipe,reps', [(3, 2048, 8, 5), (1, 512, 4, 4)])
+@pytest.mark.parametrize('cfg,n,npipe,reps', [(3, 2048, 8, 5), (1, 512, 4, 4), (4, 1056, 8, 5)])
 def test_pipelined_runs_are_bit_reproducible(cfg, n, npipe, reps):
     L = _abi.load()
     calls = workloads.CONFIGS[cfg](n=n)
@@ -22,7 +22,12 @@ def test_pipelined_runs_are_bit_reproducible(cfg, n, npipe, reps):
         lo, hi = sharding.shard_range(n, i, npipe)
         bb = sg.BatchBuilder(u_dtype=np.float32)
         for kw in calls[lo:hi]:
-            bb.add_soundgen(**kw)
+            if 'seed' in kw:      # cfg4: per-call random streams
+                kw = dict(kw)
+                z, u = workloads.streams(kw.pop('seed'), np.float32)
+                bb.add_soundgen(z=z, u=u, **kw)
+            else:
+                bb.add_soundgen(**kw)
         descs.append(bb.build())
     batches = [sg.Batch() for _ in descs]
     sums = [[] for _ in descs]
