@@ -88,7 +88,10 @@ typedef struct sgb_syllable {
 typedef struct sgb_envelope {
   int32_t n_formants;    /* 0 = formants NA and vocalTract NULL (lip radiation only)  */
   int32_t tracks_given;  /* 1: `formants` holds nc pre-upsampled rows per formant (the
-                            host ran the stochastic block sourceSpectrum.R:346-415)   */
+                            host ran the stochastic block sourceSpectrum.R:346-415);
+                            2: a literal filter matrix (wl/2 x nc_fixed doubles, column-major)
+                            at offset `formant_off` of the `pre` pool, e.g. generateNoise's
+                            filterNoise argument (R/source.R:66-68, :95-101)            */
   int64_t formant_off;   /* offset into `formant_index` (one {off,n} entry per formant) */
   int32_t mouth_n;       /* mouthAnchors: number of anchors, 0 = NA                   */
   int32_t nc_fixed;      /* >0: number of columns; 0: one column per STFT frame       */

@@ -56,3 +56,31 @@ getRolloff = function(pitch_per_gc = c(440), nHarmonics = 100, rolloff = -12, ro
   # plotting (sourceSpectrum.R:149-176) stays in R and is unchanged
   r
 }
+
+# generateNoise (R/source.R:57-138): the breathing-strength contour with 3-10 anchors uses loess, which
+# stays in R (getSmoothContour is unchanged); 1, 2 or > 10 anchors are evaluated on the device.  The
+# runif() draws are made here, in the reference's order and number (source.R:88-111).
+generateNoise = function(len, noiseAnchors = data.frame(time = c(0, 300), value = c(-120, -120)),
+                         rolloffNoise = -6, attackLen = 10, windowLength_points = 1024,
+                         samplingRate = 16000, overlap = 75, throwaway = -120, filterNoise = NA) {
+  anchors = NULL
+  strength = NULL
+  n = nrow(noiseAnchors)
+  if (n > 2 && n <= 10) {
+    strength = getSmoothContour(len = len, anchors = noiseAnchors,
+                                valueFloor = permittedValues['noiseAmpl', 'low'],
+                                valueCeiling = permittedValues['noiseAmpl', 'high'],
+                                samplingRate = samplingRate, plot = FALSE)
+  } else {
+    anchors = cbind(noiseAnchors$time, noiseAnchors$value)
+  }
+  step = seq(1, len + windowLength_points,
+             by = windowLength_points - (overlap * windowLength_points / 100))
+  nr = windowLength_points / 2
+  u = runif(nr * length(step))
+  filt = NULL
+  if (is.matrix(filterNoise) || (is.numeric(filterNoise) && length(filterNoise) > 1)) filt = as.matrix(filterNoise)
+  pars = list(rolloffNoise = rolloffNoise, attackLen = attackLen, windowLength_points = windowLength_points,
+              samplingRate = samplingRate, overlap = overlap, throwaway = throwaway)
+  .Call(sg_generate_noise, as.integer(len), anchors, strength, u, filt, pars)
+}

@@ -113,6 +113,75 @@ SEXP sg_generate_harmonics(SEXP pitch, SEXP pars, SEXP z, SEXP ampl) {
   return out;
 }
 
+/* generateNoise (source.R:57-138).  len: integer; anchors: 2-column matrix (time ms, value dB) or NULL
+ * when `strength` (numeric[len], the contour evaluated in R, e.g. by loess) is given; u: runif(nr * nc)
+ * drawn by the caller; filter: NULL or the nr x k matrix filterNoise; pars: named list of
+ * rolloffNoise, attackLen, windowLength_points, samplingRate, overlap, throwaway.  Returns numeric[len]. */
+SEXP sg_generate_noise(SEXP len, SEXP anchors, SEXP strength, SEXP u, SEXP filter, SEXP pars) {
+  const int L = Rf_asInteger(len);
+  const int wl = (int)num(pars, "windowLength_points", 1024);
+  sgb_syllable syl;
+  memset(&syl, 0, sizeof syl);
+  syl.kind = 0; syl.silent_len = 8;                       /* a bout needs a syllable; this one is silence */
+  sgb_envelope env[2];
+  memset(env, 0, sizeof env);
+  for (int i = 0; i < 2; i++) {
+    env[i].formantDep = 1; env[i].vocalTract = R_NaN; env[i].samplingRate = num(pars, "samplingRate", 16000);
+    env[i].speedSound = 35400; env[i].smoothLinearFactor = 1;
+  }
+  sgb_noise nz;
+  memset(&nz, 0, sizeof nz);
+  nz.len = L; nz.insertion = 1; nz.mix = 0; nz.wl = wl; nz.env_id = -1; nz.strength_pre_off = -1;
+  nz.rolloffNoise = num(pars, "rolloffNoise", -6); nz.attackLen = num(pars, "attackLen", 10);
+  nz.samplingRate = num(pars, "samplingRate", 16000); nz.overlap = num(pars, "overlap", 75);
+  /* pools: anchors as interleaved pairs; `pre` = [strength | filter matrix] */
+  double *anch = NULL;
+  int n_anch = 0;
+  if (!Rf_isNull(anchors)) {
+    n_anch = Rf_nrows(anchors);
+    anch = (double *)R_alloc(2 * (size_t)n_anch, sizeof(double));
+    for (int i = 0; i < n_anch; i++) { anch[2 * i] = REAL(anchors)[i]; anch[2 * i + 1] = REAL(anchors)[n_anch + i]; }
+    nz.anchor_n = n_anch;
+  }
+  int64_t n_pre = 0;
+  const int64_t n_str = Rf_isNull(strength) ? 0 : (int64_t)XLENGTH(strength);
+  const int64_t n_flt = Rf_isNull(filter) ? 0 : (int64_t)XLENGTH(filter);
+  double *pre = NULL;
+  if (n_str + n_flt > 0) {
+    pre = (double *)R_alloc((size_t)(n_str + n_flt), sizeof(double));
+    if (n_str) { memcpy(pre, REAL(strength), sizeof(double) * (size_t)n_str); nz.strength_pre_off = 0; nz.anchor_n = 0; }
+    if (n_flt) {
+      if (Rf_nrows(filter) != wl / 2) Rf_error("filterNoise must have windowLength_points / 2 rows");
+      memcpy(pre + n_str, REAL(filter), sizeof(double) * (size_t)n_flt);   /* already column-major */
+      env[1].tracks_given = 2; env[1].formant_off = n_str; env[1].nc_fixed = Rf_isMatrix(filter) ? Rf_ncols(filter) : 1;
+      nz.env_id = 1;
+    }
+    n_pre = n_str + n_flt;
+  }
+  sgb_bout bout;
+  memset(&bout, 0, sizeof bout);
+  bout.syl_end = 1; bout.noise_end = 1; bout.wl = wl < 4 ? 4 : wl; bout.overlap = 75;
+  bout.samplingRate = nz.samplingRate; bout.throwaway = num(pars, "throwaway", -120);
+  sgb_call call = {0, 1};
+  sgb_batch_desc d;
+  memset(&d, 0, sizeof d);
+  d.n_calls = d.n_bouts = d.n_syllables = d.n_noises = 1; d.n_envelopes = 2;
+  d.calls = &call; d.bouts = &bout; d.syllables = &syl; d.noises = &nz; d.envelopes = env;
+  d.anchors = anch; d.n_anchors = n_anch;
+  d.u = REAL(u); d.n_u = XLENGTH(u); d.u_is_float = 0;
+  d.pre = pre; d.n_pre = n_pre;
+  sgb_batch *b = NULL;
+  fail_if(sgb_batch_create(&b), NULL);
+  fail_if(sgb_batch_upload(b, &d), b);
+  fail_if(sgb_batch_run(b, NULL), b);
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)L));
+  int rc = sgb_batch_noise_fetch(b, 0, REAL(out), L);
+  UNPROTECT(1);
+  fail_if(rc, b);
+  sgb_batch_destroy(b);
+  return out;
+}
+
 /* getRolloff: returns a matrix rows x nGC with rownames 1..rows (used as times_f0, source.R:401) */
 SEXP sg_get_rolloff(SEXP pitch_per_gc, SEXP nHarmonics, SEXP rolloff, SEXP rolloffOct, SEXP rolloffKHz,
                     SEXP rolloffParab, SEXP rolloffParabHarm, SEXP rolloffParabCeiling, SEXP baseline,
@@ -185,6 +254,7 @@ SEXP sg_filter(SEXP sound, SEXP envelope, SEXP wl, SEXP overlap) {
 
 static const R_CallMethodDef call_methods[] = {
     {"sg_generate_harmonics", (DL_FUNC)&sg_generate_harmonics, 4},
+    {"sg_generate_noise", (DL_FUNC)&sg_generate_noise, 6},
     {"sg_get_rolloff", (DL_FUNC)&sg_get_rolloff, 11},
     {"sg_get_spectral_envelope", (DL_FUNC)&sg_get_spectral_envelope, 7},
     {"sg_filter", (DL_FUNC)&sg_filter, 4},

@@ -159,6 +159,20 @@ class BatchBuilder:
         self.envs.append(e)
         return len(self.envs) - 1
 
+    def add_envelope_matrix(self, m, samplingRate=16000):
+        """Registers a literal (nr x nc) filter matrix, e.g. generateNoise()'s filterNoise."""
+        m = np.asarray(m, dtype=np.float64)
+        if m.ndim == 1:
+            m = m[:, None]
+        e = Envelope()
+        e.n_formants, e.tracks_given = 0, 2
+        e.formant_off = self._add_pre(np.asfortranarray(m).ravel(order='F'))
+        e.mouth_n, e.nc_fixed = 0, int(m.shape[1])
+        e.formantDep, e.rolloffLip, e.mouthOpenThres, e.openMouthBoost = 1.0, 0.0, 0.0, 0.0
+        e.vocalTract, e.samplingRate, e.speedSound, e.smoothLinearFactor = float('nan'), float(samplingRate), 35400.0, 1.0
+        self.envs.append(e)
+        return len(self.envs) - 1
+
     def add_syllable(self, pitch, z=None, amplAnchors=None, pause_after=0, contour_method='loess', **pars):
         s = Syllable()
         s.kind = 1
@@ -760,15 +774,18 @@ def generateNoise(len, noiseAnchors=((0, 300), (-120, -120)), rolloffNoise=-6, a
                   u=None, strength=None):
     """generateNoise() (R/source.R:57-68).  `u`: the runif(nr * nc) draws; filterNoise:
     None or an (nr x k) matrix (as returned by getSpectralEnvelope)."""
-    if filterNoise is not None:
-        raise NotImplementedError('pass the formant specification through soundgen(formantsNoise=...); '
-                                  'a literal filter matrix is not routed through the batch ABI yet')
     bb = BatchBuilder()
     bb.add_silent_syllable(8)
+    env = bb.add_envelope(None, samplingRate=samplingRate)
+    env_n = -1
+    if filterNoise is not None:
+        fm = np.asarray(filterNoise, dtype=np.float64)
+        if fm.shape[0] != int(windowLength_points) // 2:
+            raise ValueError('filterNoise must have windowLength_points / 2 rows')
+        env_n = bb.add_envelope_matrix(fm, samplingRate=samplingRate)
     bb.add_noise(len, noiseAnchors, u, rolloffNoise=rolloffNoise, attackLen=attackLen,
                  windowLength_points=windowLength_points, samplingRate=samplingRate, overlap=overlap,
-                 insertion=1, mix=0, strength=strength)
-    env = bb.add_envelope(None, samplingRate=samplingRate)
+                 insertion=1, mix=0, strength=strength, env_id=env_n)
     bb.add_bout(0, 1, 0, 1, env, False, max(4, int(windowLength_points)), samplingRate=samplingRate,
                 throwaway=throwaway)
     bb.add_call(0, 1)

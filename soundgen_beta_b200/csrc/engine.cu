@@ -32,9 +32,9 @@ void launch_compose(const sgb_syllable *, int, SylCtrl *, const SylLayout *, con
 void launch_place_voiced(const sgb_syllable *, int, const SylCtrl *, const SylLayout *, const SylPlace *,
                          const Pools &, const float *, float *, int, cudaStream_t);
 void launch_envelope_f32(const EnvInst *, int, int, const sgb_envelope *, const sgb_formant_ref *, const double *,
-                         const double *, float *, cudaStream_t);
+                         const double *, const double *, float *, cudaStream_t);
 void launch_envelope_f64(const EnvInst *, int, int, const sgb_envelope *, const sgb_formant_ref *, const double *,
-                         const double *, double *, cudaStream_t);
+                         const double *, const double *, double *, cudaStream_t);
 size_t stft_smem_bytes(int n, double h_in, double h_out, int mode);
 cudaError_t launch_stft(int mode, int u_is_float, int spec, const FftSeg *, int, const FftJob *, const FftPlan *,
                         const float2 *, const float *, const float *, const void *, const float *, float *, int *,
@@ -811,7 +811,7 @@ int sgb_batch_run(sgb_batch *b, sgb_run_info *info_out) {
   for (auto &I : envinst) max_nc = std::max(max_nc, I.nc);
   launch_envelope_f32(b->d_envinst.as<EnvInst>(), (int)envinst.size(), max_nc, b->d_envs.as<sgb_envelope>(),
                       b->d_frefs.as<sgb_formant_ref>(), b->d_formants.as<double>(), b->d_anchors.as<double>(),
-                      b->d_env.as<float>(), st);
+                      b->d_pre.as<double>(), b->d_env.as<float>(), st);
   if (!envinst.empty()) launches++;
   CK(cudaEventRecord(ev[6], st)); trace_mark(b, 6);
   // ---- K5 noise ----
@@ -1123,7 +1123,7 @@ int sgb_get_spectral_envelope(int32_t nr, int32_t nc, const sgb_envelope *env, c
     if (E.mouth_n) CK(cudaMemcpy(dA.p, mouth_anchors, 16 * (size_t)E.mouth_n, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dI.p, &I, sizeof I, cudaMemcpyHostToDevice));
     launch_envelope_f64(dI.as<EnvInst>(), 1, nc, dE.as<sgb_envelope>(), dR.as<sgb_formant_ref>(), dF.as<double>(),
-                        dA.as<double>(), dO.as<double>(), 0);
+                        dA.as<double>(), nullptr, dO.as<double>(), 0);
     CK(cudaGetLastError());
     CK(cudaMemcpy(out, dO.p, 8 * (size_t)nr * nc, cudaMemcpyDeviceToHost));
     return SGB_OK;

@@ -12,12 +12,18 @@ template <typename OutT>
 __global__ void __launch_bounds__(ENV_THREADS)
 k_envelope(const EnvInst *__restrict__ inst, const sgb_envelope *__restrict__ envs,
            const sgb_formant_ref *__restrict__ fidx, const double *__restrict__ formants,
-           const double *__restrict__ anchors, OutT *__restrict__ out) {
+           const double *__restrict__ anchors, const double *__restrict__ pre, OutT *__restrict__ out) {
   const EnvInst I = inst[blockIdx.y];
   const int c = blockIdx.x;
   if (c >= I.nc) return;
   const sgb_envelope E = envs[I.env_id];
   const int nr = I.nr, nc = I.nc;
+  if (E.tracks_given == 2) {   // literal nr x nc matrix supplied by the caller (generateNoise's filterNoise)
+    const double *m = pre + E.formant_off + (int64_t)c * nr;
+    OutT *colL = out + I.out_off + (int64_t)c * nr;
+    for (int r = threadIdx.x; r < nr; r += blockDim.x) colL[r] = (OutT)m[r];
+    return;
+  }
   __shared__ double f_freq[ENV_MAXF], f_amp[ENV_MAXF], f_width[ENV_MAXF];
   __shared__ double g_shape[ENV_MAXF], g_rate[ENV_MAXF], g_ref[ENV_MAXF], g_amp[ENV_MAXF];
   __shared__ int nF;
@@ -123,15 +129,15 @@ k_envelope(const EnvInst *__restrict__ inst, const sgb_envelope *__restrict__ en
 
 void launch_envelope_f32(const EnvInst *inst, int n_inst, int max_nc, const sgb_envelope *envs,
                          const sgb_formant_ref *fidx, const double *formants, const double *anchors,
-                         float *out, cudaStream_t st) {
+                         const double *pre, float *out, cudaStream_t st) {
   if (n_inst <= 0 || max_nc <= 0) return;
   dim3 g(max_nc, n_inst);
-  k_envelope<float><<<g, ENV_THREADS, 0, st>>>(inst, envs, fidx, formants, anchors, out);
+  k_envelope<float><<<g, ENV_THREADS, 0, st>>>(inst, envs, fidx, formants, anchors, pre, out);
 }
 void launch_envelope_f64(const EnvInst *inst, int n_inst, int max_nc, const sgb_envelope *envs,
                          const sgb_formant_ref *fidx, const double *formants, const double *anchors,
-                         double *out, cudaStream_t st) {
+                         const double *pre, double *out, cudaStream_t st) {
   if (n_inst <= 0 || max_nc <= 0) return;
   dim3 g(max_nc, n_inst);
-  k_envelope<double><<<g, ENV_THREADS, 0, st>>>(inst, envs, fidx, formants, anchors, out);
+  k_envelope<double><<<g, ENV_THREADS, 0, st>>>(inst, envs, fidx, formants, anchors, pre, out);
 }

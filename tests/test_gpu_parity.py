@@ -88,6 +88,19 @@ def test_generate_noise():
         assert rel(sg.generateNoise(n, an, rolloffNoise=ro, attackLen=10, windowLength_points=wl, u=u), ref) < TOL
 
 
+def test_generate_noise_with_a_literal_filter_matrix():
+    # generateNoise(filterNoise = <matrix>) as soundgen() calls it (R/soundgen.R:668-690)
+    wl, n = 800, 9000
+    u = np.random.default_rng(11).random(workloads.noise_uniform_count(n, wl))
+    an = (np.array([0., 400]), np.array([-10., 5]))
+    for k in (1, 37):
+        flt = so.getSpectralEnvelope(wl // 2, k, formants=FM2 if k > 1 else FM, vocalTract=15.5)
+        ref = so.generateNoise(n, an, rolloffNoise=-8, attackLen=20, windowLength_points=wl, filterNoise=flt,
+                               rng=so.RStream(u=u))
+        y = sg.generateNoise(n, an, rolloffNoise=-8, attackLen=20, windowLength_points=wl, filterNoise=flt, u=u)
+        assert rel(y, ref) < TOL
+
+
 def _oracle_call(kw):
     kw = dict(kw)
     z, u = kw.pop('z', None), kw.pop('u', None)
