@@ -193,6 +193,8 @@ __global__ void k_build_tiles(const SylCtrl *ctrl, int S, const SylLayout *lay, 
 #define AMP_MAXS 16
 #define AMP_CG 32
 #define AMP_RPT 4
+#define AMP_VF 1024      // f-harmonics per column the dense variant keeps in shared memory
+#define AMP_DR 10        // rows per thread of the dense variant (rows <= 2560)
 __global__ void __launch_bounds__(256, 3)
 k_amp(const sgb_syllable *syl, int S, const SylCtrl *ctrl, const SylLayout *lay, Pools P, double *amp,
       float4 *amp32) {
@@ -206,6 +208,7 @@ k_amp(const sgb_syllable *syl, int S, const SylCtrl *ctrl, const SylLayout *lay,
   float4 *out32 = amp32 + lay[s].amp_off;
   __shared__ double A0[AMP_MAXH + 2];
   __shared__ double ML[AMP_MAXS * (AMP_CG + 1)], MU[AMP_MAXS * (AMP_CG + 1)];
+  __shared__ double VF[2][AMP_VF + 2];
   const int G = C.nGC, Hk = C.rows_kept;
   const double thr01 = exp2(sp.throwaway / 10.0);
   for (int c0 = blockIdx.y * AMP_CG; c0 < G; c0 += gridDim.y * AMP_CG) {
@@ -245,8 +248,62 @@ k_amp(const sgb_syllable *syl, int S, const SylCtrl *ctrl, const SylLayout *lay,
         }
       }
       __syncthreads();
-      // each thread owns rows j = rb + tid + i*256 and walks the columns, so that the FP32
-      // {Y_g, Y_{g+1} - Y_g} table K1 consumes falls out of the same pass
+      if (tabled && Hk <= AMP_VF && rows <= 256 * AMP_DR) {
+        // Dense variant.  With sub-harmonics only every (n+1)-th row is an f-harmonic (rolloff + exp2, the
+        // expensive rows); evaluated row by row they would keep 1/(n+1) of a warp's lanes busy.  So per
+        // column the f-harmonics are first computed densely over the threads into shared memory
+        // (double-buffered: one barrier per column), then every thread writes the rows it owns.
+        double prev[AMP_DR], lgk[AMP_VF / 256];
+        int hk[AMP_VF / 256];
+#pragma unroll
+        for (int i = 0; i < AMP_VF / 256; i++) {
+          const int k = (int)threadIdx.x + 1 + 256 * i;
+          hk[i] = 1; lgk[i] = 0.0;
+          if (k <= Hk) { hk[i] = A.rowmap[k - 1]; lgk[i] = log2((double)hk[i]); }
+        }
+#pragma unroll
+        for (int i = 0; i < AMP_DR; i++) prev[i] = 0.0;
+        for (int g = ga; g < gx; g++) {
+          const int gi = g - ga;
+          const double pg = A.ppg[g], roctg = A.roct[g], cmg = A.colmax[g], shg = A.shimmer[g];
+          const double slope = A.ro[g] + A.rk[g] * (pg - 200.0) / 1000.0;   // column term of rolloff_db_l
+          double *vf = VF[gi & 1];
+#pragma unroll
+          for (int i = 0; i < AMP_VF / 256; i++) {
+            const int k = (int)threadIdx.x + 1 + 256 * i;
+            if (k > Hk) continue;
+            double r = rolloff_db_s(hk[i], lgk[i], pg, slope, roctg, C.any_oct != 0, sp.rolloffParab, C.parab_harm,
+                                    C.parab_a, C.parab_b, C.parab_c, 200.0, sp.throwaway, sp.samplingRate);
+            vf[k] = exp2((r - cmg) / 10.0) * shg;
+          }
+          __syncthreads();
+          double *oc = oe + (int64_t)(g - g0) * rows;
+          float4 *oc32 = oe32 + (int64_t)(g - 1 - g0) * rows;
+#pragma unroll
+          for (int i = 0; i < AMP_DR; i++) {
+            const int j = i * 256 + (int)threadIdx.x + 1;
+            if (j > rows) continue;
+            double v;
+            if (n == 0) {
+              v = vf[j];
+            } else {
+              const int k = j / (n + 1), si = j - k * (n + 1);
+              if (si == 0) v = vf[k];
+              else v = A0[k] * ML[(si - 1) * (AMP_CG + 1) + gi] + A0[k + 1] * MU[(si - 1) * (AMP_CG + 1) + gi];
+              if (v < thr01) v = 0.0;
+            }
+            if (g < gb) oc[j - 1] = v;
+            if (g > ga) {   // {Y, Y, dY, dY}: one 16-byte load gives K1 both packed FFMA2 operands
+              const float y = (float)prev[i], dy = (float)(v - prev[i]);
+              oc32[j - 1] = make_float4(y, y, dy, dy);
+            }
+            prev[i] = v;
+          }
+        }
+        continue;
+      }
+      // General variant: each thread owns rows j = rb + tid + i*256 and walks the columns, so that the
+      // FP32 {Y_g, Y_{g+1} - Y_g} table K1 consumes falls out of the same pass
       for (int rb = 0; rb < rows; rb += 256 * AMP_RPT) {
         double prev[AMP_RPT], lg[AMP_RPT];
         int rk_[AMP_RPT], rs_[AMP_RPT], rh_[AMP_RPT];     // per owned row: f index k, sub index s, harmonic h
