@@ -438,6 +438,7 @@ static int plan_radices(int n, int *radix) {
   for (int i = 0; i < no; i++) pw /= odd[i];
   while (pw % 4 == 0) { if (np >= FFT_MAX_PASS) return -1; radix[np++] = 4; pw /= 4; }
   while (pw % 2 == 0) { if (np >= FFT_MAX_PASS) return -1; radix[np++] = 2; pw /= 2; }
+  if (np >= 2 && radix[np - 2] == 4 && radix[np - 1] == 2) { radix[np - 2] = 8; np--; }   // register radix-8
   return np;
 }
 
@@ -608,6 +609,7 @@ int sgb_batch_run(sgb_batch *b, sgb_run_info *info_out) {
   PlanTable PT;
   auto get_plan = [&](int n, double overlap) -> int { return PT.get(n, overlap); };
 
+  std::vector<int64_t> syl_pos, npos, fpos;   // reused across bouts (no allocation per bout)
   for (int c = 0; c < NC; c++) {
     const sgb_call &CL = b->calls[c];
     b->call_off[c] = out_total;
@@ -618,7 +620,7 @@ int sgb_batch_run(sgb_batch *b, sgb_run_info *info_out) {
       BoutLayout &L = b->bl[bi];
       memset(&L, 0, sizeof L);
       // voiced = c(voiced, syllable, pause)
-      std::vector<int64_t> syl_pos(B.syl_end - B.syl_begin);
+      syl_pos.assign(B.syl_end - B.syl_begin, 0);
       int64_t vlen = 0;
       bool any_voiced = false;
       for (int s = B.syl_begin; s < B.syl_end; s++) {
@@ -633,7 +635,7 @@ int sgb_batch_run(sgb_batch *b, sgb_run_info *info_out) {
       }
       // pre-filter noise: sound = addVectors(sound, unvoiced[[s]], syllableStartIdx[s])
       int64_t cur = vlen, shift = 0;
-      std::vector<int64_t> npos(std::max(0, B.noise_end - B.noise_begin), 0);
+      npos.assign(std::max(0, B.noise_end - B.noise_begin), 0);
       bool any_pre = false;
       for (int n = B.noise_begin; n < B.noise_end; n++) {
         const sgb_noise &N = b->noises[n];
@@ -690,7 +692,7 @@ int sgb_batch_run(sgb_batch *b, sgb_run_info *info_out) {
       }
       // post-filter noise: soundFiltered = addVectors(soundFiltered, unvoiced[[s]], syllableStartIdx[s])
       int64_t fcur = L.filt_len, fshift = 0;
-      std::vector<int64_t> fpos(npos.size(), 0);
+      fpos.assign(npos.size(), 0);
       for (int n = B.noise_begin; n < B.noise_end; n++) {
         const sgb_noise &N = b->noises[n];
         if (N.mix != 1) continue;

@@ -50,17 +50,52 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
 
+// Input of the first forward pass: two real frames read straight from the TMA staging buffer, multiplied by
+// the analysis window and packed as A + iB (no separate windowing pass).
+struct WinIn {
+  const float *a, *b, *w;
+  int off;
+  bool hasB;
+  __device__ __forceinline__ WinIn operator+(int o) const { WinIn r = *this; r.off += o; return r; }
+  __device__ __forceinline__ float2 operator[](int i) const {
+    const int k = off + i;
+    const float wv = w[k];
+    return make_float2(a[k] * wv, hasB ? b[k] * wv : 0.0f);
+  }
+};
+// Output of the last inverse pass: weighted overlap-add straight into the rings (frame A of a pair into
+// ring A, frame B into ring B, so no two threads of a pass touch the same slot).
+struct OlaOut {
+  float *ra, *rb;
+  const float *ws;
+  int oA, oB, ring;
+  bool hasB;
+  __device__ __forceinline__ void add(int o, float2 v) const {
+    const float wv = ws[o];
+    int sa = oA + o;
+    if (sa >= ring) sa -= ring;
+    ra[sa] += v.x * wv;
+    if (hasB) {
+      int sb = oB + o;
+      if (sb >= ring) sb -= ring;
+      rb[sb] += v.y * wv;
+    }
+  }
+};
+
 // One Stockham pass (decimation in frequency): N points, stride s (product of the
 // radices already done), radix r.  DIR = -1 forward, +1 inverse (conjugated twiddles).
-template <int DIR>
-__device__ __forceinline__ void fft_pass(const float2 *__restrict__ x, float2 *__restrict__ y, int N, int s, int r,
-                                         const float2 *__restrict__ tw) {
+// XIn: plain pointer or WinIn; LAST: the outputs go to the overlap-add rings instead of y.
+template <int DIR, class XIn, bool LAST>
+__device__ __forceinline__ void fft_pass(XIn x, float2 *__restrict__ y, int N, int s, int r,
+                                         const float2 *__restrict__ tw, const OlaOut &O) {
+  auto put = [&](int o, float2 v) { if (LAST) O.add(o, v); else y[o] = v; };
   const int nb = N / r;             // butterflies
   const int m = nb / s;             // N / (s * r)
   if (r == 4) {
     for (int b = threadIdx.x; b < nb; b += FFT_THREADS) {
       int p = b / s, q = b - p * s;
-      const float2 *xi = x + q + s * p;
+      const XIn xi = x + (q + s * p);
       float2 a0 = xi[0], a1 = xi[s * m], a2 = xi[2 * s * m], a3 = xi[3 * s * m];
       float2 t0 = make_float2(a0.x + a2.x, a0.y + a2.y), t1 = make_float2(a0.x - a2.x, a0.y - a2.y);
       float2 t2 = make_float2(a1.x + a3.x, a1.y + a3.y), t3 = make_float2(a1.x - a3.x, a1.y - a3.y);
@@ -70,37 +105,37 @@ __device__ __forceinline__ void fft_pass(const float2 *__restrict__ x, float2 *_
       float2 b2 = make_float2(t0.x - t2.x, t0.y - t2.y);
       float2 b1 = make_float2(t1.x + mi.x, t1.y + mi.y);
       float2 b3 = make_float2(t1.x - mi.x, t1.y - mi.y);
-      float2 *yo = y + q + s * 4 * p;
+      const int yo = q + s * 4 * p;
       int ti = p * s;
       float2 w1 = tw[ti], w2 = tw[2 * ti], w3 = tw[3 * ti];
       if (DIR > 0) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
-      yo[0] = b0; yo[s] = cmul(b1, w1); yo[2 * s] = cmul(b2, w2); yo[3 * s] = cmul(b3, w3);
+      put(yo, b0); put(yo + s, cmul(b1, w1)); put(yo + 2 * s, cmul(b2, w2)); put(yo + 3 * s, cmul(b3, w3));
     }
   } else if (r == 3) {
     const float c3 = 0.86602540378443864676f;   // sin(2 pi / 3)
     for (int b = threadIdx.x; b < nb; b += FFT_THREADS) {
       int p = b / s, q = b - p * s;
-      const float2 *xi = x + q + s * p;
+      const XIn xi = x + (q + s * p);
       const int sm = s * m;
       float2 a0 = xi[0], a1 = xi[sm], a2 = xi[2 * sm];
       float2 t = make_float2(a1.x + a2.x, a1.y + a2.y), u = make_float2(a1.x - a2.x, a1.y - a2.y);
       float2 mm = make_float2(fmaf(-0.5f, t.x, a0.x), fmaf(-0.5f, t.y, a0.y));
       // forward: -i * c3 * u ; inverse: +i * c3 * u
       float2 v = (DIR < 0) ? make_float2(c3 * u.y, -c3 * u.x) : make_float2(-c3 * u.y, c3 * u.x);
-      float2 *yo = y + q + s * 3 * p;
+      const int yo = q + s * 3 * p;
       int ti = p * s;
       float2 w1 = tw[ti], w2 = tw[2 * ti];
       if (DIR > 0) { w1.y = -w1.y; w2.y = -w2.y; }
-      yo[0] = make_float2(a0.x + t.x, a0.y + t.y);
-      yo[s] = cmul(make_float2(mm.x + v.x, mm.y + v.y), w1);
-      yo[2 * s] = cmul(make_float2(mm.x - v.x, mm.y - v.y), w2);
+      put(yo, make_float2(a0.x + t.x, a0.y + t.y));
+      put(yo + s, cmul(make_float2(mm.x + v.x, mm.y + v.y), w1));
+      put(yo + 2 * s, cmul(make_float2(mm.x - v.x, mm.y - v.y), w2));
     }
   } else if (r == 5) {
     const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
     const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
     for (int b = threadIdx.x; b < nb; b += FFT_THREADS) {
       int p = b / s, q = b - p * s;
-      const float2 *xi = x + q + s * p;
+      const XIn xi = x + (q + s * p);
       const int sm = s * m;
       float2 a0 = xi[0], a1 = xi[sm], a2 = xi[2 * sm], a3 = xi[3 * sm], a4 = xi[4 * sm];
       float2 t1 = make_float2(a1.x + a4.x, a1.y + a4.y), t2 = make_float2(a2.x + a3.x, a2.y + a3.y);
@@ -112,15 +147,64 @@ __device__ __forceinline__ void fft_pass(const float2 *__restrict__ x, float2 *_
       // forward: b1 = m1 - i n1, b4 = m1 + i n1, b2 = m2 - i n2, b3 = m2 + i n2 (inverse: conjugate)
       float2 i1 = (DIR < 0) ? make_float2(n1.y, -n1.x) : make_float2(-n1.y, n1.x);
       float2 i2 = (DIR < 0) ? make_float2(n2.y, -n2.x) : make_float2(-n2.y, n2.x);
-      float2 *yo = y + q + s * 5 * p;
+      const int yo = q + s * 5 * p;
       int ti = p * s;
       float2 w1 = tw[ti], w2 = tw[2 * ti], w3 = tw[3 * ti], w4 = tw[4 * ti];
       if (DIR > 0) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; w4.y = -w4.y; }
-      yo[0] = make_float2(a0.x + t1.x + t2.x, a0.y + t1.y + t2.y);
-      yo[s] = cmul(make_float2(m1.x + i1.x, m1.y + i1.y), w1);
-      yo[2 * s] = cmul(make_float2(m2.x + i2.x, m2.y + i2.y), w2);
-      yo[3 * s] = cmul(make_float2(m2.x - i2.x, m2.y - i2.y), w3);
-      yo[4 * s] = cmul(make_float2(m1.x - i1.x, m1.y - i1.y), w4);
+      put(yo, make_float2(a0.x + t1.x + t2.x, a0.y + t1.y + t2.y));
+      put(yo + s, cmul(make_float2(m1.x + i1.x, m1.y + i1.y), w1));
+      put(yo + 2 * s, cmul(make_float2(m2.x + i2.x, m2.y + i2.y), w2));
+      put(yo + 3 * s, cmul(make_float2(m2.x - i2.x, m2.y - i2.y), w3));
+      put(yo + 4 * s, cmul(make_float2(m1.x - i1.x, m1.y - i1.y), w4));
+    }
+  } else if (r == 8) {
+    const float h = 0.70710678118654752440f;
+    for (int b = threadIdx.x; b < nb; b += FFT_THREADS) {
+      int p = b / s, q = b - p * s;
+      const XIn xi = x + (q + s * p);
+      const int sm = s * m;
+      float2 a[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) a[k] = xi[k * sm];
+      // radix-2 stage: u_k = a_k + a_{k+4}; v_k = (a_k - a_{k+4}) w8^k  (w8 = e^{DIR i pi/4})
+      float2 u[4], v[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        u[k] = make_float2(a[k].x + a[k + 4].x, a[k].y + a[k + 4].y);
+        v[k] = make_float2(a[k].x - a[k + 4].x, a[k].y - a[k + 4].y);
+      }
+      // forward w8^1 = (1 - i) h, w8^2 = -i, w8^3 = (-1 - i) h; inverse: conjugates
+      if (DIR < 0) {
+        v[1] = make_float2(h * (v[1].x + v[1].y), h * (v[1].y - v[1].x));
+        v[2] = make_float2(v[2].y, -v[2].x);
+        v[3] = make_float2(h * (v[3].y - v[3].x), -h * (v[3].x + v[3].y));
+      } else {
+        v[1] = make_float2(h * (v[1].x - v[1].y), h * (v[1].x + v[1].y));
+        v[2] = make_float2(-v[2].y, v[2].x);
+        v[3] = make_float2(-h * (v[3].x + v[3].y), h * (v[3].x - v[3].y));
+      }
+      // two radix-4 butterflies: even outputs from u, odd outputs from v
+      float2 X[8];
+#pragma unroll
+      for (int par = 0; par < 2; par++) {
+        const float2 *c = par ? v : u;
+        float2 t0 = make_float2(c[0].x + c[2].x, c[0].y + c[2].y), t1 = make_float2(c[0].x - c[2].x, c[0].y - c[2].y);
+        float2 t2 = make_float2(c[1].x + c[3].x, c[1].y + c[3].y), t3 = make_float2(c[1].x - c[3].x, c[1].y - c[3].y);
+        float2 mi = (DIR < 0) ? make_float2(t3.y, -t3.x) : make_float2(-t3.y, t3.x);
+        X[par] = make_float2(t0.x + t2.x, t0.y + t2.y);
+        X[4 + par] = make_float2(t0.x - t2.x, t0.y - t2.y);
+        X[2 + par] = make_float2(t1.x + mi.x, t1.y + mi.y);
+        X[6 + par] = make_float2(t1.x - mi.x, t1.y - mi.y);
+      }
+      const int yo = q + s * 8 * p;
+      const int ti = p * s;
+      put(yo, X[0]);
+#pragma unroll
+      for (int j = 1; j < 8; j++) {
+        float2 w = tw[j * ti];
+        if (DIR > 0) w.y = -w.y;
+        put(yo + j * s, cmul(X[j], w));
+      }
     }
   } else if (r == 2) {
     for (int b = threadIdx.x; b < nb; b += FFT_THREADS) {
@@ -128,8 +212,8 @@ __device__ __forceinline__ void fft_pass(const float2 *__restrict__ x, float2 *_
       float2 a0 = x[q + s * p], a1 = x[q + s * (p + m)];
       float2 w1 = tw[p * s];
       if (DIR > 0) w1.y = -w1.y;
-      y[q + s * 2 * p] = make_float2(a0.x + a1.x, a0.y + a1.y);
-      y[q + s * (2 * p + 1)] = cmul(make_float2(a0.x - a1.x, a0.y - a1.y), w1);
+      put(q + s * 2 * p, make_float2(a0.x + a1.x, a0.y + a1.y));
+      put(q + s * (2 * p + 1), cmul(make_float2(a0.x - a1.x, a0.y - a1.y), w1));
     }
   } else {
     // generic radix: one output per work item, omega_r^(jk) looked up in the N-point table
@@ -137,7 +221,7 @@ __device__ __forceinline__ void fft_pass(const float2 *__restrict__ x, float2 *_
     for (int idx = threadIdx.x; idx < N; idx += FFT_THREADS) {
       int j = idx / nb, b = idx - j * nb;
       int p = b / s, q = b - p * s;
-      const float2 *xi = x + q + s * p;
+      const XIn xi = x + (q + s * p);
       const int sm = s * m;
       float2 acc = xi[0];
       int t = 0;
@@ -153,19 +237,24 @@ __device__ __forceinline__ void fft_pass(const float2 *__restrict__ x, float2 *_
       }
       float2 w2 = tw[p * j * s];
       if (DIR > 0) w2.y = -w2.y;
-      y[q + s * (r * p + j)] = cmul(acc, w2);
+      put(q + s * (r * p + j), cmul(acc, w2));
     }
   }
 }
 
-// full transform; returns the buffer holding the result
-template <int DIR>
-__device__ float2 *fft_run(float2 *a, float2 *b, const FftPlan &pl, const float2 *tw) {
+// full transform; returns the buffer holding the result.  FIN: the first pass reads the windowed staging
+// buffer (W); FOUT: the last pass adds into the overlap-add rings (O) and nothing is written to the buffer.
+template <int DIR, bool FIN, bool FOUT>
+__device__ float2 *fft_run(float2 *a, float2 *b, const FftPlan &pl, const float2 *tw, const WinIn &W, const OlaOut &O) {
   int s = 1;
   float2 *src = a, *dst = b;
   for (int i = 0; i < pl.npass; i++) {
-    int r = pl.radix[i];
-    fft_pass<DIR>(src, dst, pl.n, s, r, tw);
+    const int r = pl.radix[i];
+    const bool first = FIN && i == 0, last = FOUT && i == pl.npass - 1;
+    if (first && last) fft_pass<DIR, WinIn, true>(W, dst, pl.n, s, r, tw, O);
+    else if (first) fft_pass<DIR, WinIn, false>(W, dst, pl.n, s, r, tw, O);
+    else if (last) fft_pass<DIR, const float2 *, true>(src, dst, pl.n, s, r, tw, O);
+    else fft_pass<DIR, const float2 *, false>(src, dst, pl.n, s, r, tw, O);
     __syncthreads();
     s *= r;
     float2 *t = src; src = dst; dst = t;
@@ -176,23 +265,25 @@ __device__ float2 *fft_run(float2 *a, float2 *b, const FftPlan &pl, const float2
 // Compile-time plans for soundgen's usual windows (50 ms at 16 / 22.05 / 24 / 44.1 / 48 kHz and the
 // 10 ms presets): with N, the strides and the radices known, every index division folds to a
 // multiply-shift and the radix dispatch disappears.  SPEC 0 = run-time plan (any even length).
-template <int DIR, int N, int S>
-__device__ __forceinline__ float2 *run_ct(float2 *a, float2 *, const float2 *) { return a; }
-template <int DIR, int N, int S, int R, int... Rest>
-__device__ __forceinline__ float2 *run_ct(float2 *a, float2 *b, const float2 *tw) {
-  fft_pass<DIR>(a, b, N, S, R, tw);
+template <int DIR, bool FIN, bool FOUT, int N, int S, int R, int... Rest>
+__device__ __forceinline__ float2 *run_ct(float2 *a, float2 *b, const float2 *tw, const WinIn &W, const OlaOut &O) {
+  constexpr bool last = sizeof...(Rest) == 0;
+  if constexpr (S == 1 && FIN) fft_pass<DIR, WinIn, (last && FOUT)>(W, b, N, S, R, tw, O);
+  else fft_pass<DIR, const float2 *, (last && FOUT)>(a, b, N, S, R, tw, O);
   __syncthreads();
-  return run_ct<DIR, N, S * R, Rest...>(b, a, tw);
+  if constexpr (last) return b;
+  else return run_ct<DIR, FIN, FOUT, N, S * R, Rest...>(b, a, tw, W, O);
 }
-template <int DIR, int SPEC>
-__device__ __forceinline__ float2 *fft_any(float2 *a, float2 *b, const FftPlan &pl, const float2 *tw) {
-  if constexpr (SPEC == 1) return run_ct<DIR, 800, 1, 5, 5, 4, 4, 2>(a, b, tw);
-  else if constexpr (SPEC == 2) return run_ct<DIR, 1102, 1, 29, 19, 2>(a, b, tw);
-  else if constexpr (SPEC == 3) return run_ct<DIR, 1200, 1, 5, 5, 3, 4, 4>(a, b, tw);
-  else if constexpr (SPEC == 4) return run_ct<DIR, 2204, 1, 29, 19, 4>(a, b, tw);
-  else if constexpr (SPEC == 5) return run_ct<DIR, 2400, 1, 5, 5, 3, 4, 4, 2>(a, b, tw);
-  else if constexpr (SPEC == 6) return run_ct<DIR, 160, 1, 5, 4, 4, 2>(a, b, tw);
-  else return fft_run<DIR>(a, b, pl, tw);
+template <int DIR, int SPEC, bool FIN, bool FOUT>
+__device__ __forceinline__ float2 *fft_any(float2 *a, float2 *b, const FftPlan &pl, const float2 *tw, const WinIn &W,
+                                           const OlaOut &O) {
+  if constexpr (SPEC == 1) return run_ct<DIR, FIN, FOUT, 800, 1, 5, 5, 4, 8>(a, b, tw, W, O);
+  else if constexpr (SPEC == 2) return run_ct<DIR, FIN, FOUT, 1102, 1, 29, 19, 2>(a, b, tw, W, O);
+  else if constexpr (SPEC == 3) return run_ct<DIR, FIN, FOUT, 1200, 1, 5, 5, 3, 4, 4>(a, b, tw, W, O);
+  else if constexpr (SPEC == 4) return run_ct<DIR, FIN, FOUT, 2204, 1, 29, 19, 4>(a, b, tw, W, O);
+  else if constexpr (SPEC == 5) return run_ct<DIR, FIN, FOUT, 2400, 1, 5, 5, 3, 4, 8>(a, b, tw, W, O);
+  else if constexpr (SPEC == 6) return run_ct<DIR, FIN, FOUT, 160, 1, 5, 4, 8>(a, b, tw, W, O);
+  else return fft_run<DIR, FIN, FOUT>(a, b, pl, tw, W, O);
 }
 
 __device__ __forceinline__ int frame_in_start(const FftPlan &pl, int k) {   // 0-based
@@ -224,8 +315,9 @@ k_stft(const FftSeg *__restrict__ segs, const FftJob *__restrict__ jobs, const F
   float2 *bufA = reinterpret_cast<float2 *>(smem_raw);
   float2 *bufB = bufA + N;
   float2 *tw = bufB + N;
-  float *ola = reinterpret_cast<float *>(tw + N);
-  float *stage0 = ola + ((ring + 3) & ~3);
+  float *ola = reinterpret_cast<float *>(tw + N);      // ring A: even frames of the pairs
+  float *olb = ola + ((ring + 3) & ~3);                // ring B: odd frames
+  float *stage0 = olb + ((ring + 3) & ~3);
   float *stage1 = stage0 + stage_len;
   float *vec = stage1 + ((MODE == 0) ? stage_len : 0);           // noise: rolloff vector [nr]
 
@@ -233,7 +325,7 @@ k_stft(const FftSeg *__restrict__ segs, const FftJob *__restrict__ jobs, const F
   const float *wa = winpool + pl.wa_off;
   const float *ws = winpool + pl.ws_off;
   for (int i = threadIdx.x; i < N; i += FFT_THREADS) tw[i] = twg[i];
-  for (int i = threadIdx.x; i < ring; i += FFT_THREADS) ola[i] = 0.0f;
+  for (int i = threadIdx.x; i < ring; i += FFT_THREADS) { ola[i] = 0.0f; olb[i] = 0.0f; }
   if (MODE == 1) {
     // rolloff vector 2^(rolloffNoise/10 * log2(1:nr)) (source.R:103-105)
     for (int i = threadIdx.x; i < nr; i += FFT_THREADS)
@@ -283,18 +375,13 @@ k_stft(const FftSeg *__restrict__ segs, const FftJob *__restrict__ jobs, const F
       const float *st = cur ? stage1 : stage0;
       const int sA = frame_in_start(pl, k);
       const int a0 = sA & ~3;
-      const int offA = sA - a0;
-      const int offB = hasB ? (frame_in_start(pl, k + 1) - a0) : 0;
-      for (int i = threadIdx.x; i < N; i += FFT_THREADS) {
-        float wv = wa[i];
-        float xa = st[offA + i] * wv;
-        float xb = hasB ? st[offB + i] * wv : 0.0f;
-        bufA[i] = make_float2(xa, xb);
-      }
-      __syncthreads();
+      WinIn W;
+      W.a = st + (sA - a0); W.b = st + (hasB ? (frame_in_start(pl, k + 1) - a0) : 0); W.w = wa; W.off = 0; W.hasB = hasB;
+      OlaOut O0 = {};
+      // the first pass reads the staged frames through the analysis window (A + iB packing included)
+      float2 *Z = fft_any<-1, SPEC, true, false>(bufA, bufB, pl, tw, W, O0);
       // all generic-proxy reads of this staging buffer are done: make it safe for the next TMA write
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      float2 *Z = fft_any<-1, SPEC>(bufA, bufB, pl, tw);
       // ---- split the two spectra, multiply by the envelope, rebuild Hermitian halves ----
       const float *eA = envpool + jb.env_off + (int64_t)((jb.nint > 1) ? k : 0) * nr;
       const float *eB = envpool + jb.env_off + (int64_t)((jb.nint > 1 && hasB) ? (k + 1) : 0) * nr;
@@ -341,25 +428,13 @@ k_stft(const FftSeg *__restrict__ segs, const FftJob *__restrict__ jobs, const F
       spec = bufA;
     }
     float2 *other = (spec == bufA) ? bufB : bufA;
-    float2 *Y = fft_any<+1, SPEC>(spec, other, pl, tw);
-
-    // ---- weighted overlap-add into the ring (frame A, then frame B) ----
-    const int oA = frame_out_start(pl, k) % ring;
-    for (int i = threadIdx.x; i < N; i += FFT_THREADS) {
-      int slot = oA + i;
-      if (slot >= ring) slot -= ring;
-      ola[slot] += Y[i].x * ws[i];
-    }
-    __syncthreads();
-    if (hasB) {
-      const int oB = frame_out_start(pl, k + 1) % ring;
-      for (int i = threadIdx.x; i < N; i += FFT_THREADS) {
-        int slot = oB + i;
-        if (slot >= ring) slot -= ring;
-        ola[slot] += Y[i].y * ws[i];
-      }
-      __syncthreads();
-    }
+    // the last inverse pass adds the synthesis-windowed frames straight into the two rings
+    OlaOut O;
+    O.ra = ola; O.rb = olb; O.ws = ws; O.ring = ring; O.hasB = hasB;
+    O.oA = frame_out_start(pl, k) % ring;
+    O.oB = hasB ? frame_out_start(pl, k + 1) % ring : 0;
+    WinIn W0 = {};
+    fft_any<+1, SPEC, false, true>(spec, other, pl, tw, W0, O);
     // ---- samples before the next frame's start are final: write them out once ----
     int knext = k + 2;
     int done_to = (knext < sg.kb) ? frame_out_start(pl, knext) : ((sg.kb >= jb.nc) ? jb.xlen : frame_out_start(pl, sg.kb));
@@ -368,8 +443,8 @@ k_stft(const FftSeg *__restrict__ segs, const FftJob *__restrict__ jobs, const F
     for (int t = flushed + threadIdx.x; t < done_to; t += FFT_THREADS) {
       int slot = fbase + (t - flushed);
       if (slot >= ring) slot -= ring;
-      float v = ola[slot];
-      ola[slot] = 0.0f;
+      float v = ola[slot] + olb[slot];
+      ola[slot] = 0.0f; olb[slot] = 0.0f;
       if (t >= flush_lo && t < flush_hi) {
         int oi = t - jb.shift;
         if (oi >= 0 && oi < jb.out_len) {
@@ -398,7 +473,7 @@ size_t stft_smem_bytes(int n, double h_in, double h_out, int mode) {
   int hceil = (int)ceil(h_out) + 2;
   int ring = n + 2 * hceil + 4;
   int stage_len = (n + (int)ceil(h_in) + 12) & ~3;
-  size_t floats = (size_t)6 * n + ((ring + 3) & ~3) + (mode == 0 ? 2 * (size_t)stage_len : (size_t)stage_len + n / 2 + 4);
+  size_t floats = (size_t)6 * n + 2 * (size_t)((ring + 3) & ~3) + (mode == 0 ? 2 * (size_t)stage_len : (size_t)stage_len + n / 2 + 4);
   return floats * 4 + 64;
 }
 
@@ -415,8 +490,8 @@ static cudaError_t ensure_smem(K kf, size_t *slot, size_t smem) {
 
 int stft_spec_of(int n, const int *radix, int npass) {
   static const int sizes[N_SPEC] = {0, 800, 1102, 1200, 2204, 2400, 160};
-  static const int rad[N_SPEC][8] = {{0}, {5, 5, 4, 4, 2}, {29, 19, 2}, {5, 5, 3, 4, 4}, {29, 19, 4},
-                                     {5, 5, 3, 4, 4, 2}, {5, 4, 4, 2}};
+  static const int rad[N_SPEC][8] = {{0}, {5, 5, 4, 8}, {29, 19, 2}, {5, 5, 3, 4, 4}, {29, 19, 4},
+                                     {5, 5, 3, 4, 8}, {5, 4, 8}};
   for (int sp = 1; sp < N_SPEC; sp++) {
     if (sizes[sp] != n) continue;
     int np = 0;
