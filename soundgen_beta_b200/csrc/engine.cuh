@@ -97,7 +97,7 @@ struct EnvInst {
 };
 
 
-#define FFT_THREADS 256
+#define FFT_THREADS 512
 #define FFT_MAX_PASS 16
 
 struct FftPlan {

@@ -295,7 +295,7 @@ __device__ __forceinline__ int frame_out_start(const FftPlan &pl, int k) {
 
 // MODE 0: filter (K2).  MODE 1: noise (K5), UT = uniform dtype.
 template <int MODE, typename UT, int SPEC>
-__global__ void __launch_bounds__(FFT_THREADS)
+__global__ void __launch_bounds__(FFT_THREADS, 2)
 k_stft(const FftSeg *__restrict__ segs, const FftJob *__restrict__ jobs, const FftPlan *__restrict__ plans,
        const float2 *__restrict__ twpool, const float *__restrict__ winpool,
        const float *__restrict__ in_f, const UT *__restrict__ in_u, const float *__restrict__ envpool,
