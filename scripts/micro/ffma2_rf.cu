@@ -104,6 +104,8 @@ __global__ void __launch_bounds__(128, 6) kL(float2 *out, int nblk) {
     delta2[p] = f2(-1e-3f - threadIdx.x * 1e-6f, -2e-3f);
     sigma2[p] = f2(1.0f, (threadIdx.x & 1) ? -1.0f : 1.0f);
   }
+  float2 w4[4], d4[4];
+  for (int p = 0; p < 4; p++) { w4[p] = f2(0.1f + threadIdx.x * 1e-3f, 0.2f + p); d4[p] = f2(-1e-3f - threadIdx.x * 1e-6f, -2e-3f - p * 1e-4f); }
   float2 acc[4] = {f2(0, 0), f2(0, 0), f2(0, 0), f2(0, 0)};
   for (int b = 0; b < nblk; b++) {
     if (V == 0) {          // general: per-lane sigma, 2 chains, 4 FFMA2 per pair-row
@@ -179,6 +181,38 @@ __global__ void __launch_bounds__(128, 6) kL(float2 *out, int nblk) {
         }
       }
       acc[0].x += bb[0].x + dd[0].y; acc[1].x += bb[1].x + dd[1].y;
+    } else if (V == 6) {   // standard 3-op, FOUR pairs per lane share {Y, dY}: more operand reuse per load
+      float2 b1[4], b2[4];
+#pragma unroll
+      for (int c = 0; c < 4; c++) { b1[c] = f2(0, 0); b2[c] = f2(0, 0); }
+#pragma unroll 8
+      for (int m = ROWS - 1; m >= 0; m--) {
+        const float4 q = tab[m];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          float2 a_ = __ffma2_rn(w4[c], f2(q.z, q.w), f2(q.x, q.y));
+          float2 nb = __fadd2_rn(__ffma2_rn(d4[c], b1[c], a_), f2(-b2[c].x, -b2[c].y));
+          b2[c] = b1[c]; b1[c] = nb;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 4; c++) acc[c].x += b1[c].x + b2[c].y;
+    } else if (V == 7) {   // sigma = +1 Reinsch, four pairs per lane
+      float2 bb[4], dd[4];
+#pragma unroll
+      for (int c = 0; c < 4; c++) { bb[c] = f2(0, 0); dd[c] = f2(0, 0); }
+#pragma unroll 8
+      for (int m = ROWS - 1; m >= 0; m--) {
+        const float4 q = tab[m];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          float2 a_ = __ffma2_rn(w4[c], f2(q.z, q.w), f2(q.x, q.y));
+          dd[c] = __ffma2_rn(d4[c], bb[c], __fadd2_rn(dd[c], a_));
+          bb[c] = __fadd2_rn(bb[c], dd[c]);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 4; c++) acc[c].x += bb[c].x + dd[c].y;
     } else if (V == 5) {   // standard (unstable) Clenshaw, 3 ops: b_new = fma(c2, b1, a) - b2
       float2 b1[2] = {f2(0, 0), f2(0, 0)}, b2[2] = {f2(0, 0), f2(0, 0)};
 #pragma unroll 8
@@ -231,6 +265,8 @@ int main() {
   ms = timeit([&] { kL<3><<<blocks, 128>>>(d, nblk); }); printf("L3 sigma=+1 4 chains  : %.3f, %.3f\n", rate(rows * 8, ms), rate(rows * 2, ms));
   ms = timeit([&] { kL<4><<<blocks, 128>>>(d, nblk); }); printf("L4 sigma=+1 folded    : %.3f, %.3f\n", rate(rows * 8, ms), rate(rows * 2, ms));
   ms = timeit([&] { kL<5><<<blocks, 128>>>(d, nblk); }); printf("L5 standard 3-op      : %.3f (as 6 ops), %.3f\n", rate(rows * 6, ms), rate(rows * 2, ms));
+  ms = timeit([&] { kL<6><<<blocks, 128>>>(d, nblk); }); printf("L6 standard 3-op, 4 pairs/lane : %.3f (as 12 ops), %.3f pair-rows/clk/SMSP\n", rate(rows * 12, ms), rate(rows * 4, ms));
+  ms = timeit([&] { kL<7><<<blocks, 128>>>(d, nblk); }); printf("L7 sigma=+1, 4 pairs/lane      : %.3f (as 16 ops), %.3f pair-rows/clk/SMSP\n", rate(rows * 16, ms), rate(rows * 4, ms));
   printf("clock %.0f MHz, %d SMs\n", clk / 1e6, sms);
   return 0;
 }
