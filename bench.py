@@ -164,6 +164,8 @@ def main():
         torch.cuda.set_device(local)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     assert L.sgb_set_device(local) == 0
+    from soundgen_beta_b200 import sharding
+    numa_cpus = sharding.bind_to_gpu_numa(L, local) if world > 1 else []
 
     sizes = {0: 1, 1: 1024, 2: 4096, 3: 8192, 4: max(1, 65536 // world)}   # cfg4: one sweep shared by the ranks
     n = args.batch or sizes[args.config]
@@ -317,7 +319,7 @@ def main():
                        'uniforms': 'float32'},
             'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': int(bb.h2d_bytes()),
                     'd2h_bytes_per_step': int(d2h_bytes), 'ms_per_step': dt_e2e / args.steps * 1e3,
-                    'pipeline': npipe, 'runners': args.runners},
+                    'pipeline': npipe, 'runners': args.runners, 'cpus_bound': len(numa_cpus)},
             'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline,
             'roofline_filter': roof_filter, 'cpu_baseline': cpu,
             'stage_ms': {nm: float(v) for nm, v in zip(_abi.T_NAMES, stage_ms)},

@@ -47,6 +47,9 @@ int         sgb_set_device(int device);
 
 /* Page-locks / unlocks a caller-owned host buffer so that the library's
  * cudaMemcpyAsync calls on it are true DMA transfers (optional). */
+/* PCI bus id ("0000:1b:00.0") of a CUDA device: lets a one-process-per-GPU launcher bind the process to
+ * the GPU's NUMA node before it allocates its pinned buffers. */
+int sgb_device_pci_bus_id(int device, char *out, int cap);
 int sgb_pin(void *ptr, int64_t bytes);
 int sgb_unpin(void *ptr);
 /* Measures the FP32 FMA throughput of the current device with a dependent-chain

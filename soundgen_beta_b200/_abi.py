@@ -84,7 +84,7 @@ class SylArtefacts(C.Structure):
                 ('raw_max', f64)]
 
 
-EXPORTS = ['sgb_version', 'sgb_last_error', 'sgb_device_count', 'sgb_set_device', 'sgb_pin', 'sgb_unpin',
+EXPORTS = ['sgb_version', 'sgb_last_error', 'sgb_device_count', 'sgb_set_device', 'sgb_pin', 'sgb_unpin', 'sgb_device_pci_bus_id',
            'sgb_measure_fp32_peak',
            'sgb_batch_create', 'sgb_batch_destroy', 'sgb_batch_upload', 'sgb_batch_run',
            'sgb_batch_lengths', 'sgb_batch_fetch_f32', 'sgb_batch_fetch_f64', 'sgb_batch_status',
@@ -118,6 +118,7 @@ def load():
     L.sgb_device_count.restype = C.c_int
     L.sgb_set_device.argtypes = [C.c_int]
     L.sgb_pin.argtypes = [vp, i64]
+    L.sgb_device_pci_bus_id.argtypes = [C.c_int, C.c_char_p, C.c_int]
     L.sgb_unpin.argtypes = [vp]
     L.sgb_measure_fp32_peak.argtypes = [C.POINTER(f64)]
     L.sgb_batch_create.argtypes = [C.POINTER(vp)]

@@ -119,6 +119,24 @@ struct DBuf {
   template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+// grow-only page-locked host buffer: small device -> host results land here so that their copies are
+// truly asynchronous and the waiting thread can sleep (wait_stream) instead of spinning in a staged copy
+struct HBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+  template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
 static int64_t align4(int64_t x) { return (x + 3) & ~(int64_t)3; }
 
 // seq(from, to, by) length: floor((to-from)/by + 1e-10) + 1
@@ -131,6 +149,7 @@ struct sgb_batch {
   int device = 0;
   cudaStream_t st = nullptr;
   cudaEvent_t ev[SGB_T_COUNT + 2];
+  cudaEvent_t ev_wait = nullptr;   // blocking-sync event: the host thread sleeps instead of spinning (see wait_stream)
   bool have_desc = false, have_run = false;
   // host copies of the small tables
   std::vector<sgb_call> calls;
@@ -145,6 +164,7 @@ struct sgb_batch {
   DBuf d_bouts, d_syls, d_noises, d_envs, d_frefs, d_pitch, d_anchors, d_formants, d_z, d_u, d_pre;
   DBuf d_gc_off, d_h_off, d_ctrl, d_lay, d_totals, d_summary, d_tiles, d_epmax;
   DBuf p_pitch_w, p_i32[6], p_f64[19], p_pc;
+  HBuf h_tot, h_summary, h_lay;   // pinned landing zones of the two mid-run read-backs
   DBuf d_amp, d_amp32, d_wave, d_raw, d_sound, d_voiced, d_filt, d_noise_raw, d_noise_fin, d_env, d_out, d_out64;
   DBuf d_bl, d_place, d_nl, d_envinst, d_plans, d_tw, d_win, d_fjobs, d_njobs, d_fsegs, d_nsegs, d_max;
   Pools pools;
@@ -184,6 +204,15 @@ __global__ void k_checksum(const uint32_t *p, size_t n, unsigned long long *out)
   if ((threadIdx.x & 31) == 0) atomicAdd(out, a);
 }
 
+// Waits for everything queued on the handle's stream WITHOUT spinning: with several handles driven by
+// several host threads (and one process per GPU) a spinning cudaStreamSynchronize per thread oversubscribes
+// the host cores; a blocking-sync event lets the thread sleep until the stream gets there.
+static cudaError_t wait_stream(sgb_batch *b) {
+  cudaError_t e = cudaEventRecord(b->ev_wait, b->st);
+  if (e != cudaSuccess) return e;
+  return cudaEventSynchronize(b->ev_wait);
+}
+
 extern "C" {
 
 int sgb_version(void) { return SGB_VERSION; }
@@ -196,6 +225,12 @@ int sgb_device_count(void) {
 }
 int sgb_set_device(int device) {
   CK(cudaSetDevice(device));
+  return SGB_OK;
+}
+
+int sgb_device_pci_bus_id(int device, char *out, int cap) {
+  if (!out || cap < 16) return fail(SGB_ERR_INVALID, "bad buffer");
+  CK(cudaDeviceGetPCIBusId(out, cap, device));
   return SGB_OK;
 }
 
@@ -250,6 +285,7 @@ int sgb_batch_create(sgb_batch **out) {
   CK(cudaGetDevice(&b->device));
   CK(cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking));
   for (auto &e : b->ev) CK(cudaEventCreate(&e));
+  CK(cudaEventCreateWithFlags(&b->ev_wait, cudaEventBlockingSync | cudaEventDisableTiming));
   memset(&b->info, 0, sizeof b->info);
   *out = b;
   return SGB_OK;
@@ -258,7 +294,7 @@ int sgb_batch_create(sgb_batch **out) {
 void sgb_batch_destroy(sgb_batch *b) {
   if (!b) return;
   cudaSetDevice(b->device);
-  cudaStreamSynchronize(b->st);
+  wait_stream(b);
   DBuf *all[] = {&b->d_bouts, &b->d_syls, &b->d_noises, &b->d_envs, &b->d_frefs, &b->d_pitch, &b->d_anchors,
                  &b->d_formants, &b->d_z, &b->d_u, &b->d_pre, &b->d_gc_off, &b->d_h_off, &b->d_ctrl, &b->d_lay,
                  &b->d_totals, &b->d_summary, &b->d_tiles, &b->d_epmax, &b->p_pitch_w, &b->d_amp, &b->d_amp32, &b->d_wave, &b->d_raw,
@@ -269,6 +305,7 @@ void sgb_batch_destroy(sgb_batch *b) {
   for (auto &d : b->p_i32) d.release();
   for (auto &d : b->p_f64) d.release();
   b->p_pc.release();
+  b->h_tot.release(); b->h_summary.release(); b->h_lay.release();
   for (auto &e : b->ev) cudaEventDestroy(e);
   cudaStreamDestroy(b->st);
   delete b;
@@ -389,7 +426,7 @@ int sgb_batch_upload(sgb_batch *b, const sgb_batch_desc *D) {
   if ((rc = upload_array(b, b->d_h_off, h_off.data(), 8 * (size_t)(S + 1)))) return rc;
   CK(cudaEventRecord(b->ev[SGB_T_COUNT + 1], b->st));
   b->where = 10;
-  CK(cudaStreamSynchronize(b->st));   // gc_off / h_off are stack vectors
+  CK(wait_stream(b));   // gc_off / h_off are stack vectors
   b->where = 0;
   CK(cudaEventElapsedTime(&b->info.ms[SGB_T_H2D], b->ev[SGB_T_COUNT], b->ev[SGB_T_COUNT + 1]));
 
@@ -551,11 +588,14 @@ int sgb_batch_run(sgb_batch *b, sgb_run_info *info_out) {
   launch_control(d_syl, S, b->d_pitch.as<double>(), b->d_anchors.as<double>(), b->d_z.as<double>(), P, d_ctrl, d_lay,
                  d_tot, st);
   launches += 2;
-  int64_t tot[8];
+  CK(b->h_tot.ensure(64));
+  CK(b->h_summary.ensure(sizeof(SylSummary) * (size_t)S));
+  CK(b->h_lay.ensure(sizeof(SylLayout) * (size_t)S));
+  int64_t *tot = b->h_tot.as<int64_t>();
   CK(cudaMemcpyAsync(tot, d_tot, 64, cudaMemcpyDeviceToHost, st));
   CK(cudaEventRecord(ev[1], st)); trace_mark(b, 1);
   b->where = 1;
-  CK(cudaStreamSynchronize(st));
+  CK(wait_stream(b));
   b->where = 0;
   CK(cudaGetLastError());
   const int64_t amp_total = tot[0], wave_total = tot[1], n_tiles = tot[2], raw_total = tot[3];
@@ -585,14 +625,16 @@ int sgb_batch_run(sgb_batch *b, sgb_run_info *info_out) {
   launches += 2;
   b->summary.resize(S);
   b->lay_host.resize(S);
-  CK(cudaMemcpyAsync(b->summary.data(), b->d_summary.p, sizeof(SylSummary) * (size_t)S, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(b->lay_host.data(), d_lay, sizeof(SylLayout) * (size_t)S, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(b->h_summary.p, b->d_summary.p, sizeof(SylSummary) * (size_t)S, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(b->h_lay.p, d_lay, sizeof(SylLayout) * (size_t)S, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(tot, d_tot, 64, cudaMemcpyDeviceToHost, st));
   CK(cudaEventRecord(ev[4], st)); trace_mark(b, 4);
   b->where = 2;
-  CK(cudaStreamSynchronize(st));
+  CK(wait_stream(b));
   b->where = 0;
   CK(cudaGetLastError());
+  memcpy(b->summary.data(), b->h_summary.p, sizeof(SylSummary) * (size_t)S);
+  memcpy(b->lay_host.data(), b->h_lay.p, sizeof(SylLayout) * (size_t)S);
   info.synth_partials = tot[4];
   info.synth_samples = tot[5];
 
@@ -854,7 +896,7 @@ int sgb_batch_run(sgb_batch *b, sgb_run_info *info_out) {
   launches++;
   CK(cudaEventRecord(ev[10], st)); trace_mark(b, 10);
   b->where = 3;
-  CK(cudaStreamSynchronize(st));
+  CK(wait_stream(b));
   b->where = 0;
   CK(cudaGetLastError());
   if (stft_timeout_flag()) return fail(SGB_ERR_CUDA, "k_stft: a staged (TMA) frame load did not complete");
@@ -909,7 +951,7 @@ static int fetch_common(sgb_batch *b, void *out, int64_t n, bool f64) {
   }
   if (need > 0) CK(cudaMemcpyAsync(out, src, (size_t)need * esz, cudaMemcpyDeviceToHost, st));
   CK(cudaEventRecord(b->ev[SGB_T_COUNT + 1], st));
-  CK(cudaStreamSynchronize(st));
+  CK(wait_stream(b));
   CK(cudaEventElapsedTime(&b->info.ms[SGB_T_D2H], b->ev[SGB_T_COUNT], b->ev[SGB_T_COUNT + 1]));
   return SGB_OK;
 }
@@ -955,7 +997,7 @@ int sgb_batch_checksums(sgb_batch *b, uint64_t *out, int32_t cap) {
   sum(7, b->d_sound.p, 4 * (size_t)b->last_sound);
   sum(8, b->d_out.p, 4 * (size_t)b->total_out);
   CK(cudaMemcpyAsync(out, d.p, 8 * 9, cudaMemcpyDeviceToHost, b->st));
-  CK(cudaStreamSynchronize(b->st));
+  CK(wait_stream(b));
   d.release();
   return SGB_OK;
 }

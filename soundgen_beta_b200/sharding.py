@@ -25,3 +25,26 @@ def aggregate(dist, dt: float, dt_e2e: float, audio_s: float, device=None):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dist.all_reduce(a, op=dist.ReduceOp.SUM)
     return float(t[0]), float(t[1]), float(a[0])
+
+
+def bind_to_gpu_numa(L, device: int) -> list:
+    """Pins the calling process (and the threads it starts later) to the CPUs NVML reports as local to CUDA
+    device `device`, so that a rank's pinned buffers and its upload / fetch threads live on the GPU's NUMA
+    node.  Best effort: returns the CPU list, [] when NVML or the affinity call is unavailable."""
+    import ctypes
+    import os
+    try:
+        import pynvml
+        buf = ctypes.create_string_buffer(32)
+        if L.sgb_device_pci_bus_id(device, buf, 32) != 0:
+            return []
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(buf.value)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * i + b for i, w in enumerate(mask) for b in range(64) if (int(w) >> b) & 1]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return []
