@@ -250,12 +250,22 @@ def main():
     pipe.run_steps(args.steps)
     barrier()
     dt_e2e = time.perf_counter() - t1
+    d2h_f32 = sum(o.nbytes for o in pipe.outs)
+    # the same end to end, fetching 16-bit PCM (what the reference's savePath branch writes): half the D2H bytes
+    pipe.run_steps(1, dtype=np.int16)
+    barrier()
+    t2 = time.perf_counter()
+    pipe.run_steps(args.steps, dtype=np.int16)
+    barrier()
+    dt_wav = time.perf_counter() - t2
+    d2h_i16 = sum(o.nbytes for o in pipe.outs)
     stuck.cancel()
-    d2h_bytes = sum(o.nbytes for o in pipe.outs)
+    d2h_bytes = d2h_f32
     clocks = sampler.stop()
     stage_ms /= args.steps
 
-    dt, dt_e2e, audio_total = sharding.aggregate(dist, dt, dt_e2e, audio_s, device='cuda' if dist is not None else None)
+    dt, dt_e2e, audio_total, dt_wav = sharding.aggregate(dist, dt, dt_e2e, audio_s,
+                                                         device='cuda' if dist is not None else None, extra=(dt_wav,))
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -320,6 +330,9 @@ def main():
             'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': int(bb.h2d_bytes()),
                     'd2h_bytes_per_step': int(d2h_bytes), 'ms_per_step': dt_e2e / args.steps * 1e3,
                     'pipeline': npipe, 'runners': args.runners, 'cpus_bound': len(numa_cpus)},
+            'e2e_wav16': {'value': audio_total * args.steps / dt_wav, 'unit': UNIT, 'ms_per_step': dt_wav / args.steps * 1e3,
+                          'd2h_bytes_per_step': int(d2h_i16),
+                          'note': 'same pipeline, waveforms fetched as 16-bit PCM (the savePath / WAV format)'},
             'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline,
             'roofline_filter': roof_filter, 'cpu_baseline': cpu,
             'stage_ms': {nm: float(v) for nm, v in zip(_abi.T_NAMES, stage_ms)},

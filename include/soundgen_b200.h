@@ -189,6 +189,10 @@ int sgb_batch_lengths(sgb_batch *b, int64_t *out_len /* n_calls */);
 /* Concatenated outputs of all calls, call c at sum(len[0..c)). */
 int sgb_batch_fetch_f32(sgb_batch *b, float *out, int64_t n);
 int sgb_batch_fetch_f64(sgb_batch *b, double *out, int64_t n);
+/* The same, as the 16-bit PCM samples the reference's savePath branch writes (R/soundgen.R:855-857 ->
+ * seewave::savewav -> tuneR::normalize(unit = "16")): centred, largest magnitude scaled to
+ * min(1, max(x)), round(x * 32767).  Halves the device -> host bytes. */
+int sgb_batch_fetch_pcm16(sgb_batch *b, int16_t *out, int64_t n);
 /* Per-call failure flags (0 = ok, else an SGB_ERR_* code). */
 int sgb_batch_status(sgb_batch *b, int32_t *out_status /* n_calls */);
 

@@ -869,3 +869,17 @@ def generateNoise(length, noiseAnchors=((0, 300), (-120, -120)), rolloffNoise=-6
     breathing = matchLengths(breathing, length)
     breathing = breathing / np.max(breathing) * breathingStrength
     return fadeInOut(breathing, length_fade=math.floor(attackLen * samplingRate / 1000))
+
+
+def savewav_pcm16(x):
+    """The 16-bit samples seewave::savewav(x, f) writes (seewave.r:5192-5229 with rescale = NULL):
+    level = max(x) if max(x) <= 1 else 1, then tuneR::normalize(unit = "16", centre = TRUE, level)
+    (tuneR normalize.R): x - mean(x); level * x / max|x|; round(x * 32767)."""
+    x = np.asarray(x, dtype=np.float64)
+    mx = float(np.max(x))
+    level = mx if mx <= 1 else 1.0
+    xc = x - np.mean(x)
+    m = float(np.max(np.abs(xc)))
+    if abs(m) > 1.5e-8:                      # !isTRUE(all.equal(m, 0))
+        xc = level * xc / m
+    return np.rint(xc * 32767).astype(np.int64)

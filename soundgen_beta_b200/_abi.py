@@ -87,7 +87,7 @@ class SylArtefacts(C.Structure):
 EXPORTS = ['sgb_version', 'sgb_last_error', 'sgb_device_count', 'sgb_set_device', 'sgb_pin', 'sgb_unpin', 'sgb_device_pci_bus_id',
            'sgb_measure_fp32_peak',
            'sgb_batch_create', 'sgb_batch_destroy', 'sgb_batch_upload', 'sgb_batch_run',
-           'sgb_batch_lengths', 'sgb_batch_fetch_f32', 'sgb_batch_fetch_f64', 'sgb_batch_status',
+           'sgb_batch_lengths', 'sgb_batch_fetch_f32', 'sgb_batch_fetch_f64', 'sgb_batch_fetch_pcm16', 'sgb_batch_status',
            'sgb_batch_syllable_len', 'sgb_batch_syllable_fetch', 'sgb_batch_noise_fetch',
            'sgb_batch_artefacts', 'sgb_batch_artefact_ints', 'sgb_batch_pitch_per_gc', 'sgb_batch_checksums', 'sgb_batch_debug_state',
            'sgb_get_rolloff', 'sgb_get_spectral_envelope', 'sgb_filter_len', 'sgb_filter']
@@ -129,6 +129,7 @@ def load():
     L.sgb_batch_lengths.argtypes = [vp, vp]
     L.sgb_batch_fetch_f32.argtypes = [vp, vp, i64]
     L.sgb_batch_fetch_f64.argtypes = [vp, vp, i64]
+    L.sgb_batch_fetch_pcm16.argtypes = [vp, vp, i64]
     L.sgb_batch_status.argtypes = [vp, vp]
     L.sgb_batch_syllable_len.argtypes = [vp, i32, C.POINTER(i64)]
     L.sgb_batch_syllable_fetch.argtypes = [vp, i32, vp, i64]

@@ -533,7 +533,9 @@ class Batch:
         total = int(lens.sum())
         if out is None:
             out = np.zeros(max(total, 1), dtype=dtype)
-        if np.dtype(dtype) == np.float32:
+        if np.dtype(dtype) == np.int16:     # WAV samples as the reference's savePath branch writes them
+            _check(self.L.sgb_batch_fetch_pcm16(self.h, _ptr(out), out.size))
+        elif np.dtype(dtype) == np.float32:
             _check(self.L.sgb_batch_fetch_f32(self.h, _ptr(out), out.size))
         else:
             _check(self.L.sgb_batch_fetch_f64(self.h, _ptr(out), out.size))
@@ -628,7 +630,10 @@ class PipelinedBatches:
 
     def _fetch(self, i, dtype):
         bt = self.batches[i]
-        if self.outs[i] is None or self.outs[i].dtype != np.dtype(dtype):
+        if self.outs[i] is not None and self.outs[i].dtype != np.dtype(dtype):
+            _abi.load().sgb_unpin(self.outs[i].ctypes.data)     # a registration must not outlive its array
+            self.outs[i] = None
+        if self.outs[i] is None:
             n = int(bt.lengths().sum())
             self.outs[i] = np.zeros(max(n, 1), dtype=dtype)
             _abi.load().sgb_pin(self.outs[i].ctypes.data, self.outs[i].nbytes)

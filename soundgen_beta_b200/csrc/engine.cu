@@ -165,6 +165,8 @@ struct sgb_batch {
   DBuf d_gc_off, d_h_off, d_ctrl, d_lay, d_totals, d_summary, d_tiles, d_epmax;
   DBuf p_pitch_w, p_i32[6], p_f64[19], p_pc;
   HBuf h_tot, h_summary, h_lay;   // pinned landing zones of the two mid-run read-backs
+  HBuf h_calltab;
+  DBuf d_pcm, d_calltab;
   DBuf d_amp, d_amp32, d_wave, d_raw, d_sound, d_voiced, d_filt, d_noise_raw, d_noise_fin, d_env, d_out, d_out64;
   DBuf d_bl, d_place, d_nl, d_envinst, d_plans, d_tw, d_win, d_fjobs, d_njobs, d_fsegs, d_nsegs, d_max;
   Pools pools;
@@ -193,6 +195,42 @@ static void CUDART_CB trace_cb(void *p) { *reinterpret_cast<volatile int *>(p) =
 static void trace_mark(sgb_batch *b, int i) {
   if (!g_trace) return;
   cudaLaunchHostFunc(b->st, trace_cb, (void *)&b->reached[i]);
+}
+
+// 16-bit PCM of every call's waveform as seewave::savewav writes it (soundgen.R:855-857, seewave.r:5192-5229
+// -> tuneR::normalize(unit = "16", level = min(1, max(x))), tuneR normalize.R): centre, scale the largest
+// magnitude to `level`, round(x * 32767).  One CTA per call; reductions in a fixed order (reproducible).
+__global__ void __launch_bounds__(256)
+k_pcm16(const float *__restrict__ outp, const int64_t *__restrict__ off, const int64_t *__restrict__ len,
+        int16_t *__restrict__ pcm) {
+  __shared__ double rs[8], rm[8], ra[8];
+  const int64_t n = len[blockIdx.x];
+  const float *x = outp + off[blockIdx.x];
+  int16_t *y = pcm + off[blockIdx.x];
+  if (n <= 0) return;
+  double sum = 0.0, mx = -INFINITY;
+  for (int64_t i = threadIdx.x; i < n; i += 256) { double v = (double)x[i]; sum += v; mx = fmax(mx, v); }
+  for (int o = 16; o > 0; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+  if ((threadIdx.x & 31) == 0) { rs[threadIdx.x >> 5] = sum; rm[threadIdx.x >> 5] = mx; }
+  __syncthreads();
+  sum = 0.0; mx = -INFINITY;
+  for (int w = 0; w < 8; w++) { sum += rs[w]; mx = fmax(mx, rm[w]); }
+  const double mean = sum / (double)n;
+  double am = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += 256) am = fmax(am, fabs((double)x[i] - mean));
+  for (int o = 16; o > 0; o >>= 1) am = fmax(am, __shfl_xor_sync(0xffffffffu, am, o));
+  if ((threadIdx.x & 31) == 0) ra[threadIdx.x >> 5] = am;
+  __syncthreads();
+  am = 0.0;
+  for (int w = 0; w < 8; w++) am = fmax(am, ra[w]);
+  const double level = (mx <= 1.0) ? mx : 1.0;
+  const bool scale = fabs(am) > 1.5e-8;          // !isTRUE(all.equal(m, 0))
+  for (int64_t i = threadIdx.x; i < n; i += 256) {
+    double v = (double)x[i] - mean;
+    if (scale) v = level * v / am;
+    v = rint(v * 32767.0);
+    y[i] = (int16_t)fmin(32767.0, fmax(-32768.0, v));
+  }
 }
 
 // position-weighted checksum of a word array (diagnostics)
@@ -305,7 +343,8 @@ void sgb_batch_destroy(sgb_batch *b) {
   for (auto &d : b->p_i32) d.release();
   for (auto &d : b->p_f64) d.release();
   b->p_pc.release();
-  b->h_tot.release(); b->h_summary.release(); b->h_lay.release();
+  b->h_tot.release(); b->h_summary.release(); b->h_lay.release(); b->h_calltab.release();
+  b->d_pcm.release(); b->d_calltab.release();
   for (auto &e : b->ev) cudaEventDestroy(e);
   cudaStreamDestroy(b->st);
   delete b;
@@ -957,6 +996,34 @@ static int fetch_common(sgb_batch *b, void *out, int64_t n, bool f64) {
 }
 int sgb_batch_fetch_f32(sgb_batch *b, float *out, int64_t n) { return fetch_common(b, out, n, false); }
 int sgb_batch_fetch_f64(sgb_batch *b, double *out, int64_t n) { return fetch_common(b, out, n, true); }
+
+// 16-bit PCM (WAV sample format) of every call, normalised as the reference's savePath branch does
+// (k_pcm16): halves the device -> host bytes of a data-generation run.
+int sgb_batch_fetch_pcm16(sgb_batch *b, int16_t *out, int64_t n) {
+  if (!b || !out) return fail(SGB_ERR_INVALID, "null argument");
+  if (!b->have_run) return fail(SGB_ERR_STATE, "no completed run");
+  CK(cudaSetDevice(b->device));
+  int64_t need = 0;
+  for (auto l : b->call_len) need += l;
+  if (n < need) return fail(SGB_ERR_INVALID, "output buffer too small: %lld < %lld", (long long)n, (long long)need);
+  const size_t NC = b->call_len.size();
+  cudaStream_t st = b->st;
+  CK(b->d_pcm.ensure(2 * (size_t)(b->total_out + 64)));
+  CK(b->d_calltab.ensure(16 * std::max<size_t>(NC, 1)));
+  CK(b->h_calltab.ensure(16 * std::max<size_t>(NC, 1)));
+  int64_t *h = b->h_calltab.as<int64_t>();
+  for (size_t c = 0; c < NC; c++) { h[c] = b->call_off[c]; h[NC + c] = b->call_len[c]; }
+  CK(cudaEventRecord(b->ev[SGB_T_COUNT], st));
+  CK(cudaMemcpyAsync(b->d_calltab.p, h, 16 * NC, cudaMemcpyHostToDevice, st));
+  if (NC > 0) k_pcm16<<<(unsigned)NC, 256, 0, st>>>(b->d_out.as<float>(), b->d_calltab.as<int64_t>(),
+                                                   b->d_calltab.as<int64_t>() + NC, b->d_pcm.as<int16_t>());
+  if (need > 0) CK(cudaMemcpyAsync(out, b->d_pcm.p, (size_t)need * 2, cudaMemcpyDeviceToHost, st));
+  CK(cudaEventRecord(b->ev[SGB_T_COUNT + 1], st));
+  CK(wait_stream(b));
+  CK(cudaGetLastError());
+  CK(cudaEventElapsedTime(&b->info.ms[SGB_T_D2H], b->ev[SGB_T_COUNT], b->ev[SGB_T_COUNT + 1]));
+  return SGB_OK;
+}
 
 // Diagnostic for a stuck run (callable from another thread): out[0] = which wait the handle's host thread
 // is in (0 none, 10 upload, 1 after control, 2 after compose, 3 end of run), out[1 + i] = 1 if stage event i

@@ -15,16 +15,17 @@ def shard_range(n_items: int, rank: int, world: int):
     return begin, begin + base + (1 if rank < rem else 0)
 
 
-def aggregate(dist, dt: float, dt_e2e: float, audio_s: float, device=None):
-    """max over ranks of the two timings, sum over ranks of the audio seconds."""
+def aggregate(dist, dt: float, dt_e2e: float, audio_s: float, device=None, extra=()):
+    """max over ranks of the timings (dt, dt_e2e, *extra), sum over ranks of the audio seconds."""
     if dist is None:
-        return dt, dt_e2e, audio_s
+        return (dt, dt_e2e, audio_s) + tuple(extra) if extra else (dt, dt_e2e, audio_s)
     import torch
-    t = torch.tensor([dt, dt_e2e], dtype=torch.float64, device=device)
+    t = torch.tensor([dt, dt_e2e] + list(extra), dtype=torch.float64, device=device)
     a = torch.tensor([audio_s], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dist.all_reduce(a, op=dist.ReduceOp.SUM)
-    return float(t[0]), float(t[1]), float(a[0])
+    out = (float(t[0]), float(t[1]), float(a[0]))
+    return out + tuple(float(v) for v in t[2:]) if extra else out
 
 
 def bind_to_gpu_numa(L, device: int) -> list:

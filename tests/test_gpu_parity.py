@@ -101,6 +101,26 @@ def test_generate_noise_with_a_literal_filter_matrix():
         assert rel(y, ref) < TOL
 
 
+def test_pcm16_fetch_matches_savewav():
+    # savePath branch (R/soundgen.R:855-857): seewave::savewav -> tuneR::normalize(unit = '16').  The device
+    # quantises its FP32 waveform (error ~2e-6 of peak = 0.07 LSB), so a sample may land one step away from
+    # the oracle's; one LSB is 3e-5 of peak, inside the 1e-4 bar.
+    calls = workloads.config1(n=3) + workloads.config0()
+    bb = sg.BatchBuilder()
+    for kw in calls:
+        bb.add_soundgen(**kw)
+    bt = sg.Batch()
+    bt.upload(bb.build())
+    bt.run()
+    pcm = bt.fetch(np.int16)
+    for kw, q in zip(calls, pcm):
+        ref = so.savewav_pcm16(_oracle_call(kw))
+        assert q.dtype == np.int16 and q.size == ref.size
+        d = np.abs(q.astype(np.int64) - ref)
+        assert d.max() <= 1 and np.mean(d > 0) < 0.2
+        assert np.max(np.abs(ref)) >= 32700          # the scaling really happened
+
+
 def _oracle_call(kw):
     kw = dict(kw)
     z, u = kw.pop('z', None), kw.pop('u', None)
