@@ -634,7 +634,7 @@ int sgb_batch_run(sgb_batch *b, sgb_run_info *info_out) {
   CK(cudaMemcpyAsync(tot, d_tot, 64, cudaMemcpyDeviceToHost, st));
   CK(cudaEventRecord(ev[1], st)); trace_mark(b, 1);
   b->where = 1;
-  CK(wait_stream(b));
+  CK(cudaStreamSynchronize(st));   // short wait on the critical path: spin (the long waits sleep, see wait_stream)
   b->where = 0;
   CK(cudaGetLastError());
   const int64_t amp_total = tot[0], wave_total = tot[1], n_tiles = tot[2], raw_total = tot[3];
@@ -669,7 +669,7 @@ int sgb_batch_run(sgb_batch *b, sgb_run_info *info_out) {
   CK(cudaMemcpyAsync(tot, d_tot, 64, cudaMemcpyDeviceToHost, st));
   CK(cudaEventRecord(ev[4], st)); trace_mark(b, 4);
   b->where = 2;
-  CK(wait_stream(b));
+  CK(cudaStreamSynchronize(st));
   b->where = 0;
   CK(cudaGetLastError());
   memcpy(b->summary.data(), b->h_summary.p, sizeof(SylSummary) * (size_t)S);

@@ -241,7 +241,8 @@ k_compose(const sgb_syllable *__restrict__ syl, int S, SylCtrl *__restrict__ ctr
     __syncthreads();
     int Lnew;
     if (cl < 2) {
-      for (int i = threadIdx.x; i < L2; i += blockDim.x) comp[Lc1 + i] = a2[i];
+#pragma unroll 8
+      for (int i = threadIdx.x; i < L2; i += COMPOSE_THREADS) comp[Lc1 + i] = a2[i];
       Lnew = Lc1 + L2;
     } else {
       const int idx1 = Lc1 - cl;
@@ -252,7 +253,8 @@ k_compose(const sgb_syllable *__restrict__ syl, int S, SylCtrl *__restrict__ ctr
         double mr = (ir == cl - 1) ? 1.0 : (double)ir * byc;   // rev(multipl)[i]
         comp[idx1 + i] = (float)(mr * (double)comp[idx1 + i] + mu * (double)a2[i]);
       }
-      for (int i = cl + threadIdx.x; i < L2; i += blockDim.x) comp[idx1 + i] = a2[i];
+#pragma unroll 8
+      for (int i = cl + threadIdx.x; i < L2; i += COMPOSE_THREADS) comp[idx1 + i] = a2[i];
       Lnew = idx1 + L2;
     }
     if (threadIdx.x == 0) { C.ep_zc1[e] = zc1; C.ep_zc2[e] = zc2; }
@@ -295,7 +297,8 @@ k_compose(const sgb_syllable *__restrict__ syl, int S, SylCtrl *__restrict__ ctr
 
   // ---- signed maximum (source.R:449: max(waveform), not max|.|) ----
   float m = -INFINITY;
-  for (int i = threadIdx.x; i < Lc; i += blockDim.x) m = fmaxf(m, comp[i]);
+#pragma unroll 8
+  for (int i = threadIdx.x; i < Lc; i += COMPOSE_THREADS) m = fmaxf(m, comp[i]);
   for (int of = 16; of > 0; of >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, of));
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
   __syncthreads();
@@ -339,6 +342,7 @@ k_place_voiced(const sgb_syllable *__restrict__ syl, int S, const SylCtrl *__res
   const int32_t *gcup = P.gcup + o;
   const double *drift = P.drift + o;
   const int G = C.nGC;
+#pragma unroll 4
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < L; k += gridDim.x * blockDim.x) {
     double v = (double)src[k] / inv_max;
     if (lf > 0) {

@@ -95,6 +95,7 @@ k_finalize(const sgb_bout *__restrict__ bouts, const BoutLayout *__restrict__ bl
     bmin = 1.0 / (1.0 + exp(-from * slope));
     bmax = 1.0 / (1.0 + exp(-to * slope));
   }
+#pragma unroll 4
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < L.final_len; k += gridDim.x * blockDim.x) {
     double v = 0.0;
     int rel = k - L.final_shift;
