@@ -88,3 +88,12 @@ def test_invariants_random():
         assert np.all(np.diff(a.integr) > 0)
         assert a.epochs[0, 0] == 1 and a.epochs[-1, 1] == a.gc.size
         assert np.isfinite(y).all() and abs(np.max(y)) <= 1.0 + 0.5
+
+
+def test_savewav_pcm16_known_answers():
+    # seewave::savewav -> tuneR::normalize(unit = '16'): centred, max |x| -> level = min(1, max(x)), round half even
+    x = np.array([0.0, 0.5, -0.5, 0.25])
+    q = so.savewav_pcm16(x)                  # mean 0.0625; centred max |.| = 0.5625; level = 0.5
+    assert q.tolist() == [int(np.rint(0.5 * (v - 0.0625) / 0.5625 * 32767)) for v in x]
+    assert so.savewav_pcm16(np.array([2.0, -2.0])).tolist() == [32767, -32767]      # level capped at 1
+    assert so.savewav_pcm16(np.zeros(4)).tolist() == [0, 0, 0, 0]                    # all.equal(m, 0): no scaling
