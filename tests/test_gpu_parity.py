@@ -53,6 +53,22 @@ def test_generate_harmonics(T):
         assert y.size == ref.size and rel(y, ref) < TOL
 
 
+@pytest.mark.parametrize('f0a,f0b,sr', [(2400., 3300., 16000.), (900., 2600., 22050.), (55., 70., 48000.)])
+def test_generate_harmonics_pitch_extremes(f0a, f0b, sr):
+    # very high pitch: a warp's 128 samples span more than 16 glottal cycles (K1's direct, unstaged path and
+    # the short staged blocks); very low pitch at 48 kHz: hundreds of rows, one cycle per warp
+    P = 1400
+    pitch = np.exp(np.linspace(np.log(f0a), np.log(f0b), P))
+    z = np.random.default_rng(int(f0a)).standard_normal(20000)
+    pars = dict(samplingRate=sr, pitchFloor=50, pitchCeiling=3500, nonlinBalance=100, jitterDep=1.0, jitterLen=5,
+                shimmerDep=10, rolloff=-6, rolloffOct=-1, rolloffKHz=-2, subFreq=90, subDep=40, shortestEpoch=100,
+                attackLen=10)
+    ref, art = so.generateHarmonics(pitch, rng=so.RStream(z=z), want_artefacts=True, **pars)
+    y, a = sg.generateHarmonics(pitch, z=z, want_artefacts=True, **pars)
+    assert np.array_equal(a['gc_upsampled'], art.gc_upsampled) and np.array_equal(a['epochs'], art.epochs)
+    assert y.size == ref.size and rel(y, ref) < TOL
+
+
 @pytest.mark.parametrize('wl,n,moving,sr', [(800, 16000, False, 16000), (2204, 22050, True, 44100),
                                             (1102, 44100, False, 22050), (2400, 48000, True, 48000),
                                             (160, 5000, False, 16000), (1200, 30000, True, 24000),
