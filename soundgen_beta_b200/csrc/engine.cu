@@ -762,7 +762,7 @@ int sgb_batch_run(sgb_batch *b, sgb_run_info *info_out) {
       if (!L.bypass) {
         L.filt_off = filt_total; filt_total += align4(L.filt_len + 4);
         L.env_off = env_total; env_total += align4((int64_t)(L.wl / 2) * L.nint);
-        EnvInst I; I.out_off = L.env_off; I.env_id = B.env_id; I.nr = L.wl / 2; I.nc = L.nint; I.pad = 0;
+        EnvInst I; I.out_off = L.env_off; I.env_id = B.env_id; I.nr = L.wl / 2; I.nc = L.nint; I.col0 = 0;
         envinst.push_back(I);
         FftJob J; memset(&J, 0, sizeof J);
         J.in_off = L.sound_off; J.out_off = L.filt_off; J.env_off = L.env_off; J.plan = L.fft_plan;
@@ -810,7 +810,7 @@ int sgb_batch_run(sgb_batch *b, sgb_run_info *info_out) {
           const sgb_envelope &E = b->envs[N.env_id];
           Q.nc_env = std::max(1, E.nc_fixed);
           Q.env_off = env_total; env_total += align4((int64_t)(N.wl / 2) * Q.nc_env);
-          EnvInst I; I.out_off = Q.env_off; I.env_id = N.env_id; I.nr = N.wl / 2; I.nc = Q.nc_env; I.pad = 0;
+          EnvInst I; I.out_off = Q.env_off; I.env_id = N.env_id; I.nr = N.wl / 2; I.nc = Q.nc_env; I.col0 = 0;
           envinst.push_back(I);
         }
         FftJob J; memset(&J, 0, sizeof J);
@@ -839,6 +839,8 @@ int sgb_batch_run(sgb_batch *b, sgb_run_info *info_out) {
   std::vector<float> &win_host = PT.win;
   const int64_t tw_total = (int64_t)tw_host.size(), win_total = (int64_t)win_host.size();
   // ---- upload layout ----
+  int max_nc = 0;   // total (instance, column) work items of K4: the kernel runs one CTA per item
+  for (auto &I : envinst) { I.col0 = max_nc; max_nc += I.nc; }
   CK(b->d_bl.ensure(sizeof(BoutLayout) * (size_t)NB));
   CK(b->d_place.ensure(sizeof(SylPlace) * (size_t)S));
   CK(b->d_nl.ensure(sizeof(NoiseLayout) * (size_t)std::max(NN, 1)));
@@ -890,8 +892,6 @@ int sgb_batch_run(sgb_batch *b, sgb_run_info *info_out) {
   }
   CK(cudaEventRecord(ev[5], st)); trace_mark(b, 5);   // assemble (part 1)
   // ---- K4 envelopes (bouts + noises) ----
-  int max_nc = 0;
-  for (auto &I : envinst) max_nc = std::max(max_nc, I.nc);
   launch_envelope_f32(b->d_envinst.as<EnvInst>(), (int)envinst.size(), max_nc, b->d_envs.as<sgb_envelope>(),
                       b->d_frefs.as<sgb_formant_ref>(), b->d_formants.as<double>(), b->d_anchors.as<double>(),
                       b->d_pre.as<double>(), b->d_env.as<float>(), st);
@@ -1223,7 +1223,7 @@ int sgb_get_spectral_envelope(int32_t nr, int32_t nc, const sgb_envelope *env, c
     refs[f].off = rows; refs[f].n = n; refs[f].pad = 0; rows += n;
   }
   E.formant_off = 0; E.mouth_off = 0;
-  EnvInst I; I.out_off = 0; I.env_id = 0; I.nr = nr; I.nc = nc; I.pad = 0;
+  EnvInst I; I.out_off = 0; I.env_id = 0; I.nr = nr; I.nc = nc; I.col0 = -1;
   DBuf dE, dR, dF, dA, dI, dO;
   auto run = [&]() -> int {
     CK(dE.ensure(sizeof E)); CK(dR.ensure(sizeof(sgb_formant_ref) * refs.size())); CK(dF.ensure(32 * (size_t)std::max<int64_t>(rows, 1)));

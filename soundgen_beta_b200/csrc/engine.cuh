@@ -93,7 +93,7 @@ struct EnvInst {
   int32_t env_id;
   int32_t nr;
   int32_t nc;
-  int32_t pad;
+  int32_t col0;         // first column of this instance in the flat (instance, column) work list; -1: 2-D grid
 };
 
 

@@ -248,8 +248,8 @@ k_amp(const sgb_syllable *syl, int S, const SylCtrl *ctrl, const SylLayout *lay,
         }
       }
       __syncthreads();
-      if (tabled && Hk <= AMP_VF && rows <= 256 * AMP_DR) {
-        // Dense variant.  With sub-harmonics only every (n+1)-th row is an f-harmonic (rolloff + exp2, the
+      if (tabled && n > 0 && rows >= 512 && Hk <= AMP_VF && rows <= 256 * AMP_DR) {
+        // Dense variant (epochs with sub-harmonics).  Only every (n+1)-th row is an f-harmonic (rolloff + exp2, the
         // expensive rows); evaluated row by row they would keep 1/(n+1) of a warp's lanes busy.  So per
         // column the f-harmonics are first computed densely over the threads into shared memory
         // (double-buffered: one barrier per column), then every thread writes the rows it owns.

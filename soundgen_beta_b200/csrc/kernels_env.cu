@@ -12,9 +12,21 @@ template <typename OutT>
 __global__ void __launch_bounds__(ENV_THREADS)
 k_envelope(const EnvInst *__restrict__ inst, const sgb_envelope *__restrict__ envs,
            const sgb_formant_ref *__restrict__ fidx, const double *__restrict__ formants,
-           const double *__restrict__ anchors, const double *__restrict__ pre, OutT *__restrict__ out) {
-  const EnvInst I = inst[blockIdx.y];
-  const int c = blockIdx.x;
+           const double *__restrict__ anchors, const double *__restrict__ pre, OutT *__restrict__ out,
+           int n_flat) {
+  // work item -> (instance, column): flat list (gridDim.y == 1; n_inst passed through gridDim.z's slot is
+  // not available, so the instance is found by bisection over col0) or the plain 2-D grid of the API call
+  int ii = blockIdx.y, c = blockIdx.x;
+  if (n_flat > 0) {
+    int lo = 0, hi = n_flat - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (inst[mid].col0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    ii = lo;
+    c = (int)blockIdx.x - inst[lo].col0;
+  }
+  const EnvInst I = inst[ii];
   if (c >= I.nc) return;
   const sgb_envelope E = envs[I.env_id];
   const int nr = I.nr, nc = I.nc;
@@ -114,6 +126,23 @@ k_envelope(const EnvInst *__restrict__ inst, const sgb_envelope *__restrict__ en
   const int n = nF;
   const double boost = exp2(mouth_open * E.openMouthBoost / 10.0);
   OutT *col = out + I.out_off + (int64_t)c * nr;
+  if constexpr (sizeof(OutT) == 4) {
+    // FP32 table for the filter kernels: the log-density difference stays in double (its terms cancel),
+    // the exponentials and the dB sum run in FP32 (relative error of the result ~1e-6)
+    const float fdep = (float)E.formantDep, lip = (float)(E.rolloffLip * mouth_bin), fboost = (float)boost;
+    for (int r = threadIdx.x; r < nr; r += blockDim.x) {
+      const double x = (double)(r + 1), lx = log(x);
+      float v = 0.0f;
+      for (int f = 0; f < n; f++) {
+        const double ld = (g_shape[f] - 1.0) * lx - g_rate[f] * x - g_ref[f];
+        v = fmaf(expf((float)ld), (float)g_amp[f], v);
+      }
+      v = v * fdep;
+      v = (v + lip * (float)(lx * 1.4426950408889634)) * fboost;
+      col[r] = (OutT)exp2f(v / 10.0f);
+    }
+    return;
+  }
   for (int r = threadIdx.x; r < nr; r += blockDim.x) {
     double x = (double)(r + 1), lx = log(x);
     double v = 0.0;
@@ -131,13 +160,13 @@ void launch_envelope_f32(const EnvInst *inst, int n_inst, int max_nc, const sgb_
                          const sgb_formant_ref *fidx, const double *formants, const double *anchors,
                          const double *pre, float *out, cudaStream_t st) {
   if (n_inst <= 0 || max_nc <= 0) return;
-  dim3 g(max_nc, n_inst);
-  k_envelope<float><<<g, ENV_THREADS, 0, st>>>(inst, envs, fidx, formants, anchors, pre, out);
+  // max_nc carries the TOTAL number of (instance, column) work items here: one CTA each, no empty CTAs
+  k_envelope<float><<<max_nc, ENV_THREADS, 0, st>>>(inst, envs, fidx, formants, anchors, pre, out, n_inst);
 }
 void launch_envelope_f64(const EnvInst *inst, int n_inst, int max_nc, const sgb_envelope *envs,
                          const sgb_formant_ref *fidx, const double *formants, const double *anchors,
                          const double *pre, double *out, cudaStream_t st) {
   if (n_inst <= 0 || max_nc <= 0) return;
   dim3 g(max_nc, n_inst);
-  k_envelope<double><<<g, ENV_THREADS, 0, st>>>(inst, envs, fidx, formants, anchors, pre, out);
+  k_envelope<double><<<g, ENV_THREADS, 0, st>>>(inst, envs, fidx, formants, anchors, pre, out, 0);
 }

@@ -93,7 +93,7 @@ __device__ __forceinline__ void fft_pass(XIn x, float2 *__restrict__ y, int N, i
   const int nb = N / r;             // butterflies
   const int m = nb / s;             // N / (s * r)
   if (r == 4) {
-    for (int b = threadIdx.x; b < nb; b += FFT_THREADS) {
+    for (int b = threadIdx.x; b < nb; b += (int)blockDim.x) {
       int p = b / s, q = b - p * s;
       const XIn xi = x + (q + s * p);
       float2 a0 = xi[0], a1 = xi[s * m], a2 = xi[2 * s * m], a3 = xi[3 * s * m];
@@ -113,7 +113,7 @@ __device__ __forceinline__ void fft_pass(XIn x, float2 *__restrict__ y, int N, i
     }
   } else if (r == 3) {
     const float c3 = 0.86602540378443864676f;   // sin(2 pi / 3)
-    for (int b = threadIdx.x; b < nb; b += FFT_THREADS) {
+    for (int b = threadIdx.x; b < nb; b += (int)blockDim.x) {
       int p = b / s, q = b - p * s;
       const XIn xi = x + (q + s * p);
       const int sm = s * m;
@@ -133,7 +133,7 @@ __device__ __forceinline__ void fft_pass(XIn x, float2 *__restrict__ y, int N, i
   } else if (r == 5) {
     const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
     const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
-    for (int b = threadIdx.x; b < nb; b += FFT_THREADS) {
+    for (int b = threadIdx.x; b < nb; b += (int)blockDim.x) {
       int p = b / s, q = b - p * s;
       const XIn xi = x + (q + s * p);
       const int sm = s * m;
@@ -159,7 +159,7 @@ __device__ __forceinline__ void fft_pass(XIn x, float2 *__restrict__ y, int N, i
     }
   } else if (r == 8) {
     const float h = 0.70710678118654752440f;
-    for (int b = threadIdx.x; b < nb; b += FFT_THREADS) {
+    for (int b = threadIdx.x; b < nb; b += (int)blockDim.x) {
       int p = b / s, q = b - p * s;
       const XIn xi = x + (q + s * p);
       const int sm = s * m;
@@ -207,7 +207,7 @@ __device__ __forceinline__ void fft_pass(XIn x, float2 *__restrict__ y, int N, i
       }
     }
   } else if (r == 2) {
-    for (int b = threadIdx.x; b < nb; b += FFT_THREADS) {
+    for (int b = threadIdx.x; b < nb; b += (int)blockDim.x) {
       int p = b / s, q = b - p * s;
       float2 a0 = x[q + s * p], a1 = x[q + s * (p + m)];
       float2 w1 = tw[p * s];
@@ -218,7 +218,7 @@ __device__ __forceinline__ void fft_pass(XIn x, float2 *__restrict__ y, int N, i
   } else {
     // generic radix: one output per work item, omega_r^(jk) looked up in the N-point table
     const int wstep = N / r;
-    for (int idx = threadIdx.x; idx < N; idx += FFT_THREADS) {
+    for (int idx = threadIdx.x; idx < N; idx += (int)blockDim.x) {
       int j = idx / nb, b = idx - j * nb;
       int p = b / s, q = b - p * s;
       const XIn xi = x + (q + s * p);
@@ -324,11 +324,11 @@ k_stft(const FftSeg *__restrict__ segs, const FftJob *__restrict__ jobs, const F
   const float2 *twg = twpool + pl.tw_off;
   const float *wa = winpool + pl.wa_off;
   const float *ws = winpool + pl.ws_off;
-  for (int i = threadIdx.x; i < N; i += FFT_THREADS) tw[i] = twg[i];
-  for (int i = threadIdx.x; i < ring; i += FFT_THREADS) { ola[i] = 0.0f; olb[i] = 0.0f; }
+  for (int i = threadIdx.x; i < N; i += (int)blockDim.x) tw[i] = twg[i];
+  for (int i = threadIdx.x; i < ring; i += (int)blockDim.x) { ola[i] = 0.0f; olb[i] = 0.0f; }
   if (MODE == 1) {
     // rolloff vector 2^(rolloffNoise/10 * log2(1:nr)) (source.R:103-105)
-    for (int i = threadIdx.x; i < nr; i += FFT_THREADS)
+    for (int i = threadIdx.x; i < nr; i += (int)blockDim.x)
       vec[i] = (float)exp2(jb.rolloffNoise / 10.0 * log2((double)(i + 1)));
   }
   if (MODE == 0 && threadIdx.x == 0) {
@@ -378,14 +378,25 @@ k_stft(const FftSeg *__restrict__ segs, const FftJob *__restrict__ jobs, const F
       WinIn W;
       W.a = st + (sA - a0); W.b = st + (hasB ? (frame_in_start(pl, k + 1) - a0) : 0); W.w = wa; W.off = 0; W.hasB = hasB;
       OlaOut O0 = {};
-      // the first pass reads the staged frames through the analysis window (A + iB packing included)
-      float2 *Z = fft_any<-1, SPEC, true, false>(bufA, bufB, pl, tw, W, O0);
+      // Register-butterfly first passes (radix 2/3/4/5/8) read every input once: there the analysis window
+      // and the A + iB packing are fused into the pass.  A generic (prime) first radix reads every input r
+      // times, so those plans (1102 = 29*19*2, 2204, clamped windows) window the frame in a pass of its own.
+      constexpr bool FUSE_CT = (SPEC == 1 || SPEC == 3 || SPEC == 5 || SPEC == 6);
+      const bool fuse_rt = (SPEC == 0) && (pl.radix[0] <= 5 || pl.radix[0] == 8);
+      float2 *Z;
+      if (FUSE_CT || fuse_rt) {
+        Z = fft_any<-1, SPEC, true, false>(bufA, bufB, pl, tw, W, O0);
+      } else {
+        for (int i = threadIdx.x; i < N; i += (int)blockDim.x) bufA[i] = W[i];
+        __syncthreads();
+        Z = fft_any<-1, SPEC, false, false>(bufA, bufB, pl, tw, W, O0);
+      }
       // all generic-proxy reads of this staging buffer are done: make it safe for the next TMA write
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       // ---- split the two spectra, multiply by the envelope, rebuild Hermitian halves ----
       const float *eA = envpool + jb.env_off + (int64_t)((jb.nint > 1) ? k : 0) * nr;
       const float *eB = envpool + jb.env_off + (int64_t)((jb.nint > 1 && hasB) ? (k + 1) : 0) * nr;
-      for (int kk = threadIdx.x; kk < nr; kk += FFT_THREADS) {
+      for (int kk = threadIdx.x; kk < nr; kk += (int)blockDim.x) {
         if (kk == 0) {
           float2 z0 = Z[0];
           Z[0] = make_float2(eA[0] * z0.x, eB[0] * z0.y);
@@ -415,7 +426,7 @@ k_stft(const FftSeg *__restrict__ segs, const FftJob *__restrict__ jobs, const F
         fA = envpool + jb.env_off + (int64_t)cA * nr;
         fB = envpool + jb.env_off + (int64_t)cB * nr;
       }
-      for (int kk = threadIdx.x; kk < nr; kk += FFT_THREADS) {
+      for (int kk = threadIdx.x; kk < nr; kk += (int)blockDim.x) {
         float ro = vec[kk];
         float va = (float)uA[kk] * ro * (fA ? fA[kk] : 1.0f);
         float vb = hasB ? (float)uB[kk] * ro * (fB ? fB[kk] : 1.0f) : 0.0f;
@@ -440,7 +451,7 @@ k_stft(const FftSeg *__restrict__ segs, const FftJob *__restrict__ jobs, const F
     int done_to = (knext < sg.kb) ? frame_out_start(pl, knext) : ((sg.kb >= jb.nc) ? jb.xlen : frame_out_start(pl, sg.kb));
     if (knext >= sg.kb && sg.kb < jb.nc) done_to = flush_hi;
     const int fbase = flushed % ring;
-    for (int t = flushed + threadIdx.x; t < done_to; t += FFT_THREADS) {
+    for (int t = flushed + threadIdx.x; t < done_to; t += (int)blockDim.x) {
       int slot = fbase + (t - flushed);
       if (slot >= ring) slot -= ring;
       float v = ola[slot] + olb[slot];
@@ -464,7 +475,7 @@ k_stft(const FftSeg *__restrict__ segs, const FftJob *__restrict__ jobs, const F
   __syncthreads();
   if (threadIdx.x == 0) {
     float v = red[0];
-    for (int i = 1; i < FFT_THREADS / 32; i++) v = fmaxf(v, red[i]);
+    for (int i = 1; i < (int)(blockDim.x >> 5); i++) v = fmaxf(v, red[i]);
     if (v > -INFINITY) atomicMax(&maxpool[jb.max_slot], float_to_ordered(v));
   }
 }
@@ -513,15 +524,15 @@ static cudaError_t launch_spec(int mode, int u_is_float, const FftSeg *segs, int
   if (mode == 0) {
     auto kf = k_stft<0, float, SPEC>;
     if ((e = ensure_smem(kf, &attr_smem[0][SPEC], smem)) != cudaSuccess) return e;
-    kf<<<n_segs, FFT_THREADS, smem, st>>>(segs, jobs, plans, tw, win, in_f, nullptr, env, out, maxpool);
+    kf<<<n_segs, (SPEC == 0 || SPEC == 2 || SPEC == 4) ? 256 : FFT_THREADS, smem, st>>>(segs, jobs, plans, tw, win, in_f, nullptr, env, out, maxpool);
   } else if (u_is_float) {
     auto kf = k_stft<1, float, SPEC>;
     if ((e = ensure_smem(kf, &attr_smem[1][SPEC], smem)) != cudaSuccess) return e;
-    kf<<<n_segs, FFT_THREADS, smem, st>>>(segs, jobs, plans, tw, win, nullptr, (const float *)in_u, env, out, maxpool);
+    kf<<<n_segs, (SPEC == 0 || SPEC == 2 || SPEC == 4) ? 256 : FFT_THREADS, smem, st>>>(segs, jobs, plans, tw, win, nullptr, (const float *)in_u, env, out, maxpool);
   } else {
     auto kf = k_stft<1, double, SPEC>;
     if ((e = ensure_smem(kf, &attr_smem[2][SPEC], smem)) != cudaSuccess) return e;
-    kf<<<n_segs, FFT_THREADS, smem, st>>>(segs, jobs, plans, tw, win, nullptr, (const double *)in_u, env, out, maxpool);
+    kf<<<n_segs, (SPEC == 0 || SPEC == 2 || SPEC == 4) ? 256 : FFT_THREADS, smem, st>>>(segs, jobs, plans, tw, win, nullptr, (const double *)in_u, env, out, maxpool);
   }
   return cudaGetLastError();
 }
