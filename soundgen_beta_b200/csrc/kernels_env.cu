@@ -1,30 +1,35 @@
 // K4: spectral envelope -- getSpectralEnvelope (R/sourceSpectrum.R:261-566), the
 // deterministic part: formant tracks -> gamma-density bumps + lip radiation + mouth
-// opening + nasalisation -> 2^(dB/10).  One CTA per (column, instance), FP64.
+// opening + nasalisation -> 2^(dB/10).  One WARP per (column, instance) (four per CTA): the per-column
+// set-up runs on a few lanes, so a whole CTA per column would leave most of its threads waiting for it.
 #include "engine.cuh"
 #include "contour.cuh"
 
 #define ENV_THREADS 128
+#define ENV_WARPS (ENV_THREADS / 32)
 #define ENV_MAXF 32        // formants per filter (incl. nasal pole / zero)
 #define ENV_MAXK 64        // knots after the approx() pre-smoothing
 
 template <typename OutT>
-__global__ void __launch_bounds__(ENV_THREADS)
+__global__ void __launch_bounds__(ENV_THREADS, 6)
 k_envelope(const EnvInst *__restrict__ inst, const sgb_envelope *__restrict__ envs,
            const sgb_formant_ref *__restrict__ fidx, const double *__restrict__ formants,
            const double *__restrict__ anchors, const double *__restrict__ pre, OutT *__restrict__ out,
-           int n_flat) {
-  // work item -> (instance, column): flat list (gridDim.y == 1; n_inst passed through gridDim.z's slot is
-  // not available, so the instance is found by bisection over col0) or the plain 2-D grid of the API call
-  int ii = blockIdx.y, c = blockIdx.x;
+           int n_flat, int n_items) {
+  // work item -> (instance, column): flat list (one item per warp; the instance is found by bisection
+  // over col0) or the plain 2-D grid of the stand-alone API call (blockIdx.y = instance)
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int ii = blockIdx.y, c = (int)blockIdx.x * ENV_WARPS + wid;
   if (n_flat > 0) {
+    const int item = c;
+    if (item >= n_items) return;
     int lo = 0, hi = n_flat - 1;
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;
-      if (inst[mid].col0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+      if (inst[mid].col0 <= item) lo = mid; else hi = mid - 1;
     }
     ii = lo;
-    c = (int)blockIdx.x - inst[lo].col0;
+    c = item - inst[lo].col0;
   }
   const EnvInst I = inst[ii];
   if (c >= I.nc) return;
@@ -33,18 +38,21 @@ k_envelope(const EnvInst *__restrict__ inst, const sgb_envelope *__restrict__ en
   if (E.tracks_given == 2) {   // literal nr x nc matrix supplied by the caller (generateNoise's filterNoise)
     const double *m = pre + E.formant_off + (int64_t)c * nr;
     OutT *colL = out + I.out_off + (int64_t)c * nr;
-    for (int r = threadIdx.x; r < nr; r += blockDim.x) colL[r] = (OutT)m[r];
+    for (int r = lane; r < nr; r += 32) colL[r] = (OutT)m[r];
     return;
   }
-  __shared__ double f_freq[ENV_MAXF], f_amp[ENV_MAXF], f_width[ENV_MAXF];
-  __shared__ double g_shape[ENV_MAXF], g_rate[ENV_MAXF], g_ref[ENV_MAXF], g_amp[ENV_MAXF];
-  __shared__ int nF;
-  __shared__ double mouth_open, mouth_bin;
+  __shared__ double sf_freq[ENV_WARPS][ENV_MAXF], sf_amp[ENV_WARPS][ENV_MAXF], sf_width[ENV_WARPS][ENV_MAXF];
+  __shared__ double sg_shape[ENV_WARPS][ENV_MAXF], sg_rate[ENV_WARPS][ENV_MAXF], sg_ref[ENV_WARPS][ENV_MAXF],
+      sg_amp[ENV_WARPS][ENV_MAXF];
+  __shared__ int s_nF[ENV_WARPS];
+  __shared__ double s_mouth_open[ENV_WARPS], s_mouth_bin[ENV_WARPS];
+  double *f_freq = sf_freq[wid], *f_amp = sf_amp[wid], *f_width = sf_width[wid];
+  double *g_shape = sg_shape[wid], *g_rate = sg_rate[wid], *g_ref = sg_ref[wid], *g_amp = sg_amp[wid];
   const int F = min(E.n_formants, ENV_MAXF - 2);
 
   // ---- formant values at column c (sourceSpectrum.R:321-344) ----
-  if ((int)threadIdx.x < F) {
-    const sgb_formant_ref R = fidx[E.formant_off + threadIdx.x];
+  if (lane < F) {
+    const sgb_formant_ref R = fidx[E.formant_off + lane];
     const double *rows = formants + 4 * R.off;
     double val[3];
     if (E.tracks_given) {
@@ -67,12 +75,12 @@ k_envelope(const EnvInst *__restrict__ inst, const sgb_envelope *__restrict__ en
         val[j] = r_spline_at(na, ax, ay, b, cc, d, nc, c);                     // spline(., n = nc)
       }
     }
-    f_freq[threadIdx.x] = val[0]; f_amp[threadIdx.x] = val[1]; f_width[threadIdx.x] = val[2];
+    f_freq[lane] = val[0]; f_amp[lane] = val[1]; f_width[lane] = val[2];
   }
-  __syncthreads();
+  __syncwarp();
 
   // ---- Hz -> bins, mouth opening, nasalisation (sourceSpectrum.R:417-504) ----
-  if (threadIdx.x == 0) {
+  if (lane == 0) {
     double mo = 0.5, mb = 1.0;
     int n = 0;
     if (F > 0) {
@@ -119,18 +127,19 @@ k_envelope(const EnvInst *__restrict__ inst, const sgb_envelope *__restrict__ en
         g_ref[f] = (shape - 1.0) * log(xs) - rate * xs;
       }
     }
-    nF = n; mouth_open = mo; mouth_bin = mb;
+    s_nF[wid] = n; s_mouth_open[wid] = mo; s_mouth_bin[wid] = mb;
   }
-  __syncthreads();
+  __syncwarp();
 
-  const int n = nF;
+  const int n = s_nF[wid];
+  const double mouth_open = s_mouth_open[wid], mouth_bin = s_mouth_bin[wid];
   const double boost = exp2(mouth_open * E.openMouthBoost / 10.0);
   OutT *col = out + I.out_off + (int64_t)c * nr;
   if constexpr (sizeof(OutT) == 4) {
     // FP32 table for the filter kernels: the log-density difference stays in double (its terms cancel),
     // the exponentials and the dB sum run in FP32 (relative error of the result ~1e-6)
     const float fdep = (float)E.formantDep, lip = (float)(E.rolloffLip * mouth_bin), fboost = (float)boost;
-    for (int r = threadIdx.x; r < nr; r += blockDim.x) {
+    for (int r = lane; r < nr; r += 32) {
       const double x = (double)(r + 1), lx = log(x);
       float v = 0.0f;
       for (int f = 0; f < n; f++) {
@@ -143,7 +152,7 @@ k_envelope(const EnvInst *__restrict__ inst, const sgb_envelope *__restrict__ en
     }
     return;
   }
-  for (int r = threadIdx.x; r < nr; r += blockDim.x) {
+  for (int r = lane; r < nr; r += 32) {
     double x = (double)(r + 1), lx = log(x);
     double v = 0.0;
     for (int f = 0; f < n; f++) {
@@ -160,13 +169,14 @@ void launch_envelope_f32(const EnvInst *inst, int n_inst, int max_nc, const sgb_
                          const sgb_formant_ref *fidx, const double *formants, const double *anchors,
                          const double *pre, float *out, cudaStream_t st) {
   if (n_inst <= 0 || max_nc <= 0) return;
-  // max_nc carries the TOTAL number of (instance, column) work items here: one CTA each, no empty CTAs
-  k_envelope<float><<<max_nc, ENV_THREADS, 0, st>>>(inst, envs, fidx, formants, anchors, pre, out, n_inst);
+  // max_nc carries the TOTAL number of (instance, column) work items here: one warp each
+  k_envelope<float><<<(max_nc + ENV_WARPS - 1) / ENV_WARPS, ENV_THREADS, 0, st>>>(inst, envs, fidx, formants, anchors, pre,
+                                                                           out, n_inst, max_nc);
 }
 void launch_envelope_f64(const EnvInst *inst, int n_inst, int max_nc, const sgb_envelope *envs,
                          const sgb_formant_ref *fidx, const double *formants, const double *anchors,
                          const double *pre, double *out, cudaStream_t st) {
   if (n_inst <= 0 || max_nc <= 0) return;
-  dim3 g(max_nc, n_inst);
-  k_envelope<double><<<g, ENV_THREADS, 0, st>>>(inst, envs, fidx, formants, anchors, pre, out, 0);
+  dim3 g((max_nc + ENV_WARPS - 1) / ENV_WARPS, n_inst);
+  k_envelope<double><<<g, ENV_THREADS, 0, st>>>(inst, envs, fidx, formants, anchors, pre, out, 0, 0);
 }
