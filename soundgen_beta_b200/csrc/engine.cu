@@ -1079,7 +1079,7 @@ int sgb_batch_syllable_len(sgb_batch *b, int32_t syl, int64_t *out_len) {
 }
 
 int sgb_batch_syllable_fetch(sgb_batch *b, int32_t syl, double *out, int64_t n) {
-  int64_t len;
+  int64_t len = 0;
   int rc = sgb_batch_syllable_len(b, syl, &len);
   if (rc) return rc;
   if (!b->keep_voiced) return fail(SGB_ERR_STATE, "intermediates are kept only for batches of <= 64 calls");
