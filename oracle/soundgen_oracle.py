@@ -344,9 +344,8 @@ def fadeInOut(ampl, do_fadeIn=True, do_fadeOut=True, length_fade=1000):
 # --------------------------------------------------------------------------
 def getSmoothContour(anchors, length=None, thisIsPitch=False, method='loess',
                      valueFloor=None, valueCeiling=None, samplingRate=16000):
-    """smoothContours.R:53-227.  `anchors` = (time[], value[]).  loess (3-10
-    anchors, the R default) is NOT restated: pass method='spline'
-    or a contour evaluated elsewhere."""
+    """smoothContours.R:53-227.  `anchors` = (time[], value[]).  The loess branch
+    (3-10 anchors, the R default) goes through oracle/rloess.py."""
     if anchors is None:
         return None
     time = np.array(anchors[0], dtype=np.float64)
@@ -383,11 +382,13 @@ def getSmoothContour(anchors, length=None, thisIsPitch=False, method='loess',
         if method == 'spline':
             sc = r_spline(value, length, x=time)
         else:
-            raise NotImplementedError('loess contour (3-10 anchors) is host-side R; not restated')
-        if valueFloor is not None:
-            sc[sc < valueFloor] = valueFloor
-        if valueCeiling is not None:
-            sc[sc > valueCeiling] = valueCeiling
+            from .rloess import smooth_contour_loess
+            sc, _ = smooth_contour_loess(time, value, length, duration_ms, n, valueFloor)
+        with np.errstate(invalid='ignore'):
+            if valueFloor is not None:
+                sc[sc < valueFloor] = valueFloor
+            if valueCeiling is not None:
+                sc[sc > valueCeiling] = valueCeiling
     sc = np.nan_to_num(sc, nan=0.0)
     if thisIsPitch:
         sc = semitonesToHz(sc)
