@@ -89,10 +89,11 @@ def oracle_one(kw):
     kw = dict(kw)
     z = kw.pop('z', None)
     u = kw.pop('u', None)
-    if 'seed' in kw:      # cfg4: generous per-call streams (the oracle consumes what it needs)
-        r = np.random.default_rng(kw.pop('seed'))
-        z, u = [r.standard_normal(200000)], [r.random(6000000)]
-    rng = so.RStream(z=np.concatenate(z) if z else None, u=np.concatenate(u) if u else None)
+    if 'seed' in kw:      # cfg0 / cfg4: R's own stream after set.seed(seed)
+        from oracle.rrng import RRng
+        rng = RRng(kw.pop('seed'))
+    else:
+        rng = so.RStream(z=np.concatenate(z) if z else None, u=np.concatenate(u) if u else None)
     y = osg(rng=rng, **kw)
     return y.size / float(kw.get('samplingRate', 16000))
 
@@ -107,7 +108,7 @@ def run_reference(args, rank, world):
     per_step = max(cores, 2 * cores if args.config in (1,) else cores)
     if args.config == 4:
         per_step = max(per_step, 33)
-    calls = workloads.CONFIGS[args.config](n=per_step) if args.config != 0 else workloads.config0() * per_step
+    calls = workloads.CONFIGS[args.config](n=per_step)
     with mp.Pool(cores) as pool:
         for _ in range(args.warmup):
             pool.map(oracle_one, calls[:cores])
@@ -171,17 +172,12 @@ def main():
     n = args.batch or sizes[args.config]
     gen = workloads.CONFIGS[args.config]
     from soundgen_beta_b200 import sharding
-    calls = gen(n=n, seed=sharding.shard_seed(args.config, rank)) if args.config != 0 else workloads.config0()
+    calls = gen(n=n, seed=sharding.shard_seed(args.config, rank))
     srs = np.array([float(kw.get('samplingRate', 16000)) for kw in calls])
 
     def add_calls(builder, some):
         for kw in some:
-            if 'seed' in kw:     # cfg4: the call's random streams are drawn on demand from its own seed
-                kw = dict(kw)
-                z, u = workloads.streams(kw.pop('seed'), np.float32)
-                builder.add_soundgen(z=z, u=u, **kw)
-            else:
-                builder.add_soundgen(**kw)
+            builder.add_soundgen(**kw)
 
     bb = sg.BatchBuilder(u_dtype=np.float32)   # uniforms travel as float32 (halves the PCIe bytes)
     add_calls(bb, calls)

@@ -38,7 +38,7 @@ extern "C" {
 #define SGB_ERR_STREAM        -5   /* a z/u stream was shorter than the draws needed  */
 #define SGB_ERR_STATE         -6   /* call sequence error on a batch handle           */
 
-#define SGB_VERSION 100
+#define SGB_VERSION 200
 
 int         sgb_version(void);
 const char *sgb_last_error(void);
@@ -63,10 +63,12 @@ int sgb_measure_fp32_peak(double *out_tflops);
 /* ------------------------------------------------------------------------- */
 
 /* Anchors are (time, value) pairs stored interleaved in the `anchors` pool;
- * contour evaluation follows getSmoothContour (R/smoothContours.R:53-227) for 1
- * anchor (flat), 2 anchors (seq) and method = 'spline'; a loess contour (3-10
- * anchors, host-side in R) must be passed pre-evaluated where the struct has a
- * `*_pre_off` field. */
+ * contour evaluation follows getSmoothContour (R/smoothContours.R:53-227): 1
+ * anchor flat, 2 anchors seq(), 3-10 anchors loess (the reference's default
+ * method, fitted on the device where the contour length is only known there),
+ * more than 10 anchors or method 'spline': FMM spline. */
+#define SGB_CONTOUR_LOESS  0
+#define SGB_CONTOUR_SPLINE 1
 
 /* One voiced syllable = one generateHarmonics() call (R/source.R:173-205). */
 typedef struct sgb_syllable {
@@ -80,6 +82,14 @@ typedef struct sgb_syllable {
   int32_t z_cap;         /* normals available                                         */
   int32_t ampl_n;        /* amplAnchors: number of anchors, 0 = NA                    */
   int64_t ampl_off;      /* offset (in pairs) into `anchors`                          */
+  int32_t ampl_method;   /* SGB_CONTOUR_LOESS (reference default) or SGB_CONTOUR_SPLINE */
+  int32_t pitch_anchor_n;/* > 0: the pitch contour is evaluated on the device from these
+                            pitchAnchors (getSmoothContour, thisIsPitch = TRUE, len =
+                            pitch_len, soundgen.R:596-603) and `pitch` is not read      */
+  int64_t pitch_anchor_off; /* offset (pairs) into `anchors`                          */
+  int32_t pitch_method;  /* contour method of the pitch anchors                       */
+  int32_t reserved0;
+  double pitch_scale;    /* pitchDeltas[s] (soundgen.R:603); used with pitch anchors  */
   double attackLen, nonlinBalance, jitterDep, jitterLen, vibratoFreq, vibratoDep,
          shimmerDep, rolloff, rolloffOct, rolloffKHz, rolloffParab, rolloffParabHarm,
          rolloff_perAmpl, temperature, pitchDriftDep, pitchDriftFreq,
@@ -99,6 +109,8 @@ typedef struct sgb_envelope {
   int32_t mouth_n;       /* mouthAnchors: number of anchors, 0 = NA                   */
   int32_t nc_fixed;      /* >0: number of columns; 0: one column per STFT frame       */
   int64_t mouth_off;     /* offset (pairs) into `anchors`                             */
+  int32_t mouth_method;  /* contour method of the mouth anchors                       */
+  int32_t reserved0;
   double formantDep, rolloffLip, mouthOpenThres, openMouthBoost,
          vocalTract /* NaN = NULL */, samplingRate, speedSound, smoothLinearFactor;
 } sgb_envelope;
@@ -115,6 +127,8 @@ typedef struct sgb_noise {
   int32_t anchor_n;
   int32_t env_id;        /* index into envelopes[], -1 = no filterNoise               */
   int64_t strength_pre_off; /* >= 0: pre-evaluated dB contour (len doubles) in `pre`  */
+  int32_t anchor_method; /* contour method of the noise anchors                       */
+  int32_t reserved0;
   double rolloffNoise, attackLen, samplingRate, overlap;
 } sgb_noise;
 
@@ -130,6 +144,8 @@ typedef struct sgb_bout {
   int32_t aglobal_n;                /* amplAnchorsGlobal anchors (values already
                                        2^(dB/10), soundgen.R:724), 0 = NA             */
   int64_t aglobal_off;
+  int32_t aglobal_method;           /* contour method of amplAnchorsGlobal            */
+  int32_t reserved0;
   double overlap, amDep, amFreq, amShape, samplingRate, throwaway;
 } sgb_bout;
 
@@ -218,6 +234,106 @@ int sgb_batch_checksums(sgb_batch *b, uint64_t *out, int32_t cap);
 /* Diagnostic for a stuck run, callable from another thread: out[0] = the wait the handle's host thread is
  * in, out[1..11] = completion of the stage events of the current run (see engine.cu). */
 int sgb_batch_debug_state(sgb_batch *b, int32_t *out, int32_t cap);
+
+/* Two-phase run: sgb_batch_run == sgb_batch_run_begin + sgb_batch_run_finish.  Between the two the
+ * lengths that only the device can know (syllables after their zero-crossing joins, hence STFT
+ * frames per bout) are available, which is what the host needs to draw the stochastic formant
+ * tracks of a moving main filter in R's order (getRandomWalk(len = nc), sourceSpectrum.R:346-415). */
+int sgb_batch_run_begin(sgb_batch *b);
+int sgb_batch_run_finish(sgb_batch *b, sgb_run_info *info);
+/* After run_begin: geometry of one bout (STFT frames, envelope columns, clamped window, length(sound)). */
+int sgb_batch_bout_geometry(sgb_batch *b, int32_t bout, int32_t *nc, int32_t *nint, int32_t *wl, int32_t *sound_len);
+/* Between begin and finish: replaces envelope `env` by host-drawn tracks (tracks_given = 1):
+ * rows = n_formants blocks of nc rows (time, freq, amp, width). */
+int sgb_batch_set_tracks(sgb_batch *b, int32_t env, const double *rows, int32_t n_formants, int32_t nc);
+/* Normal draws each voiced syllable consumed (valid after run_begin); n_syllables values. */
+int sgb_batch_z_used(sgb_batch *b, int32_t *out);
+/* sizeof() of the ABI structs, for bindings to verify their mirrors:
+ * syllable, envelope, noise, bout, call, formant_ref, batch_desc, run_info, soundgen_args. */
+int sgb_abi_sizes(int32_t *out, int32_t cap);
+
+/* ------------------------------------------------------------------------- */
+/* Host front-end: the host stage of soundgen() (R/soundgen.R:279-733)         */
+/* ------------------------------------------------------------------------- */
+/* Argument validation against permittedValues, hyper-parameters, syllable segmentation and -- with
+ * temperature > 0 -- every draw the reference makes from R's RNG stream, in the reference's order
+ * ("RNG ledger"): rbinom (fractional nSyl / repeatBout), rnorm_bounded, divideIntoSyllables,
+ * wiggleAnchors, the normals generateHarmonics consumes, stochastic formants, runif for the noise.
+ * The stream is R's: Mersenne-Twister seeded like set.seed(seed) (or continued from a caller-supplied
+ * .Random.seed), inversion normals, R < 3.6 sample().  The result is an sgb_batch_desc for
+ * sgb_batch_upload; nothing here computes samples. */
+
+typedef struct sgb_anchor_arg {      /* a data.frame(time, value); n = 0: NA                    */
+  const double *time;                /* NULL: plain numeric vector (soundgen.R:305-315)         */
+  const double *value;
+  int32_t n, reserved;
+} sgb_anchor_arg;
+
+typedef struct sgb_formant_arg {     /* one formant: list(time, freq, amp, width), each recycled */
+  const double *time, *freq, *amp, *width;
+  int32_t n_time, n_freq, n_amp, n_width;
+} sgb_formant_arg;
+
+typedef struct sgb_soundgen_args {   /* arguments of soundgen(), R/soundgen.R:208-277 */
+  double repeatBout, nSyl, sylLen, pauseLen, temperature, maleFemale, creakyBreathy, nonlinBalance,
+         nonlinDep, jitterLen, jitterDep, vibratoFreq, vibratoDep, shimmerDep, attackLen, rolloff,
+         rolloffOct, rolloffKHz, rolloffParab, rolloffParabHarm, rolloffLip, formantDep,
+         formantDepStoch, vocalTract, subFreq, subDep, shortestEpoch, amDep, amFreq, amShape,
+         rolloffNoise, samplingRate, windowLength, overlap, addSilence /* NaN = NULL */, pitchFloor,
+         pitchCeiling, pitchSamplingRate, throwaway;
+  /* tempEffects: sylLenDep, formDrift, formDisp, pitchDriftDep, pitchDriftFreq, pitchAnchorsDep,
+   * noiseAnchorsDep, amplAnchorsDep (NaN = missing; all but sylLenDep then get their defaults) */
+  double tempEffects[8];
+  sgb_anchor_arg pitchAnchors, pitchAnchorsGlobal, noiseAnchors, mouthAnchors, amplAnchors, amplAnchorsGlobal;
+  const sgb_formant_arg *formants;      int32_t n_formants;       /* 0 = NA */
+  int32_t reserved0;
+  const sgb_formant_arg *formantsNoise; int32_t n_formantsNoise;  /* 0 = NA */
+  int32_t invalidArgAction;             /* 0 adjust, 1 abort, 2 ignore (soundgen.R:285-300)     */
+  int32_t contour_method;               /* SGB_CONTOUR_LOESS (reference) / SGB_CONTOUR_SPLINE   */
+  int32_t rng_mode;                     /* 0: R stream from `seed`; 1: continue `rng_state`;
+                                           2: caller buffers z / u (temperature must be 0)       */
+  uint32_t seed;
+  int32_t sample_rejection;             /* 1: R >= 3.6 sample() ("Rejection")                   */
+  const int32_t *rng_state;             /* rng_mode 1: .Random.seed[2:626]                      */
+  /* rng_mode 2: one normal buffer per voiced syllable / one uniform buffer per noise segment    */
+  const double *z; const int64_t *z_len; int32_t n_z; int32_t device_pitch;
+  const void *u;   const int64_t *u_len; int32_t n_u; int32_t reserved1;
+} sgb_soundgen_args;
+
+typedef struct sgb_frontend sgb_frontend;   /* opaque */
+int  sgb_frontend_create(sgb_frontend **out, int32_t u_is_float);
+void sgb_frontend_destroy(sgb_frontend *fe);
+/* Registers one soundgen() call (copies its arguments); returns the call index or an error.
+ * The host stage up to the bout loop (validation, hyper-parameters, rbinom draws) runs here. */
+int  sgb_frontend_add(sgb_frontend *fe, const sgb_soundgen_args *args);
+/* Builds the description of the next round.  One round covers every call that still has bouts
+ * to generate, up to and including the first bout whose main filter has to be drawn after the
+ * device has run (stochastic moving formants): most batches need exactly one round.
+ * *n_subcalls = 0 when every call is complete. */
+int  sgb_frontend_round_begin(sgb_frontend *fe, sgb_batch_desc *desc, int32_t *n_subcalls);
+/* Call between sgb_batch_run_begin and sgb_batch_run_finish: draws the deferred formant tracks. */
+int  sgb_frontend_resolve(sgb_frontend *fe, sgb_batch *b);
+/* After sgb_batch_run_finish: records statuses / lengths, checks the draw counts against the device. */
+int  sgb_frontend_round_end(sgb_frontend *fe, sgb_batch *b);
+/* Which original call each sub-call of the current round belongs to (n_subcalls values). */
+int  sgb_frontend_round_calls(sgb_frontend *fe, int32_t *out);
+/* Status of every registered call so far (SGB_OK or the first error), warnings text of a call. */
+int  sgb_frontend_status(sgb_frontend *fe, int32_t *out);
+const char *sgb_frontend_warnings(sgb_frontend *fe, int32_t call);
+/* rng_mode 0/1: the call's stream state after everything drawn so far (.Random.seed[2:626]). */
+int  sgb_frontend_rng_state(sgb_frontend *fe, int32_t call, int32_t *out625);
+/* Bytes the current round's description uploads. */
+int64_t sgb_frontend_h2d_bytes(sgb_frontend *fe);
+
+/* R's stream by itself (set.seed(seed); runif / rnorm / rexp / rgamma / rbinom / sample): used by the
+ * bindings and by the tests that pin the stream to published R answers.
+ * kind: 0 runif, 1 rnorm, 2 rexp, 3 rgamma(shape = p1, rate = p2), 4 rbinom(size = p1, prob = p2),
+ *       5 sample.int(p1, 1). */
+int sgb_rng_draw(uint32_t seed, int32_t kind, double p1, double p2, int32_t skip_uniforms, double *out, int32_t n);
+/* getSmoothContour on the host (same scalar code the kernels run): out[len]. */
+int sgb_smooth_contour(const double *time, const double *value, int32_t n, int32_t len, double samplingRate,
+                       int32_t has_floor, double valueFloor, int32_t has_ceiling, double valueCeiling,
+                       int32_t thisIsPitch, int32_t method, double *out);
 
 /* ------------------------------------------------------------------------- */
 /* Single-call interfaces                                                     */

@@ -2,10 +2,11 @@
 
 TEST INFRASTRUCTURE ONLY -- PARITY UNPINNED (see oracle/__init__.py).
 
-Covers the deterministic control flow (temperature = 0 at the `soundgen` level:
-no rnorm_bounded / wiggleAnchors / stochastic-formant draws; SURVEY.md 8d uses
-temperature = 0 for every batch config).  Jitter / shimmer normals and noise
-uniforms come from an `RStream` in R's consumption order.
+`rng` is either an `RStream` (pre-drawn normals / uniforms for the draws generateHarmonics and
+generateNoise make; temperature must then be 0) or an `oracle.rrng.RRng` -- R's own stream after
+`set.seed()`, from which every draw of the call is taken in the reference's order: rbinom
+(:394-400), rnorm_bounded (:485-506, :549-562), divideIntoSyllables, wiggleAnchors (:563-590),
+the draws inside generateHarmonics, stochastic formants (sourceSpectrum.R:346-415), runif.
 """
 from __future__ import annotations
 
@@ -28,6 +29,80 @@ def _df(anchors, t_hi=1.0):
         return (np.asarray(anchors[0], dtype=np.float64), np.asarray(anchors[1], dtype=np.float64))
     v = np.atleast_1d(np.asarray(anchors, dtype=np.float64))
     return (r_seq_len_out(0, t_hi, v.size), v)
+
+
+def rnorm_bounded(rng, n=1, mean=0.0, sd=1.0, low=None, high=None, roundToInteger=False):
+    """R/utilities_math.R:187-231 (scalar `roundToInteger`: out[TRUE] is every element)."""
+    mean = np.atleast_1d(np.asarray(mean, dtype=np.float64)).copy()
+    sd = np.atleast_1d(np.asarray(sd, dtype=np.float64)).copy()
+    if low is not None and high is not None:
+        mean = np.minimum(np.maximum(mean, low), high)
+    if mean.size < n:
+        mean = np.repeat(mean[0], n)
+    if sd.size < n:
+        sd = np.repeat(sd[0], n)
+    if np.sum(sd != 0) == 0:
+        out = mean.copy()
+        return r_round(out) if roundToInteger else out
+    out = rng.rnorm(n, mean, sd)
+    if roundToInteger:
+        out = r_round(out)
+    if low is None and high is None:
+        return out
+    lo = np.full(n, -np.inf if low is None else low)
+    hi = np.full(n, np.inf if high is None else high)
+    for i in range(n):
+        while out[i] < lo[i] or out[i] > hi[i]:
+            out[i] = rng.rnorm(1, mean[i], sd[i])[0]
+            if roundToInteger:
+                out = r_round(out)
+    return out
+
+
+def wiggleAnchors(rng, df, temperature, temp_coef, low, high, wiggleAllRows=False):
+    """R/utilities_soundgen.R:634-735; df = (time[], value[])."""
+    if df is None:
+        return None
+    t, v = np.array(df[0], dtype=np.float64), np.array(df[1], dtype=np.float64)
+    if np.any(np.isnan(t)) or np.any(np.isnan(v)):
+        return None
+    action = ['nothing', 'remove', 'add'][rng.sample_prob1([1 - temperature, temperature / 2,
+                                                           temperature / 2]) - 1]
+    if action == 'add':
+        if t.size == 1:
+            new = rnorm_bounded(rng, 1, mean=v[0], sd=v[0] * temperature * temp_coef, low=low[1],
+                                high=high[1])
+            t = np.array([0.0, 1.0])
+            v = np.array([v[0], new[0]])
+        else:
+            a1 = rng.sample_int1(t.size)
+            direction = (-1, 1)[rng.sample_int1(2) - 1]
+            a2 = a1 - direction if (a1 + direction < 1 or a1 + direction > t.size) else a1 + direction
+            i1, i2 = min(a1, a2), max(a1, a2)
+            nt, nv = np.mean(t[i1 - 1:i2]), np.mean(v[i1 - 1:i2])
+            t = np.concatenate((t[:i1], [nt], t[i2 - 1:]))
+            v = np.concatenate((v[:i1], [nv], v[i2 - 1:]))
+    elif action == 'remove':
+        if wiggleAllRows:
+            idx = rng.sample_int1(t.size)
+            t, v = np.delete(t, idx - 1), np.delete(v, idx - 1)
+        elif t.size > 2:
+            idx = np.arange(2, t.size)[rng.sample_int1(t.size - 2) - 1]   # sampleModif(2:(n - 1))
+            t, v = np.delete(t, idx - 1), np.delete(v, idx - 1)
+    orig = None if wiggleAllRows else (t[0], t[-1])
+    cols = [t, v]
+    if t.size == 1:
+        ranges = [t[0], v[0]]
+    else:
+        ranges = [abs(np.max(c) - np.min(c)) for c in cols]
+        ranges = [abs(c[0]) if r == 0 else r for r, c in zip(ranges, cols)]
+    for i in range(2):
+        cols[i] = rnorm_bounded(rng, cols[i].size, mean=cols[i], sd=ranges[i] * temperature * temp_coef,
+                                low=low[i], high=high[i])
+    t, v = cols
+    if orig is not None:
+        t[0], t[-1] = orig
+    return (t, v)
 
 
 def soundgen(repeatBout=1, nSyl=1, sylLen=300, pauseLen=200,
@@ -66,9 +141,9 @@ def soundgen(repeatBout=1, nSyl=1, sylLen=300, pauseLen=200,
      rolloffOct, rolloffParab, rolloffParabHarm, rolloffKHz, rolloffLip, formantDep,
      formantDepStoch, vocalTract, subFreq, subDep, shortestEpoch, amDep, amFreq, amShape,
      samplingRate, windowLength, rolloffNoise) = [loc[p] for p in so.CHECKED_PARS]
-    if temperature > 0:
-        raise NotImplementedError('oracle soundgen(): host-side stochastic stage (temperature > 0) '
-                                  'needs R\'s RNG; use temperature = 0')
+    r_stream = hasattr(rng, 'rbinom1')     # R's own stream: every draw of the call comes from it
+    if temperature > 0 and not r_stream:
+        raise ValueError('temperature > 0 draws from R\'s stream: pass rng = oracle.rrng.RRng(seed)')
 
     pitchAnchors = _df(pitchAnchors)
     pitchAnchorsGlobal = _df(pitchAnchorsGlobal)
@@ -109,8 +184,12 @@ def soundgen(repeatBout=1, nSyl=1, sylLen=300, pauseLen=200,
                 f[:, 1] = f[:, 1] * 1.25 ** maleFemale
         vocalTract = vocalTract * (1 - .25 * maleFemale)
 
-    nSyl = int(math.floor(nSyl))  # :394-400 (fraction 0: rbinom(1,1,0) draws nothing)
-    repeatBout = int(math.floor(repeatBout))
+    if r_stream:  # :394-400
+        nSyl = int(math.floor(nSyl) + rng.rbinom1(1, nSyl - math.floor(nSyl)))
+        repeatBout = int(math.floor(repeatBout) + rng.rbinom1(1, repeatBout - math.floor(repeatBout)))
+    else:  # fraction 0: rbinom(1, 1, 0) draws nothing
+        nSyl = int(math.floor(nSyl))
+        repeatBout = int(math.floor(repeatBout))
 
     pars = dict(attackLen=attackLen, jitterDep=jitterDep, jitterLen=jitterLen,
                 vibratoFreq=vibratoFreq, vibratoDep=vibratoDep, shimmerDep=shimmerDep,
@@ -140,21 +219,42 @@ def soundgen(repeatBout=1, nSyl=1, sylLen=300, pauseLen=200,
         pitchAnchors = (t, pitchAnchors[1])
 
     has_noise = noiseAnchors is not None and np.sum(noiseAnchors[1] > throwaway) > 0
+    wiggleNoise = temperature > 0 and has_noise
+    wiggleAmpl_per_syl = temperature > 0 and amplAnchors is not None and np.sum(amplAnchors[1] < -throwaway) > 0
+    P = so.PERMITTED
+    pars_to_vary = ['nonlinDep', 'attackLen', 'jitterDep', 'shimmerDep', 'rolloff', 'rolloffOct',
+                    'shortestEpoch', 'subFreq', 'subDep']
+    pars_to_round = ['attackLen', 'subFreq', 'subDep']
     arts = []
     bout = None
     for b in range(repeatBout):  # :482
-        sylDur_s = sylLen  # rnorm_bounded with sd = 0 returns the mean
-        pauseDur_s = pauseLen
+        if temperature > 0:  # :484-506 (sd = 0 returns the mean without drawing)
+            sylDur_s = sylLen
+            if P['sylLen'][1] <= sylLen <= P['sylLen'][2]:
+                sylDur_s = rnorm_bounded(rng, 1, sylLen, (P['sylLen'][2] - P['sylLen'][1]) * temperature *
+                                         tempEffects['sylLenDep'], P['sylLen'][1], P['sylLen'][2])[0]
+            pauseDur_s = rnorm_bounded(rng, 1, pauseLen, (P['pauseLen'][2] - P['pauseLen'][1]) * temperature *
+                                       tempEffects['sylLenDep'], P['pauseLen'][1], P['pauseLen'][2])[0]
+        else:
+            sylDur_s = sylLen
+            pauseDur_s = min(max(pauseLen, P['pauseLen'][1]), P['pauseLen'][2])
         if nSyl == 1:  # divideIntoSyllables, utilities_soundgen.R:515-551
             syllables = np.array([[0., sylDur_s]])
         else:
             rows = []
             c = 0.
+            Td = temperature * tempEffects['sylLenDep']
             while len(rows) < nSyl:
+                if Td > 0:
+                    dur = rnorm_bounded(rng, 1, sylDur_s, sylDur_s * Td, P['sylLen'][1], P['sylLen'][2])[0]
+                    pau = rnorm_bounded(rng, 1, pauseDur_s, pauseDur_s * Td, P['pauseLen'][1], P['pauseLen'][2])[0]
+                else:
+                    dur = min(max(sylDur_s, P['sylLen'][1]), P['sylLen'][2])
+                    pau = min(max(pauseDur_s, P['pauseLen'][1]), P['pauseLen'][2])
                 start = 1 + c
-                end = start + sylDur_s
+                end = start + dur
                 rows.append([start, end])
-                c = end + pauseDur_s
+                c = end + pau
             syllables = np.array(rows)
         syllableStartIdx = r_round(syllables[:, 0] * samplingRate / 1000)  # :517-532
         syllableStartIdx[0] = 1
@@ -168,22 +268,39 @@ def soundgen(repeatBout=1, nSyl=1, sylLen=300, pauseLen=200,
         voiced = np.zeros(0)
         unvoiced = []
         for s in range(syllables.shape[0]):  # :540
+            pars_syl = dict(pars)
+            pitchAnchors_syl, amplAnchors_syl = pitchAnchors, amplAnchors
+            if temperature > 0:  # :546-591
+                for p in pars_to_vary:
+                    lo_, hi_ = P[p][1], P[p][2]
+                    pars_syl[p] = float(rnorm_bounded(rng, 1, pars[p], (hi_ - lo_) * temperature / 10, lo_, hi_,
+                                                      roundToInteger=(p in pars_to_round))[0])
+                if pitchAnchors_syl is not None:
+                    pitchAnchors_syl = wiggleAnchors(rng, pitchAnchors_syl, temperature,
+                                                     tempEffects['pitchAnchorsDep'], (0, P['pitch'][1]),
+                                                     (1, P['pitch'][2]))
+                if wiggleNoise:  # the result is overwritten at :646; only its draws matter
+                    wiggleAnchors(rng, noiseAnchors, temperature, tempEffects['noiseAnchorsDep'],
+                                  (-np.inf, P['noiseAmpl'][1]), (np.inf, P['noiseAmpl'][2]), wiggleAllRows=True)
+                if wiggleAmpl_per_syl:
+                    amplAnchors_syl = wiggleAnchors(rng, amplAnchors_syl, temperature,
+                                                    tempEffects['amplAnchorsDep'], (0, 0), (1, -throwaway))
             dur_syl = float(syllables[s, 1] - syllables[s, 0])
             pitchContour_syl = None
-            if pitchAnchors is not None:
+            if pitchAnchors_syl is not None:
                 pitchContour_syl = so.getSmoothContour(
-                    pitchAnchors, length=r_round(dur_syl * pitchSamplingRate / 1000),
+                    pitchAnchors_syl, length=r_round(dur_syl * pitchSamplingRate / 1000),
                     samplingRate=pitchSamplingRate, valueFloor=pitchFloor,
                     valueCeiling=pitchCeiling, thisIsPitch=True,
                     method=contour_method) * pitchDeltas[s]
             if (dur_syl < so.PERMITTED['sylLen'][1]
                     or (noiseAnchors is not None and np.min(noiseAnchors[1]) >= 40)
-                    or pitchAnchors is None):
+                    or pitchAnchors_syl is None):
                 syllable = np.zeros(int(r_round(dur_syl * samplingRate / 1000)))
             else:
                 syllable, art = so.generateHarmonics(
-                    pitchContour_syl, amplAnchors=amplAnchors, rng=rng,
-                    contour_method=contour_method, want_artefacts=True, **pars)
+                    pitchContour_syl, amplAnchors=amplAnchors_syl, rng=rng,
+                    contour_method=contour_method, want_artefacts=True, **pars_syl)
                 arts.append(art)
             if s < syllables.shape[0] - 1:
                 pause = np.zeros(int(math.floor((syllables[s + 1, 0] - syllables[s, 1]) *
@@ -210,7 +327,9 @@ def soundgen(repeatBout=1, nSyl=1, sylLen=300, pauseLen=200,
                         nr=windowLength_points / 2, nc=nInt, formants=formantsNoise,
                         formantDep=formantDep, rolloffLip=rolloffLip, mouthAnchors=mouthAnchors,
                         temperature=temperature, samplingRate=samplingRate,
-                        vocalTract=vocalTract, contour_method=contour_method)
+                        vocalTract=vocalTract, contour_method=contour_method,
+                        formDrift=tempEffects['formDrift'], formDisp=tempEffects['formDisp'],
+                        formantDepStoch=formantDepStoch, rng=rng)
                 unvoiced.append(so.generateNoise(
                     length=unvoicedDur_syl, noiseAnchors=na_syl, rolloffNoise=rolloffNoise,
                     attackLen=attackLen, samplingRate=samplingRate,
@@ -249,7 +368,8 @@ def soundgen(repeatBout=1, nSyl=1, sylLen=300, pauseLen=200,
             spectralEnvelope = so.getSpectralEnvelope(
                 nr=nr, nc=nInt, formants=formants, formantDep=formantDep, rolloffLip=rolloffLip,
                 mouthAnchors=mouthAnchors, temperature=temperature, samplingRate=samplingRate,
-                vocalTract=vocalTract, contour_method=contour_method)
+                vocalTract=vocalTract, contour_method=contour_method, formDrift=tempEffects['formDrift'],
+                formDisp=tempEffects['formDisp'], formantDepStoch=formantDepStoch, rng=rng)
             soundFiltered = so.filter_sound(sound, spectralEnvelope, windowLength_points, overlap)
 
         if len(unvoiced) > 0 and formantsNoise is not None:  # :813-818

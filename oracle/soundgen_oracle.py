@@ -184,10 +184,13 @@ def clumper(s, minLength):
 
 def getRandomWalk(length, rng, rw_range=1.0, rw_smoothing=.2, method='spline',
                   trend=0.0):
-    """utilities_math.R:289-326 (len >= 2 branch; len < 2 draws rgamma on the host)."""
+    """utilities_math.R:289-326.  `trend` may be a callable: R passes `trend = rnorm(1)` as a
+    promise, which is only forced (drawn) once `length(trend)` is looked at, i.e. when len >= 2."""
     length = int(length)
     if length < 2:
-        raise NotImplementedError('len < 2 draws rgamma(1): host side')
+        return np.array([rng.rgamma(1, 1 / rw_range ** 2, 1 / rw_range ** 2)[0]])
+    if callable(trend):
+        trend = trend()
     with np.errstate(over='ignore', divide='ignore'):
         p = 2.0 ** (1.0 / rw_smoothing) if rw_smoothing != 0 else np.inf
     n = math.floor(max(2.0, p)) if np.isfinite(p) else np.inf
@@ -675,7 +678,7 @@ def generateHarmonics(pitch, attackLen=50, nonlinBalance=0, nonlinDep=0, jitterD
     if temperature > 0:  # :459-467
         drift_upsampled = r_approx(drift, waveform.size, x=gc_upsampled[:-1].astype(np.float64))
         waveform = waveform * drift_upsampled
-    art.z_used = rng.zi
+    art.z_used = getattr(rng, "zi", None)
     return (waveform, art) if want_artefacts else waveform
 
 
@@ -704,7 +707,8 @@ def upsample_formants(formants, nc, smoothLinearFactor=1):
 def getSpectralEnvelope(nr, nc, formants=None, formantDep=1, rolloffLip=6, mouthAnchors=None,
                         mouthOpenThres=0, openMouthBoost=0, vocalTract=None, temperature=0,
                         smoothLinearFactor=1, samplingRate=16000, speedSound=35400,
-                        formants_upsampled=None, contour_method='loess'):
+                        formants_upsampled=None, contour_method='loess', formDrift=.3, formDisp=.2,
+                        formantDepStoch=30, rng=None):
     """sourceSpectrum.R:261-566 with temperature == 0 (the stochastic block
     :346-415 draws rgamma/rnorm on the host; pass its result via
     `formants_upsampled`).  `formants`: list of (k,4) arrays or None."""
@@ -723,9 +727,41 @@ def getSpectralEnvelope(nr, nc, formants=None, formantDep=1, rolloffLip=6, mouth
     if formants is not None:
         fu = formants_upsampled if formants_upsampled is not None else \
             upsample_formants(formants, nc, smoothLinearFactor)
-        if temperature > 0 and formants_upsampled is None:
-            raise NotImplementedError('stochastic formants are drawn on the host')
         fu = [np.array(f, dtype=np.float64) for f in fu]
+        if temperature > 0 and formants_upsampled is None:  # :346-415
+            if rng is None:
+                raise ValueError('temperature > 0 needs an R random stream')
+            if vocalTract is None and len(formants) > 1:
+                ff = np.array([np.asarray(f)[0, 1] for f in formants])
+                formantDispersion = float(np.mean(np.concatenate(([ff[0]], np.diff(ff)))))
+            elif vocalTract is not None:
+                formantDispersion = 2 * speedSound / (4 * vocalTract)
+            else:
+                formantDispersion = float('nan')
+            sdG = formantDispersion * temperature * formDisp
+            freq_max = np.max(fu[-1][:, 1])
+            if not np.isnan(sdG) and formantDepStoch > 0:
+                while freq_max < (samplingRate / 2 - 1000):
+                    rw = getRandomWalk(nc, rng, rw_range=temperature * formDrift, rw_smoothing=0, trend=0)
+                    if rw.size > 1:
+                        rw = rw - r_mean(rw) + 1
+                    new = np.zeros((nc, 4))
+                    new[:, 0] = fu[0][:, 0]
+                    new[:, 1] = fu[-1][:, 1] + r_round(
+                        rng.rgamma(1, formantDispersion ** 2 / sdG ** 2, formantDispersion / sdG ** 2)[0] * rw)
+                    new[:, 2] = r_round(rng.rgamma(
+                        1, (formantDep / temperature) ** 2,
+                        formantDepStoch * formantDep / (formantDepStoch * temperature) ** 2)[0] * rw)
+                    new[:, 3] = 50 + (np.log2(new[:, 1]) - 5) * 20
+                    fu.append(new)
+                    freq_max = np.max(new[:, 1])
+            for f in fu:
+                for c in (1, 2, 3):
+                    rw = getRandomWalk(nc, rng, rw_range=temperature * formDrift, rw_smoothing=0.3,
+                                       trend=lambda: rng.rnorm(1)[0])
+                    if rw.size > 1:
+                        rw = rw - r_mean(rw) + 1
+                    f[:, c] = f[:, c] * rw
         bin_width = samplingRate / 2 / nr  # :419
         for f in fu:
             f[:, 1] = (f[:, 1] - bin_width / 2) / bin_width + 1

@@ -9,6 +9,7 @@ i32, i64, f64, f32 = C.c_int32, C.c_int64, C.c_double, C.c_float
 SGB_OK = 0
 SGB_ERR_INVALID, SGB_ERR_CUDA, SGB_ERR_UNSUPPORTED = -1, -2, -3
 SGB_ERR_SYNTH, SGB_ERR_STREAM, SGB_ERR_STATE = -4, -5, -6
+SGB_CONTOUR_LOESS, SGB_CONTOUR_SPLINE = 0, 1
 
 SYL_DOUBLES = ['attackLen', 'nonlinBalance', 'jitterDep', 'jitterLen', 'vibratoFreq',
                'vibratoDep', 'shimmerDep', 'rolloff', 'rolloffOct', 'rolloffKHz', 'rolloffParab',
@@ -20,13 +21,15 @@ SYL_DOUBLES = ['attackLen', 'nonlinBalance', 'jitterDep', 'jitterLen', 'vibratoF
 class Syllable(C.Structure):
     _fields_ = [('kind', i32), ('silent_len', i32), ('pitch_off', i64), ('pitch_len', i32),
                 ('pause_after', i32), ('z_off', i64), ('z_cap', i32), ('ampl_n', i32),
-                ('ampl_off', i64)] + [(n, f64) for n in SYL_DOUBLES]
+                ('ampl_off', i64), ('ampl_method', i32), ('pitch_anchor_n', i32),
+                ('pitch_anchor_off', i64), ('pitch_method', i32), ('reserved0', i32),
+                ('pitch_scale', f64)] + [(n, f64) for n in SYL_DOUBLES]
 
 
 class Envelope(C.Structure):
     _fields_ = [('n_formants', i32), ('tracks_given', i32), ('formant_off', i64),
                 ('mouth_n', i32), ('nc_fixed', i32), ('mouth_off', i64),
-                ('formantDep', f64), ('rolloffLip', f64), ('mouthOpenThres', f64),
+                ('mouth_method', i32), ('reserved0', i32), ('formantDep', f64), ('rolloffLip', f64), ('mouthOpenThres', f64),
                 ('openMouthBoost', f64), ('vocalTract', f64), ('samplingRate', f64),
                 ('speedSound', f64), ('smoothLinearFactor', f64)]
 
@@ -34,7 +37,8 @@ class Envelope(C.Structure):
 class Noise(C.Structure):
     _fields_ = [('len', i32), ('insertion', i32), ('mix', i32), ('wl', i32), ('u_off', i64),
                 ('anchor_off', i64), ('anchor_n', i32), ('env_id', i32),
-                ('strength_pre_off', i64), ('rolloffNoise', f64), ('attackLen', f64),
+                ('strength_pre_off', i64), ('anchor_method', i32), ('reserved0', i32),
+                ('rolloffNoise', f64), ('attackLen', f64),
                 ('samplingRate', f64), ('overlap', f64)]
 
 
@@ -42,7 +46,7 @@ class Bout(C.Structure):
     _fields_ = [('syl_begin', i32), ('syl_end', i32), ('noise_begin', i32), ('noise_end', i32),
                 ('env_id', i32), ('moving', i32), ('wl', i32), ('lead_silence', i32),
                 ('tail_silence', i32), ('aglobal_n', i32), ('aglobal_off', i64),
-                ('overlap', f64), ('amDep', f64), ('amFreq', f64), ('amShape', f64),
+                ('aglobal_method', i32), ('reserved0', i32), ('overlap', f64), ('amDep', f64), ('amFreq', f64), ('amShape', f64),
                 ('samplingRate', f64), ('throwaway', f64)]
 
 
@@ -68,6 +72,38 @@ class BatchDesc(C.Structure):
                 ('pre', C.c_void_p), ('n_pre', i64)]
 
 
+class AnchorArg(C.Structure):
+    _fields_ = [('time', C.c_void_p), ('value', C.c_void_p), ('n', i32), ('reserved', i32)]
+
+
+class FormantArg(C.Structure):
+    _fields_ = [('time', C.c_void_p), ('freq', C.c_void_p), ('amp', C.c_void_p), ('width', C.c_void_p),
+                ('n_time', i32), ('n_freq', i32), ('n_amp', i32), ('n_width', i32)]
+
+
+SG_DOUBLES = ['repeatBout', 'nSyl', 'sylLen', 'pauseLen', 'temperature', 'maleFemale', 'creakyBreathy',
+              'nonlinBalance', 'nonlinDep', 'jitterLen', 'jitterDep', 'vibratoFreq', 'vibratoDep', 'shimmerDep',
+              'attackLen', 'rolloff', 'rolloffOct', 'rolloffKHz', 'rolloffParab', 'rolloffParabHarm', 'rolloffLip',
+              'formantDep', 'formantDepStoch', 'vocalTract', 'subFreq', 'subDep', 'shortestEpoch', 'amDep',
+              'amFreq', 'amShape', 'rolloffNoise', 'samplingRate', 'windowLength', 'overlap', 'addSilence',
+              'pitchFloor', 'pitchCeiling', 'pitchSamplingRate', 'throwaway']
+SG_ANCHORS = ['pitchAnchors', 'pitchAnchorsGlobal', 'noiseAnchors', 'mouthAnchors', 'amplAnchors',
+              'amplAnchorsGlobal']
+TEMP_EFFECTS = ['sylLenDep', 'formDrift', 'formDisp', 'pitchDriftDep', 'pitchDriftFreq', 'pitchAnchorsDep',
+                'noiseAnchorsDep', 'amplAnchorsDep']
+
+
+class SoundgenArgs(C.Structure):
+    _fields_ = [(n, f64) for n in SG_DOUBLES] + [('tempEffects', f64 * 8)] + \
+               [(n, AnchorArg) for n in SG_ANCHORS] + \
+               [('formants', C.c_void_p), ('n_formants', i32), ('reserved0', i32),
+                ('formantsNoise', C.c_void_p), ('n_formantsNoise', i32), ('invalidArgAction', i32),
+                ('contour_method', i32), ('rng_mode', i32), ('seed', C.c_uint32), ('sample_rejection', i32),
+                ('rng_state', C.c_void_p),
+                ('z', C.c_void_p), ('z_len', C.c_void_p), ('n_z', i32), ('device_pitch', i32),
+                ('u', C.c_void_p), ('u_len', C.c_void_p), ('n_u', i32), ('reserved1', i32)]
+
+
 T_NAMES = ['h2d', 'control', 'ampl', 'synth', 'compose', 'noise', 'assemble', 'envelope',
            'filter', 'finalize', 'd2h', 'total']
 
@@ -90,7 +126,12 @@ EXPORTS = ['sgb_version', 'sgb_last_error', 'sgb_device_count', 'sgb_set_device'
            'sgb_batch_lengths', 'sgb_batch_fetch_f32', 'sgb_batch_fetch_f64', 'sgb_batch_fetch_pcm16', 'sgb_batch_status',
            'sgb_batch_syllable_len', 'sgb_batch_syllable_fetch', 'sgb_batch_noise_fetch',
            'sgb_batch_artefacts', 'sgb_batch_artefact_ints', 'sgb_batch_pitch_per_gc', 'sgb_batch_checksums', 'sgb_batch_debug_state',
-           'sgb_get_rolloff', 'sgb_get_spectral_envelope', 'sgb_filter_len', 'sgb_filter']
+           'sgb_get_rolloff', 'sgb_get_spectral_envelope', 'sgb_filter_len', 'sgb_filter',
+           'sgb_batch_run_begin', 'sgb_batch_run_finish', 'sgb_batch_bout_geometry', 'sgb_batch_set_tracks',
+           'sgb_batch_z_used', 'sgb_abi_sizes', 'sgb_frontend_create', 'sgb_frontend_destroy', 'sgb_frontend_add',
+           'sgb_frontend_round_begin', 'sgb_frontend_resolve', 'sgb_frontend_round_end', 'sgb_frontend_round_calls',
+           'sgb_frontend_status', 'sgb_frontend_warnings', 'sgb_frontend_rng_state', 'sgb_frontend_h2d_bytes',
+           'sgb_rng_draw', 'sgb_smooth_contour']
 
 
 def lib_path():
@@ -145,5 +186,32 @@ def load():
     L.sgb_filter_len.argtypes = [i64, i32, f64]
     L.sgb_filter_len.restype = i64
     L.sgb_filter.argtypes = [vp, i64, vp, i32, i32, f64, vp, i64]
+    L.sgb_batch_run_begin.argtypes = [vp]
+    L.sgb_batch_run_finish.argtypes = [vp, C.POINTER(RunInfo)]
+    L.sgb_batch_bout_geometry.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    L.sgb_batch_set_tracks.argtypes = [vp, i32, vp, i32, i32]
+    L.sgb_batch_z_used.argtypes = [vp, vp]
+    L.sgb_abi_sizes.argtypes = [vp, i32]
+    L.sgb_frontend_create.argtypes = [C.POINTER(vp), i32]
+    L.sgb_frontend_destroy.argtypes = [vp]
+    L.sgb_frontend_destroy.restype = None
+    L.sgb_frontend_add.argtypes = [vp, C.POINTER(SoundgenArgs)]
+    L.sgb_frontend_round_begin.argtypes = [vp, C.POINTER(BatchDesc), C.POINTER(i32)]
+    L.sgb_frontend_resolve.argtypes = [vp, vp]
+    L.sgb_frontend_round_end.argtypes = [vp, vp]
+    L.sgb_frontend_round_calls.argtypes = [vp, vp]
+    L.sgb_frontend_status.argtypes = [vp, vp]
+    L.sgb_frontend_warnings.argtypes = [vp, i32]
+    L.sgb_frontend_warnings.restype = C.c_char_p
+    L.sgb_frontend_rng_state.argtypes = [vp, i32, vp]
+    L.sgb_frontend_h2d_bytes.argtypes = [vp]
+    L.sgb_frontend_h2d_bytes.restype = i64
+    L.sgb_rng_draw.argtypes = [C.c_uint32, i32, f64, f64, i32, vp, i32]
+    L.sgb_smooth_contour.argtypes = [vp, vp, i32, i32, f64, i32, f64, i32, f64, i32, i32, vp]
+    sizes = (i32 * 9)()
+    L.sgb_abi_sizes(sizes, 9)
+    mine = [C.sizeof(t) for t in (Syllable, Envelope, Noise, Bout, Call, FormantRef, BatchDesc, RunInfo, SoundgenArgs)]
+    if list(sizes) != mine:
+        raise RuntimeError('ctypes mirror out of date: library struct sizes %s, mirror %s' % (list(sizes), mine))
     _lib = L
     return L

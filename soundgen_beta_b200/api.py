@@ -64,6 +64,227 @@ def _formant_list(formants):
     return [_formant_rows(f) for f in formants]
 
 
+def _anchor_arg(a, keep):
+    """None / numeric vector / (time, value) / dict -> sgb_anchor_arg"""
+    A = _abi.AnchorArg()
+    if a is None:
+        return A
+    if isinstance(a, dict):
+        t, v = a['time'], a['value']
+    elif isinstance(a, (tuple, list)) and len(a) == 2 and np.ndim(a[0]) == 1 and np.ndim(a[1]) == 1 \
+            and len(a[0]) == len(a[1]) and not np.isscalar(a[0]):
+        t, v = a
+    else:
+        t, v = None, a
+    v = np.ascontiguousarray(np.atleast_1d(v), dtype=np.float64)
+    if v.size == 0 or np.all(np.isnan(v)):
+        return A
+    keep.append(v)
+    A.value, A.n = v.ctypes.data, v.size
+    if t is not None:
+        t = np.ascontiguousarray(np.atleast_1d(t), dtype=np.float64)
+        keep.append(t)
+        A.time = t.ctypes.data
+    return A
+
+
+def _formant_args(fl, keep):
+    arr = (_abi.FormantArg * max(1, len(fl)))()
+    for i, f in enumerate(fl):
+        cols = np.ascontiguousarray(f.T, dtype=np.float64)     # 4 x k
+        keep.append(cols)
+        k = cols.shape[1]
+        for j, nm in enumerate(('time', 'freq', 'amp', 'width')):
+            setattr(arr[i], nm, cols[j].ctypes.data)
+            setattr(arr[i], 'n_' + nm, k)
+    keep.append(arr)
+    return arr
+
+
+SOUNDGEN_DEFAULTS = dict(
+    repeatBout=1, nSyl=1, sylLen=300, pauseLen=200, temperature=0.025, maleFemale=0, creakyBreathy=0,
+    nonlinBalance=0, nonlinDep=50, jitterLen=1, jitterDep=3, vibratoFreq=5, vibratoDep=0, shimmerDep=0,
+    attackLen=50, rolloff=-12, rolloffOct=-12, rolloffKHz=-6, rolloffParab=0, rolloffParabHarm=3, rolloffLip=6,
+    formantDep=1, formantDepStoch=30, vocalTract=15.5, subFreq=100, subDep=100, shortestEpoch=300, amDep=0,
+    amFreq=30, amShape=0, rolloffNoise=-14, samplingRate=16000, windowLength=50, overlap=75, addSilence=100,
+    pitchFloor=50, pitchCeiling=3500, pitchSamplingRate=3500, throwaway=-120)     # R/soundgen.R:208-277
+_ANCHOR_DEFAULTS = dict(pitchAnchors=((0, .1, .9, 1), (100, 150, 135, 100)), pitchAnchorsGlobal=None,
+                        noiseAnchors=((0, 300), (-120, -120)), mouthAnchors=((0, 1), (.5, .5)), amplAnchors=None,
+                        amplAnchorsGlobal=None)
+_ACTIONS = {'adjust': 0, 'abort': 1, 'ignore': 2}
+_METHODS = {'loess': _abi.SGB_CONTOUR_LOESS, 'spline': _abi.SGB_CONTOUR_SPLINE}
+
+
+class FrontEnd:
+    """Handle of the library's host front-end: soundgen() argument lists in, batch descriptions out."""
+
+    def __init__(self, u_dtype=np.float64):
+        self.L = _abi.load()
+        self.u_dtype = np.dtype(u_dtype)
+        self.h = C.c_void_p()
+        _check(self.L.sgb_frontend_create(C.byref(self.h), 1 if self.u_dtype == np.float32 else 0))
+        self.n_calls = 0
+        self.n_sub = 0
+
+    def close(self):
+        if self.h:
+            self.L.sgb_frontend_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def add(self, seed=None, z=None, u=None, contour_method='loess', warn=None, invalidArgAction='adjust',
+            formants='default', formantsNoise=None, tempEffects=None, device_pitch=True, rng_state=None,
+            sample_kind='Rounding', **kw):
+        keep = []
+        A = _abi.SoundgenArgs()
+        for k, d in SOUNDGEN_DEFAULTS.items():
+            v = kw.pop(k, d)
+            if v is None:
+                v = float('nan')
+            elif not isinstance(v, (int, float, np.integer, np.floating)):
+                raise TypeError('%s must be numeric' % k)
+            setattr(A, k, float(v))
+        for k, d in _ANCHOR_DEFAULTS.items():
+            setattr(A, k, _anchor_arg(kw.pop(k, d), keep))
+        if kw:
+            raise TypeError('soundgen() got unexpected arguments: %s' % ', '.join(sorted(kw)))
+        te = dict(sylLenDep=.02)
+        te.update(tempEffects or {})
+        for i, k in enumerate(_abi.TEMP_EFFECTS):
+            A.tempEffects[i] = float(te.get(k, float('nan')))
+        if isinstance(formants, str) and formants == 'default':
+            formants = DEFAULT_FORMANTS
+        elif isinstance(formants, str):
+            formants = host.convert_string_to_formants(formants)     # soundgen.R:384-386
+        fl = _formant_list(formants)
+        if fl:
+            A.formants = C.cast(_formant_args(fl, keep), C.c_void_p)
+            A.n_formants = len(fl)
+        fn = _formant_list(formantsNoise)
+        if fn:
+            A.formantsNoise = C.cast(_formant_args(fn, keep), C.c_void_p)
+            A.n_formantsNoise = len(fn)
+        A.invalidArgAction = _ACTIONS[invalidArgAction]
+        A.contour_method = _METHODS[contour_method]
+        A.device_pitch = 1 if device_pitch else 0
+        A.sample_rejection = 1 if sample_kind == 'Rejection' else 0
+        if rng_state is not None:
+            st = np.ascontiguousarray(rng_state, dtype=np.int32)
+            keep.append(st)
+            A.rng_mode, A.rng_state = 1, st.ctypes.data
+        elif seed is not None:
+            A.rng_mode, A.seed = 0, int(seed) & 0xFFFFFFFF
+        else:
+            A.rng_mode = 2
+            zl = [] if z is None else (list(z) if isinstance(z, (list, tuple)) else [z])
+            ul = [] if u is None else (list(u) if isinstance(u, (list, tuple)) else [u])
+            if zl:
+                zc = np.ascontiguousarray(np.concatenate([np.ravel(q) for q in zl]), dtype=np.float64)
+                zn = np.array([np.size(q) for q in zl], dtype=np.int64)
+                keep += [zc, zn]
+                A.z, A.z_len, A.n_z = zc.ctypes.data, zn.ctypes.data, len(zl)
+            if ul:
+                uc = np.ascontiguousarray(np.concatenate([np.ravel(q) for q in ul]), dtype=self.u_dtype)
+                un = np.array([np.size(q) for q in ul], dtype=np.int64)
+                keep += [uc, un]
+                A.u, A.u_len, A.n_u = uc.ctypes.data, un.ctypes.data, len(ul)
+        rc = self.L.sgb_frontend_add(self.h, C.byref(A))
+        if rc < 0:
+            msg = self.L.sgb_last_error().decode()
+            if rc == _abi.SGB_ERR_INVALID and 'must be between' in msg:
+                raise ValueError(msg)
+            if rc == _abi.SGB_ERR_UNSUPPORTED:
+                raise NotImplementedError(msg)
+            raise SoundgenError(rc, msg)
+        self.n_calls = rc + 1
+        if warn is not None:
+            w = self.L.sgb_frontend_warnings(self.h, rc).decode()
+            if w:
+                warn.extend(w.split('\n'))
+        return rc
+
+    def round_begin(self):
+        d = BatchDesc()
+        n = C.c_int32()
+        _check(self.L.sgb_frontend_round_begin(self.h, C.byref(d), C.byref(n)))
+        self.n_sub = n.value
+        esz = 4 if self.u_dtype == np.float32 else 8
+        d._keep = {'pitch': _Raw(d.pitch, 8 * d.n_pitch), 'anchors': _Raw(d.anchors, 16 * d.n_anchors),
+                   'formants': _Raw(d.formants, 32 * d.n_formants), 'z': _Raw(d.z, 8 * d.n_z),
+                   'u': _Raw(d.u, esz * d.n_u), 'pre': _Raw(d.pre, 8 * d.n_pre)}
+        d._fe = self
+        return d, n.value
+
+    def resolve(self, batch):
+        _check(self.L.sgb_frontend_resolve(self.h, batch.h))
+
+    def round_end(self, batch):
+        _check(self.L.sgb_frontend_round_end(self.h, batch.h))
+
+    def round_calls(self):
+        out = np.zeros(max(1, self.n_sub), dtype=np.int32)
+        _check(self.L.sgb_frontend_round_calls(self.h, _ptr(out)))
+        return out[:self.n_sub]
+
+    def status(self):
+        out = np.zeros(max(1, self.n_calls), dtype=np.int32)
+        _check(self.L.sgb_frontend_status(self.h, _ptr(out)))
+        return out[:self.n_calls]
+
+    def warnings(self, call):
+        return self.L.sgb_frontend_warnings(self.h, call).decode()
+
+    def rng_state(self, call):
+        out = np.zeros(625, dtype=np.int32)
+        _check(self.L.sgb_frontend_rng_state(self.h, call, _ptr(out)))
+        return out
+
+    def h2d_bytes(self):
+        return int(self.L.sgb_frontend_h2d_bytes(self.h))
+
+
+class _Raw:
+    """A library-owned host buffer (pointer + bytes) in the shape pin_desc expects."""
+
+    def __init__(self, ptr, nbytes):
+        self.ptr, self.nbytes, self.size = ptr or 0, int(nbytes), int(nbytes)
+
+    @property
+    def ctypes(self):
+        return self
+
+    @property
+    def data(self):
+        return self.ptr
+
+
+def run_rounds(fe, batch=None, out_dtype=np.float32, copy=True):
+    """Drives every round of a front-end through one batch handle: upload, run_begin, draw the
+    deferred formant tracks, run_finish, fetch.  Returns (waveforms per call, statuses)."""
+    own = batch is None
+    bt = batch or Batch()
+    parts = [[] for _ in range(fe.n_calls)]
+    while True:
+        desc, n = fe.round_begin()
+        if n == 0:
+            break
+        bt.upload(desc)
+        bt.run()
+        segs = bt.fetch(out_dtype)
+        for k, ci in enumerate(fe.round_calls()):
+            parts[ci].append(segs[k].copy() if copy else segs[k])
+    st = fe.status()
+    if own:
+        bt.close()
+    outs = [(np.concatenate(p) if len(p) > 1 else (p[0] if p else np.zeros(0, dtype=out_dtype))) for p in parts]
+    return outs, st
+
+
 class BatchBuilder:
     """Accumulates soundgen() calls into the flat pools of an sgb_batch_desc."""
 
@@ -73,6 +294,7 @@ class BatchBuilder:
         self.n_pitch = self.n_anchors = self.n_formants = self.n_z = self.n_u = self.n_pre = 0
         self.u_dtype = np.dtype(u_dtype)
         self._keep = []
+        self._fe = None
 
     # ---- pools ----
     def _add_pitch(self, p):
@@ -253,192 +475,20 @@ class BatchBuilder:
         self.calls.append(c)
         return len(self.calls) - 1
 
-    # ---- the bout orchestrator's host-side part (R/soundgen.R:278-699) ----
-    def add_soundgen(self, repeatBout=1, nSyl=1, sylLen=300, pauseLen=200,
-                     pitchAnchors=((0, .1, .9, 1), (100, 150, 135, 100)), pitchAnchorsGlobal=None,
-                     temperature=0.025, maleFemale=0, creakyBreathy=0, nonlinBalance=0, nonlinDep=50,
-                     jitterLen=1, jitterDep=3, vibratoFreq=5, vibratoDep=0, shimmerDep=0, attackLen=50,
-                     rolloff=-12, rolloffOct=-12, rolloffKHz=-6, rolloffParab=0, rolloffParabHarm=3,
-                     rolloffLip=6, formants='default', formantDep=1, formantDepStoch=30, vocalTract=15.5,
-                     subFreq=100, subDep=100, shortestEpoch=300, amDep=0, amFreq=30, amShape=0,
-                     noiseAnchors=((0, 300), (-120, -120)), formantsNoise=None, rolloffNoise=-14,
-                     mouthAnchors=((0, 1), (.5, .5)), amplAnchors=None, amplAnchorsGlobal=None,
-                     samplingRate=16000, windowLength=50, overlap=75, addSilence=100, pitchFloor=50,
-                     pitchCeiling=3500, pitchSamplingRate=3500, throwaway=-120,
-                     invalidArgAction='adjust', z=None, u=None, contour_method='loess',
-                     pitchContours=None, warn=None):
-        """Adds one soundgen() call.  z: list of normal streams (one per voiced syllable, in
-        order); u: list of uniform buffers (one per noise segment).  Returns the call index."""
-        loc = dict(locals())
-        for p, (dflt, lo, hi) in host.PERMITTED.items():   # soundgen.R:279-302
-            v = loc[p]
-            if not isinstance(v, (int, float)) or v < lo or v > hi:
-                if invalidArgAction == 'abort':
-                    raise ValueError('%s must be between %s and %s' % (p, lo, hi))
-                if invalidArgAction == 'ignore':
-                    if warn is not None:
-                        warn.append("%s outside its range in 'permittedValues'" % p)
-                else:
-                    loc[p] = dflt
-                    if warn is not None:
-                        warn.append('%s outside permitted range, reset to %s' % (p, dflt))
-        g = lambda k: loc[k]
-        repeatBout, nSyl, sylLen, pauseLen, temperature = g('repeatBout'), g('nSyl'), g('sylLen'), g('pauseLen'), g('temperature')
-        maleFemale, creakyBreathy, nonlinBalance, nonlinDep = g('maleFemale'), g('creakyBreathy'), g('nonlinBalance'), g('nonlinDep')
-        jitterDep, jitterLen, vibratoFreq, vibratoDep, shimmerDep = g('jitterDep'), g('jitterLen'), g('vibratoFreq'), g('vibratoDep'), g('shimmerDep')
-        attackLen, rolloff, rolloffOct, rolloffParab, rolloffParabHarm = g('attackLen'), g('rolloff'), g('rolloffOct'), g('rolloffParab'), g('rolloffParabHarm')
-        rolloffKHz, rolloffLip, formantDep, vocalTract = g('rolloffKHz'), g('rolloffLip'), g('formantDep'), g('vocalTract')
-        subFreq, subDep, shortestEpoch, amDep, amFreq, amShape = g('subFreq'), g('subDep'), g('shortestEpoch'), g('amDep'), g('amFreq'), g('amShape')
-        samplingRate, windowLength, rolloffNoise = g('samplingRate'), g('windowLength'), g('rolloffNoise')
-        if temperature > 0:
-            raise NotImplementedError('temperature > 0 at the soundgen() level draws rnorm_bounded / '
-                                      'wiggleAnchors / stochastic formants from R\'s RNG on the host '
-                                      '(SURVEY.md 8f-2); use temperature = 0 here')
-        pitchAnchors = host.as_anchors(pitchAnchors)
-        pitchAnchorsGlobal = host.as_anchors(pitchAnchorsGlobal)
-        amplAnchors = host.as_anchors(amplAnchors)
-        amplAnchorsGlobal = host.as_anchors(amplAnchorsGlobal)
-        mouthAnchors = host.as_anchors(mouthAnchors)
-        noiseAnchors = host.as_anchors(noiseAnchors, t_hi=sylLen)
-        if isinstance(formants, str) and formants == 'default':
-            formants = DEFAULT_FORMANTS
-        formants = _formant_list(formants)
-        formantsNoise = _formant_list(formantsNoise)
-        wl_points = int(math.floor(windowLength / 1000 * samplingRate / 2) * 2)   # :317
-        if creakyBreathy < 0:   # :337-351
-            nonlinBalance = min(100, nonlinBalance - creakyBreathy * 50)
-            jitterDep = max(0, jitterDep - creakyBreathy / 2)
-            shimmerDep = max(0, shimmerDep - creakyBreathy * 5)
-            subDep = subDep * 2 ** (-creakyBreathy)
-        elif creakyBreathy > 0:
-            v = np.array([-120., -120.]) + creakyBreathy * 160
-            v[v > host.NOISE_AMPL[1]] = host.NOISE_AMPL[1]
-            noiseAnchors = (np.array([0., sylLen + 100]), v)
-        rolloff = rolloff - creakyBreathy * 10
-        rolloffOct = rolloffOct - creakyBreathy * 5
-        subFreq = 2 * (subFreq - 50) / (1 + math.exp(-.1 * (50 - nonlinDep))) + 50
-        jitterDep = 2 * jitterDep / (1 + math.exp(.1 * (50 - nonlinDep)))
-        if maleFemale != 0:   # :364-379
-            if pitchAnchors is not None:
-                pitchAnchors = (pitchAnchors[0], pitchAnchors[1] * 2 ** maleFemale)
-            if formants is not None:
-                for f in formants:
-                    f[:, 1] = f[:, 1] * 1.25 ** maleFemale
-            vocalTract = vocalTract * (1 - .25 * maleFemale)
-        nSyl, repeatBout = int(math.floor(nSyl)), int(math.floor(repeatBout))
-        pars = dict(attackLen=attackLen, jitterDep=jitterDep, jitterLen=jitterLen, vibratoFreq=vibratoFreq,
-                    vibratoDep=vibratoDep, shimmerDep=shimmerDep, rolloff=rolloff, rolloffOct=rolloffOct,
-                    rolloffKHz=rolloffKHz, rolloffParab=rolloffParab, rolloffParabHarm=rolloffParabHarm,
-                    temperature=temperature, pitchDriftDep=.5, pitchDriftFreq=.125,
-                    shortestEpoch=shortestEpoch, subFreq=subFreq, subDep=subDep,
-                    nonlinBalance=nonlinBalance, pitchFloor=pitchFloor, pitchCeiling=pitchCeiling,
-                    pitchSamplingRate=pitchSamplingRate, throwaway=throwaway, samplingRate=samplingRate)
-        if pitchAnchorsGlobal is not None and np.any(pitchAnchorsGlobal[1] != 0) and nSyl > 1:   # :448-462
-            pitchDeltas = 2 ** (host.smooth_contour(pitchAnchorsGlobal, nSyl, method='spline') / 12)
-        else:
-            pitchDeltas = np.ones(nSyl)
-        if pitchAnchors is not None:   # :465-472
-            t = pitchAnchors[0]
-            if np.min(t) < 0:
-                t = t - np.min(t)
-            if np.max(t) > 1:
-                t = t / np.max(t)
-            pitchAnchors = (t, pitchAnchors[1])
-        has_noise = noiseAnchors is not None and np.sum(noiseAnchors[1] > throwaway) > 0
-        z_fn = z if callable(z) else None    # z(n) / u(n): draw n values when a syllable / noise segment needs them
-        u_fn = u if callable(u) else None
-        z = [] if z_fn else (list(z) if isinstance(z, (list, tuple)) else ([z] if z is not None else []))
-        u = [] if u_fn else (list(u) if isinstance(u, (list, tuple)) else ([u] if u is not None else []))
-        zi = ui = si = 0
-        # main vocal-tract filter (soundgen.R:751-775)
-        moving = formants is not None and max(f.shape[0] for f in formants) > 1
-        if mouthAnchors is not None and np.sum(mouthAnchors[1] != .5) > 0:
-            moving = True
-        env_main = self.add_envelope(formants, formantDep=formantDep, rolloffLip=rolloffLip,
-                                     mouthAnchors=mouthAnchors, vocalTract=vocalTract,
-                                     samplingRate=samplingRate, contour_method=contour_method)
-        if amplAnchorsGlobal is not None and 3 <= amplAnchorsGlobal[0].size <= 10 and contour_method != 'spline':
-            raise NotImplementedError('amplAnchorsGlobal with 3-10 anchors use loess in the reference '
-                                      "(pass contour_method='spline')")
-        bout0 = len(self.bouts)
-        n_sil = int(host.rint(samplingRate / 1000 * addSilence)) if addSilence is not None else 0
-        for b in range(repeatBout):   # :482
-            if nSyl == 1:
-                syllables = np.array([[0., float(sylLen)]])
-            else:
-                rows, c = [], 0.
-                while len(rows) < nSyl:
-                    start = 1 + c
-                    end = start + sylLen
-                    rows.append([start, end])
-                    c = end + pauseLen
-                syllables = np.array(rows)
-            startIdx = host.rint(syllables[:, 0] * samplingRate / 1000)   # :517-532
-            startIdx[0] = 1
-            if noiseAnchors is not None and noiseAnchors[0][0] != 0:
-                shift = -host.rint(noiseAnchors[0][0] * samplingRate / 1000)
-                if noiseAnchors[0][0] < 0:
-                    startIdx[0] = (startIdx - shift)[0]
-                else:
-                    startIdx = startIdx - shift
-            syl_begin, noise_begin = len(self.syls), len(self.noises)
-            for s in range(syllables.shape[0]):   # :540
-                dur_syl = float(syllables[s, 1] - syllables[s, 0])
-                pause = 0
-                if s < syllables.shape[0] - 1:
-                    pause = int(math.floor((syllables[s + 1, 0] - syllables[s, 1]) * samplingRate / 1000))
-                silent = (dur_syl < host.SYLLEN_LOW or pitchAnchors is None or
-                          (noiseAnchors is not None and np.min(noiseAnchors[1]) >= 40))
-                if silent:
-                    self.add_silent_syllable(int(host.rint(dur_syl * samplingRate / 1000)), pause_after=pause)
-                else:
-                    if pitchContours is not None:
-                        pc = np.asarray(pitchContours[si], dtype=np.float64)
-                    else:
-                        pc = host.smooth_contour(pitchAnchors, int(host.rint(dur_syl * pitchSamplingRate / 1000)),
-                                                 thisIsPitch=True, method=contour_method,
-                                                 valueFloor=pitchFloor, valueCeiling=pitchCeiling)
-                    pc = pc * pitchDeltas[s]
-                    zs = z_fn(2 * pc.size + 64) if z_fn else (z[zi] if zi < len(z) else None)
-                    zi += 1
-                    self.add_syllable(pc, z=zs, amplAnchors=amplAnchors, pause_after=pause,
-                                      contour_method=contour_method, **pars)
-                si += 1
-                if has_noise:   # :643-698
-                    t = noiseAnchors[0].copy()
-                    t[t > 0] = t[t > 0] * dur_syl / sylLen
-                    rng_t = float(np.max(t) - np.min(t))
-                    ulen = int(host.rint(rng_t * samplingRate / 1000))
-                    env_n = -1
-                    if formantsNoise is not None:
-                        nInt = int(host.rint(rng_t / 10))   # :662-666 (always "moving", see oracle note)
-                        env_n = self.add_envelope(formantsNoise, formantDep=formantDep, rolloffLip=rolloffLip,
-                                                  mouthAnchors=mouthAnchors, vocalTract=vocalTract,
-                                                  samplingRate=samplingRate, nc_fixed=nInt,
-                                                  contour_method=contour_method)
-                    if u_fn:
-                        u_seg = u_fn(self.noise_uniform_count(ulen, wl_points, overlap))
-                    elif ui >= len(u):
-                        raise ValueError('soundgen(): a uniform buffer `u` is needed for each noise segment')
-                    else:
-                        u_seg = u[ui]
-                    self.add_noise(ulen, (t, noiseAnchors[1]), u_seg, rolloffNoise=rolloffNoise,
-                                   attackLen=attackLen, windowLength_points=wl_points, samplingRate=samplingRate,
-                                   overlap=overlap, env_id=env_n, insertion=int(startIdx[s]),
-                                   mix=0 if formantsNoise is None else 1, contour_method=contour_method)
-                    ui += 1
-            ag = None
-            if amplAnchorsGlobal is not None and np.sum(amplAnchorsGlobal[1] < -throwaway) > 0:   # :721-724
-                # the reference converts the anchors in place, so a later bout sees converted values
-                amplAnchorsGlobal = (amplAnchorsGlobal[0], 2 ** (amplAnchorsGlobal[1] / 10))
-                ag = amplAnchorsGlobal
-            lead = n_sil if b == 0 else int(pauseLen * samplingRate / 1000)   # :836-849
-            tail = n_sil if b == repeatBout - 1 else 0
-            self.add_bout(syl_begin, len(self.syls), noise_begin, len(self.noises), env_main, moving, wl_points,
-                          overlap=overlap, lead_silence=lead, tail_silence=tail, amplAnchorsGlobal=ag,
-                          amDep=amDep, amFreq=amFreq, amShape=amShape, samplingRate=samplingRate,
-                          throwaway=throwaway)
-        return self.add_call(bout0, len(self.bouts))
+    # ---- the bout orchestrator's host stage (R/soundgen.R:279-733): C front-end ----
+    def add_soundgen(self, **kw):
+        """Adds one soundgen() call through the library's host front-end (csrc/frontend.cu).
+        Besides soundgen()'s own arguments: `seed` (R's set.seed; every draw of the call then comes
+        from R's stream in the reference's order), or `z` / `u` (lists of caller-drawn normal /
+        uniform buffers, one per voiced syllable / noise segment; temperature must be 0),
+        `contour_method` ('loess' = reference, 'spline'), `warn` (list receiving the warnings),
+        `device_pitch` (evaluate the pitch contour on the device when no draw count depends on it).
+        Returns the call index."""
+        if self.syls or self.bouts:
+            raise ValueError('add_soundgen cannot be mixed with the low-level add_* calls in one builder')
+        if self._fe is None:
+            self._fe = FrontEnd(self.u_dtype)
+        return self._fe.add(**kw)
 
     def noise_uniform_count(self, length, windowLength_points, overlap=75):
         """number of runif() draws generateNoise makes (R/source.R:88-111)."""
@@ -448,6 +498,10 @@ class BatchBuilder:
 
     # ---- finalise ----
     def build(self):
+        if self._fe is not None:
+            desc, _ = self._fe.round_begin()
+            return desc
+
         def arr(T, items):
             a = (T * max(1, len(items)))()
             for i, it in enumerate(items):
@@ -480,6 +534,8 @@ class BatchBuilder:
         return d
 
     def h2d_bytes(self):
+        if self._fe is not None:
+            return self._fe.h2d_bytes()
         return (8 * (self.n_pitch + 2 * self.n_anchors + 4 * self.n_formants + self.n_z + self.n_pre) +
                 self.u_dtype.itemsize * self.n_u + C.sizeof(Syllable) * len(self.syls) +
                 C.sizeof(Bout) * len(self.bouts) + C.sizeof(Noise) * len(self.noises) +
@@ -512,8 +568,18 @@ class Batch:
         _check(self.L.sgb_batch_upload(self.h, C.byref(desc)))
 
     def run(self):
+        """One pass of the whole path over the uploaded batch.  A description that came from the host
+        front-end may hold main filters whose stochastic tracks can only be drawn once the device knows
+        the number of STFT frames: those are resolved between the two phases of the run."""
         info = RunInfo()
-        _check(self.L.sgb_batch_run(self.h, C.byref(info)))
+        fe = getattr(self.desc, '_fe', None)
+        if fe is None:
+            _check(self.L.sgb_batch_run(self.h, C.byref(info)))
+        else:
+            _check(self.L.sgb_batch_run_begin(self.h))
+            fe.resolve(self)
+            _check(self.L.sgb_batch_run_finish(self.h, C.byref(info)))
+            fe.round_end(self)
         self.info = info
         return info
 
@@ -576,41 +642,45 @@ class Batch:
 # ------------------------------------------------------------------------------
 # R-named entry points
 # ------------------------------------------------------------------------------
-def soundgen(*args, z=None, u=None, contour_method='loess', pitchContours=None, return_batch=False,
-             **kwargs):
+def soundgen(*args, return_batch=False, **kwargs):
     """soundgen() (R/soundgen.R:208-277): returns the synthesised waveform (float64).
-    Raises SoundgenError('Failed to generate the new syllable!') where the reference stops."""
+    `seed` plays the role of set.seed() before the call; without it the call must not need host
+    draws (temperature = 0) and takes its jitter / shimmer normals `z` and noise uniforms `u` from the
+    caller.  Raises SoundgenError('Failed to generate the new syllable!') where the reference stops."""
     names = ['repeatBout', 'nSyl', 'sylLen', 'pauseLen', 'pitchAnchors', 'pitchAnchorsGlobal', 'temperature']
     kwargs.update(dict(zip(names, args)))
-    bb = BatchBuilder()
-    bb.add_soundgen(z=z, u=u, contour_method=contour_method, pitchContours=pitchContours, **kwargs)
+    kwargs.pop('pitchContours', None)
+    fe = FrontEnd()
+    fe.add(**kwargs)
     bt = Batch()
-    bt.upload(bb.build())
-    bt.run()
-    st = bt.status()
+    try:
+        outs, st = run_rounds(fe, bt, np.float64)
+    except SoundgenError as e:
+        if e.code == _abi.SGB_ERR_STREAM:
+            raise ValueError('soundgen(): a uniform buffer `u` is needed for each noise segment (%s)' % e)
+        raise
     if st[0] == _abi.SGB_ERR_SYNTH:
         raise SoundgenError(st[0], 'Failed to generate the new syllable!')
+    if st[0] == _abi.SGB_ERR_STREAM and kwargs.get('seed') is None:
+        raise ValueError('soundgen(): the `z` / `u` buffers are shorter than the draws needed')
     if st[0] != 0:
-        raise SoundgenError(int(st[0]), 'soundgen failed')
-    y = bt.fetch(np.float64)[0].copy()
+        raise SoundgenError(int(st[0]), 'soundgen failed: %s' % fe.warnings(0))
+    y = outs[0]
     if return_batch:
         return y, bt
     bt.close()
+    fe.close()
     return y
 
 
 def soundgen_batch(list_of_kwargs, out_dtype=np.float32, u_dtype=np.float64):
     """Many soundgen() calls in one pass (the batched entry the reference lacks)."""
-    bb = BatchBuilder(u_dtype=u_dtype)
+    fe = FrontEnd(u_dtype)
     for kw in list_of_kwargs:
-        bb.add_soundgen(**kw)
-    bt = Batch()
-    bt.upload(bb.build())
-    bt.run()
-    out = [a.copy() for a in bt.fetch(out_dtype)]
-    st = bt.status()
-    bt.close()
-    return out, st
+        fe.add(**kw)
+    outs, st = run_rounds(fe, None, out_dtype)
+    fe.close()
+    return outs, st
 
 
 class PipelinedBatches:

@@ -3,7 +3,7 @@
 // artefacts (glottal cycles, epochs, nSubharm, rw_bin, jitter idx, gc_upsampled)
 // and the per-glottal-cycle arrays the sample-rate kernels consume.
 #pragma once
-#include "rmath.cuh"
+#include "contour.cuh"
 
 // ---------------------------------------------------------------- helpers ---
 // noiseThresholdsDict (data-raw/noiseThresholdsDict.R:4-18); a fractional
@@ -192,32 +192,13 @@ SGB_HD void ctrl_sequential(const sgb_syllable &sp, const double *anchors, const
   }
   double *rolloffAmpl = A.t4;
   if (C.use_ampl) {
-    const double *an = anchors + 2 * sp.ampl_off;
-    int n = sp.ampl_n;
-    // getSmoothContour(len = nGC, valueFloor = 0, valueCeiling = -throwaway)
-    // anchors: values clamped, time rescaled to 0..1 (smoothContours.R:78-99)
-    double tmin = an[0], tmax = an[0];
-    for (int i = 1; i < n; i++) { tmin = fmin(tmin, an[2 * i]); tmax = fmax(tmax, an[2 * i]); }
-    if (n > SGB_MAX_RW_KNOTS) { C.status = SGB_ERR_UNSUPPORTED; return; }
-    double tx[SGB_MAX_RW_KNOTS], vy[SGB_MAX_RW_KNOTS], cb[SGB_MAX_RW_KNOTS], cc[SGB_MAX_RW_KNOTS],
-        cd[SGB_MAX_RW_KNOTS];
-    for (int i = 0; i < n; i++) {
-      double v = an[2 * i + 1];
-      if (v < 0.0) v = 0.0;
-      if (v > -sp.throwaway) v = -sp.throwaway;
-      vy[i] = v;
-      tx[i] = (an[2 * i] - tmin) / (tmax - tmin);
-    }
-    if (n >= 3) fmm_coef(n, tx, vy, cb, cc, cd);
+    // getSmoothContour(len = nGC, valueFloor = 0, valueCeiling = -throwaway, samplingRate)
+    ContourTab T;
+    contour_prepare(&T, anchors + 2 * sp.ampl_off, sp.ampl_n, G, sp.samplingRate, true, 0.0, true,
+                    -sp.throwaway, false, sp.ampl_method);
+    if (T.status != SGB_OK) { C.status = T.status; return; }
     for (int g = 0; g < G; g++) {
-      double v;
-      if (n == 1) v = vy[0];
-      else if (n == 2) v = r_seq_at(vy[0], vy[1], G, g);
-      else {
-        v = r_spline_at(n, tx, vy, cb, cc, cd, G, g);
-        if (v < 0.0) v = 0.0;
-        if (v > -sp.throwaway) v = -sp.throwaway;
-      }
+      double v = contour_eval(&T, G, g);
       rolloffAmpl[g] = (v / fabs(sp.throwaway) - 1.0) * sp.rolloff_perAmpl;
     }
   } else {
@@ -406,7 +387,7 @@ SGB_HD void ctrl_sequential(const sgb_syllable &sp, const double *anchors, const
     A.gcup[0] = 1;
     for (int g = 0; g < G; g++) {
       double len = rint(sr / A.ppg[g]);
-      if (len < 2.0) { C.status = SGB_ERR_INVALID; return; }
+      if (len < 4.0) { C.status = SGB_ERR_UNSUPPORTED; return; }   // glottal cycles shorter than 4 samples (f0 > sr/4)
       A.t3[g] = len;
       c += len;
       if (c > 2.0e9) { C.status = SGB_ERR_INVALID; return; }

@@ -31,10 +31,12 @@ void launch_compose(const sgb_syllable *, int, SylCtrl *, const SylLayout *, con
                     const float *, float *, const double *, const double *, const int *, cudaStream_t);
 void launch_place_voiced(const sgb_syllable *, int, const SylCtrl *, const SylLayout *, const SylPlace *,
                          const Pools &, const float *, float *, int, cudaStream_t);
+void launch_env_tracks(const EnvInst *, int, const sgb_envelope *, const sgb_formant_ref *, const double *,
+                       const double *, double *, double *, cudaStream_t);
 void launch_envelope_f32(const EnvInst *, int, int, const sgb_envelope *, const sgb_formant_ref *, const double *,
-                         const double *, const double *, float *, cudaStream_t);
+                         const double *, const double *, const double *, const double *, float *, cudaStream_t);
 void launch_envelope_f64(const EnvInst *, int, int, const sgb_envelope *, const sgb_formant_ref *, const double *,
-                         const double *, const double *, double *, cudaStream_t);
+                         const double *, const double *, const double *, const double *, double *, cudaStream_t);
 size_t stft_smem_bytes(int n, double h_in, double h_out, int mode);
 cudaError_t launch_stft(int mode, int u_is_float, int spec, const FftSeg *, int, const FftJob *, const FftPlan *,
                         const float2 *, const float *, const float *, const void *, const float *, float *, int *,
@@ -83,11 +85,12 @@ static int fail(int code, const char *fmt, ...) {
     }                                                                                          \
   } while (0)
 
-struct SylSummary { int32_t status, out_len, n_up, nGC; };
+struct SylSummary { int32_t status, out_len, n_up, nGC, z_used, pad; };
 __global__ void k_summary(const SylCtrl *ctrl, int S, SylSummary *out) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= S) return;
   out[s].status = ctrl[s].status; out[s].out_len = ctrl[s].out_len; out[s].n_up = ctrl[s].n_up; out[s].nGC = ctrl[s].nGC;
+  out[s].z_used = ctrl[s].z_used; out[s].pad = 0;
 }
 __global__ void k_fill_int(int *p, int n, int v) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -145,6 +148,7 @@ static int seq_by_count(double from, double to, double by) {
   return (int)std::floor((to - from) / by + 1e-10) + 1;
 }
 
+struct RunState;
 struct sgb_batch {
   int device = 0;
   cudaStream_t st = nullptr;
@@ -158,6 +162,7 @@ struct sgb_batch {
   std::vector<sgb_noise> noises;
   std::vector<sgb_envelope> envs;
   std::vector<sgb_formant_ref> frefs;
+  std::vector<double> h_anchors;   // host copy of the anchor pool (contour_fits)
   int64_t n_pitch = 0, n_anchors = 0, n_formants = 0, n_z = 0, n_u = 0, n_pre = 0;
   int u_is_float = 0;
   // device copies
@@ -168,6 +173,10 @@ struct sgb_batch {
   HBuf h_calltab;
   DBuf d_pcm, d_calltab;
   DBuf d_amp, d_amp32, d_wave, d_raw, d_sound, d_voiced, d_filt, d_noise_raw, d_noise_fin, d_env, d_out, d_out64;
+  DBuf d_trk, d_mouth, d_formants_late;
+  struct RunState *rs = nullptr;     // state carried from run_begin to run_finish
+  std::vector<double> late_rows;     // host-drawn formant tracks set between begin and finish
+  bool envs_dirty = false;
   DBuf d_bl, d_place, d_nl, d_envinst, d_plans, d_tw, d_win, d_fjobs, d_njobs, d_fsegs, d_nsegs, d_max;
   Pools pools;
   int64_t gc_total = 0, h_total = 0;
@@ -251,6 +260,8 @@ static cudaError_t wait_stream(sgb_batch *b) {
   return cudaEventSynchronize(b->ev_wait);
 }
 
+int sgb_fail_msg(int code, const char *msg) { return fail(code, "%s", msg); }
+
 extern "C" {
 
 int sgb_version(void) { return SGB_VERSION; }
@@ -320,10 +331,22 @@ int sgb_batch_create(sgb_batch **out) {
   if (cudaGetDeviceCount(&n) != cudaSuccess || n < 1)
     return fail(SGB_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
   sgb_batch *b = new sgb_batch();
-  CK(cudaGetDevice(&b->device));
-  CK(cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking));
-  for (auto &e : b->ev) CK(cudaEventCreate(&e));
-  CK(cudaEventCreateWithFlags(&b->ev_wait, cudaEventBlockingSync | cudaEventDisableTiming));
+  for (auto &e : b->ev) e = nullptr;
+  auto init = [&]() -> int {
+    CK(cudaGetDevice(&b->device));
+    CK(cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking));
+    for (auto &e : b->ev) CK(cudaEventCreate(&e));
+    CK(cudaEventCreateWithFlags(&b->ev_wait, cudaEventBlockingSync | cudaEventDisableTiming));
+    return SGB_OK;
+  };
+  int rc = init();
+  if (rc != SGB_OK) {            // do not leak a half-built handle
+    for (auto &e : b->ev) if (e) cudaEventDestroy(e);
+    if (b->ev_wait) cudaEventDestroy(b->ev_wait);
+    if (b->st) cudaStreamDestroy(b->st);
+    delete b;
+    return rc;
+  }
   memset(&b->info, 0, sizeof b->info);
   *out = b;
   return SGB_OK;
@@ -338,14 +361,16 @@ void sgb_batch_destroy(sgb_batch *b) {
                  &b->d_totals, &b->d_summary, &b->d_tiles, &b->d_epmax, &b->p_pitch_w, &b->d_amp, &b->d_amp32, &b->d_wave, &b->d_raw,
                  &b->d_sound, &b->d_voiced, &b->d_filt, &b->d_noise_raw, &b->d_noise_fin, &b->d_env, &b->d_out,
                  &b->d_out64, &b->d_bl, &b->d_place, &b->d_nl, &b->d_envinst, &b->d_plans, &b->d_tw, &b->d_win,
-                 &b->d_fjobs, &b->d_njobs, &b->d_fsegs, &b->d_nsegs, &b->d_max};
+                 &b->d_fjobs, &b->d_njobs, &b->d_fsegs, &b->d_nsegs, &b->d_max, &b->d_trk, &b->d_mouth, &b->d_formants_late};
   for (auto d : all) d->release();
   for (auto &d : b->p_i32) d.release();
   for (auto &d : b->p_f64) d.release();
   b->p_pc.release();
   b->h_tot.release(); b->h_summary.release(); b->h_lay.release(); b->h_calltab.release();
   b->d_pcm.release(); b->d_calltab.release();
+  delete b->rs;
   for (auto &e : b->ev) cudaEventDestroy(e);
+  if (b->ev_wait) cudaEventDestroy(b->ev_wait);
   cudaStreamDestroy(b->st);
   delete b;
 }
@@ -377,20 +402,28 @@ int sgb_batch_upload(sgb_batch *b, const sgb_batch_desc *D) {
     if (B.wl < 4) return fail(SGB_ERR_INVALID, "bout %d: windowLength_points %d < 4", i, B.wl);
     if (!(B.overlap >= 0.0 && B.overlap < 100.0)) return fail(SGB_ERR_INVALID, "bout %d: overlap out of range", i);
     if (!(B.samplingRate > 0)) return fail(SGB_ERR_INVALID, "bout %d: samplingRate", i);
-    if (B.aglobal_n > ENV_MAXK_HOST) return fail(SGB_ERR_UNSUPPORTED, "bout %d: too many amplAnchorsGlobal", i);
+    if (B.aglobal_n > ENV_MAXK_HOST) return fail(SGB_ERR_UNSUPPORTED, "bout %d: more than %d amplAnchorsGlobal", i, ENV_MAXK_HOST);
+    if (B.aglobal_n < 0 || (B.aglobal_n > 0 && (B.aglobal_off < 0 || B.aglobal_off + B.aglobal_n > D->n_anchors)))
+      return fail(SGB_ERR_INVALID, "bout %d: amplAnchorsGlobal range outside the anchor pool", i);
+    if (!(B.throwaway < 0)) return fail(SGB_ERR_INVALID, "bout %d: throwaway must be negative", i);
   }
   for (int s = 0; s < D->n_syllables; s++) {
     const sgb_syllable &Y = D->syllables[s];
     if (Y.kind < 0 || Y.kind > 2) return fail(SGB_ERR_INVALID, "syllable %d: bad kind", s);
     if (Y.kind == 0) { if (Y.silent_len < 0) return fail(SGB_ERR_INVALID, "syllable %d: silent_len", s); continue; }
-    if (Y.pitch_len < 1 || Y.pitch_off < 0 || Y.pitch_off + Y.pitch_len > D->n_pitch)
+    const bool dev_pitch = (Y.kind == 1 && Y.pitch_anchor_n > 0);
+    if (Y.pitch_len < 1 || Y.pitch_off < 0 || (!dev_pitch && Y.pitch_off + Y.pitch_len > D->n_pitch))
       return fail(SGB_ERR_INVALID, "syllable %d: pitch range outside the pool", s);
+    if (Y.kind == 1 && Y.pitch_anchor_n != 0) {
+      if (Y.pitch_anchor_n < 0 || Y.pitch_anchor_n > ENV_MAXK_HOST)
+        return fail(SGB_ERR_UNSUPPORTED, "syllable %d: more than %d pitchAnchors", s, ENV_MAXK_HOST);
+      if (Y.pitch_anchor_off < 0 || Y.pitch_anchor_off + Y.pitch_anchor_n > D->n_anchors)
+        return fail(SGB_ERR_INVALID, "syllable %d: pitchAnchors range outside the anchor pool", s);
+    }
     if (Y.kind == 2) continue;
     if (Y.pitch_len < 3) return fail(SGB_ERR_INVALID, "syllable %d: pitch contour shorter than 3 points", s);
     if (!(Y.samplingRate > 0) || !(Y.pitchSamplingRate > 0) || !(Y.pitchFloor > 0) || !(Y.pitchCeiling >= Y.pitchFloor))
       return fail(SGB_ERR_INVALID, "syllable %d: sampling rates / pitch bounds", s);
-    if (Y.pitchCeiling > Y.samplingRate / 4.0)
-      return fail(SGB_ERR_UNSUPPORTED, "syllable %d: pitchCeiling above samplingRate/4 (glottal cycles < 4 samples)", s);
     if (Y.z_cap < 0 || Y.z_off < 0 || Y.z_off + Y.z_cap > D->n_z) return fail(SGB_ERR_INVALID, "syllable %d: z range", s);
     if (Y.ampl_n < 0 || Y.ampl_n > SGB_MAX_RW_KNOTS || (Y.ampl_n > 0 && (Y.ampl_off < 0 || Y.ampl_off + Y.ampl_n > D->n_anchors)))
       return fail(SGB_ERR_INVALID, "syllable %d: amplAnchors range", s);
@@ -412,10 +445,26 @@ int sgb_batch_upload(sgb_batch *b, const sgb_batch_desc *D) {
   }
   for (int e = 0; e < D->n_envelopes; e++) {
     const sgb_envelope &E = D->envelopes[e];
-    if (E.n_formants < 0 || E.n_formants > 30) return fail(SGB_ERR_UNSUPPORTED, "envelope %d: more than 30 formants", e);
+    if (E.n_formants < 0 || E.n_formants > 62) return fail(SGB_ERR_UNSUPPORTED, "envelope %d: more than 62 formants", e);
     if (E.n_formants > 0 && (E.formant_off < 0 || E.formant_off + E.n_formants > D->n_formant_refs))
       return fail(SGB_ERR_INVALID, "envelope %d: formant refs", e);
-    if (E.mouth_n < 0 || E.mouth_n > ENV_MAXK_HOST) return fail(SGB_ERR_UNSUPPORTED, "envelope %d: mouth anchors", e);
+    if (E.mouth_n < 0 || E.mouth_n > ENV_MAXK_HOST) return fail(SGB_ERR_UNSUPPORTED, "envelope %d: more than %d mouth anchors", e, ENV_MAXK_HOST);
+    if (E.mouth_n > 0 && (E.mouth_off < 0 || E.mouth_off + E.mouth_n > D->n_anchors))
+      return fail(SGB_ERR_INVALID, "envelope %d: mouthAnchors range outside the anchor pool", e);
+    if (E.tracks_given < 0 || E.tracks_given > 3) return fail(SGB_ERR_INVALID, "envelope %d: tracks_given", e);
+    if (E.tracks_given == 2) {
+      if (E.nc_fixed < 1 || E.formant_off < 0) return fail(SGB_ERR_INVALID, "envelope %d: literal filter matrix needs nc_fixed >= 1", e);
+    } else if (E.n_formants > 0) {
+      int np = 0;
+      for (int f = 0; f < E.n_formants; f++) {
+        const sgb_formant_ref &R = D->formant_index[E.formant_off + f];
+        np = std::max(np, (int)R.n);
+        if (E.tracks_given == 1 && E.nc_fixed > 0 && R.n < E.nc_fixed)
+          return fail(SGB_ERR_INVALID, "envelope %d: formant %d has %d track rows for %d columns", e, f, R.n, E.nc_fixed);
+      }
+      if (E.tracks_given == 0 && np > 1 && (double)np + std::exp2(E.smoothLinearFactor) > (double)ENV_MAXK_HOST)
+        return fail(SGB_ERR_UNSUPPORTED, "envelope %d: %d formant time points (+ 2^smoothLinearFactor) exceed the %d knots supported", e, np, ENV_MAXK_HOST);
+    }
   }
   for (int f = 0; f < D->n_formant_refs; f++) {
     const sgb_formant_ref &R = D->formant_index[f];
@@ -428,6 +477,8 @@ int sgb_batch_upload(sgb_batch *b, const sgb_batch_desc *D) {
   b->noises.assign(D->noises, D->noises + D->n_noises);
   b->envs.assign(D->envelopes, D->envelopes + D->n_envelopes);
   b->frefs.assign(D->formant_index, D->formant_index + D->n_formant_refs);
+  b->h_anchors.assign(D->anchors, D->anchors + 2 * D->n_anchors);
+  if (b->h_anchors.empty()) b->h_anchors.assign(2, 0.0);
   b->n_pitch = D->n_pitch; b->n_anchors = D->n_anchors; b->n_formants = D->n_formants;
   b->n_z = D->n_z; b->n_u = D->n_u; b->n_pre = D->n_pre; b->u_is_float = D->u_is_float;
   const int S = D->n_syllables;
@@ -469,7 +520,10 @@ int sgb_batch_upload(sgb_batch *b, const sgb_batch_desc *D) {
   b->where = 0;
   CK(cudaEventElapsedTime(&b->info.ms[SGB_T_H2D], b->ev[SGB_T_COUNT], b->ev[SGB_T_COUNT + 1]));
 
-  CK(b->p_pitch_w.ensure(8 * (size_t)std::max<int64_t>(1, D->n_pitch)));
+  int64_t pw = std::max<int64_t>(1, D->n_pitch);   // device-evaluated contours only live in the work pool
+  for (int s = 0; s < S; s++)
+    if (b->syls[s].kind == 1) pw = std::max<int64_t>(pw, b->syls[s].pitch_off + b->syls[s].pitch_len);
+  CK(b->p_pitch_w.ensure(8 * (size_t)pw));
   for (int i = 0; i < 5; i++) CK(b->p_i32[i].ensure(4 * (size_t)g));
   CK(b->p_i32[5].ensure(4 * (size_t)h));
   for (auto &d : b->p_f64) CK(d.ensure(8 * (size_t)g));
@@ -489,6 +543,7 @@ int sgb_batch_upload(sgb_batch *b, const sgb_batch_desc *D) {
   CK(b->d_totals.ensure(64));
   CK(b->d_summary.ensure(sizeof(SylSummary) * (size_t)S));
   CK(b->d_epmax.ensure(4 * (size_t)S * SGB_MAX_EPOCHS));
+  b->late_rows.clear(); b->envs_dirty = false;
   b->have_desc = true;
   b->have_run = false;
   b->keep_voiced = (D->n_calls <= 64);
@@ -522,6 +577,18 @@ struct PlanKey {
   int n; double overlap;
   bool operator<(const PlanKey &o) const { return n < o.n || (n == o.n && overlap < o.overlap); }
 };
+
+// A loess contour (3-10 anchors) can fail the way the reference's loess() does ("span is too small"
+// after the span-shrinking loop of smoothContours.R:145-152).  The kernels evaluate the contours; the
+// host runs the same scalar fit once per contour whose length it knows to learn whether the reference
+// call would have stopped.  1, 2 or more than 10 anchors and method 'spline' never fail.
+static bool contour_fits(int na, int method, int len, double samplingRate, bool has_lo, double lo, bool has_hi,
+                         double hi, const double *an) {
+  if (na < 3 || na > 10 || method != SGB_CONTOUR_LOESS || len < 1) return true;
+  ContourTab T;
+  contour_prepare(&T, an, na, len, samplingRate, has_lo, lo, has_hi, hi, false, method);
+  return T.status == SGB_OK;
+}
 
 // FFT plans + twiddle / window tables (seewave hamming.w / hanning.w, seewave.r:7431-7450)
 struct PlanTable {
@@ -601,10 +668,29 @@ static void match_lengths(int xlen, int len, int *pad, int *start0) {
   *start0 = (int)std::ceil(center - halflen) - 1;
 }
 
+struct RunState {
+  std::vector<EnvInst> envinst;
+  std::vector<FftJob> fjobs, njobs;
+  PlanTable PT;
+  int64_t sound_total = 0, filt_total = 0, env_total = 0, out_total = 0, noise_total = 0;
+  int launches = 0;
+  bool begun = false;
+};
+
 int sgb_batch_run(sgb_batch *b, sgb_run_info *info_out) {
+  int rc = sgb_batch_run_begin(b);
+  if (rc != SGB_OK) return rc;
+  return sgb_batch_run_finish(b, info_out);
+}
+
+int sgb_batch_run_begin(sgb_batch *b) {
   if (!b) return fail(SGB_ERR_INVALID, "null batch");
   if (!b->have_desc) return fail(SGB_ERR_STATE, "sgb_batch_run before sgb_batch_upload");
+  if (!b->rs) b->rs = new RunState();
+  RunState &R = *b->rs;
+  R.begun = false;
   CK(cudaSetDevice(b->device));
+  b->have_run = false;           // a failed run must not leave the previous run's results fetchable
   cudaStream_t st = b->st;
   const int S = (int)b->syls.size(), NB = (int)b->bouts.size(), NN = (int)b->noises.size(), NC = (int)b->calls.size();
   sgb_run_info &info = b->info;
@@ -682,12 +768,14 @@ int sgb_batch_run(sgb_batch *b, sgb_run_info *info_out) {
   b->place.assign(S, SylPlace());
   b->nl.assign(NN, NoiseLayout());
   b->call_len.assign(NC, 0); b->call_off.assign(NC, 0); b->call_status.assign(NC, SGB_OK);
-  std::vector<EnvInst> envinst;
-  std::vector<FftJob> fjobs, njobs;
+  std::vector<EnvInst> &envinst = R.envinst;
+  std::vector<FftJob> &fjobs = R.fjobs, &njobs = R.njobs;
+  envinst.clear(); fjobs.clear(); njobs.clear();
+  R.PT = PlanTable();
+  PlanTable &PT = R.PT;
   int64_t sound_total = 0, filt_total = 0, env_total = 0, out_total = 0, noise_total = 0;
   int n_failed = 0;
 
-  PlanTable PT;
   auto get_plan = [&](int n, double overlap) -> int { return PT.get(n, overlap); };
 
   std::vector<int64_t> syl_pos, npos, fpos;   // reused across bouts (no allocation per bout)
@@ -734,6 +822,8 @@ int sgb_batch_run(sgb_batch *b, sgb_run_info *info_out) {
       }
       L.sound_len = (int32_t)cur;
       L.voiced_shift = (int32_t)shift;
+      if (!contour_fits(B.aglobal_n, B.aglobal_method, (int)cur, B.samplingRate, true, 0.0, true, -B.throwaway,
+                        b->h_anchors.data() + 2 * B.aglobal_off)) b->call_status[c] = SGB_ERR_SYNTH;
       L.sound_off = sound_total;
       for (int s = B.syl_begin; s < B.syl_end; s++) b->place[s].dst_off = L.sound_off + shift + syl_pos[s - B.syl_begin];
       for (int n = B.noise_begin; n < B.noise_end; n++)
@@ -762,8 +852,10 @@ int sgb_batch_run(sgb_batch *b, sgb_run_info *info_out) {
       if (!L.bypass) {
         L.filt_off = filt_total; filt_total += align4(L.filt_len + 4);
         L.env_off = env_total; env_total += align4((int64_t)(L.wl / 2) * L.nint);
-        EnvInst I; I.out_off = L.env_off; I.env_id = B.env_id; I.nr = L.wl / 2; I.nc = L.nint; I.col0 = 0;
+        EnvInst I; I.out_off = L.env_off; I.env_id = B.env_id; I.nr = L.wl / 2; I.nc = L.nint; I.col0 = 0; I.trk_off = -1;
         envinst.push_back(I);
+        if (!contour_fits(b->envs[B.env_id].mouth_n, b->envs[B.env_id].mouth_method, L.nint, 16000.0, true, 0.0, true, 1.0,
+                          b->h_anchors.data() + 2 * b->envs[B.env_id].mouth_off)) b->call_status[c] = SGB_ERR_SYNTH;
         FftJob J; memset(&J, 0, sizeof J);
         J.in_off = L.sound_off; J.out_off = L.filt_off; J.env_off = L.env_off; J.plan = L.fft_plan;
         J.nc = L.nc; J.nint = L.nint; J.xlen = L.filt_len; J.out_len = L.filt_len; J.shift = 0; J.max_slot = bi;
@@ -803,6 +895,8 @@ int sgb_batch_run(sgb_batch *b, sgb_run_info *info_out) {
         Q.nc = seq_by_count(1.0, (double)N.len + N.wl, h_in);
         Q.xlen = (int32_t)std::floor(N.wl + (Q.nc - 1) * h_out);
         match_lengths(Q.xlen, N.len, &Q.pad_len, &Q.trim_start);
+        if (N.strength_pre_off < 0 && !contour_fits(N.anchor_n, N.anchor_method, N.len, N.samplingRate, true, -120.0, true, 40.0,
+                                                    b->h_anchors.data() + 2 * N.anchor_off)) b->call_status[c] = SGB_ERR_SYNTH;
         Q.fft_plan = get_plan(N.wl, N.overlap);
         Q.env_off = -1; Q.nc_env = 0;
         if (Q.fft_plan < 0) { b->call_status[c] = SGB_ERR_UNSUPPORTED; continue; }
@@ -810,8 +904,10 @@ int sgb_batch_run(sgb_batch *b, sgb_run_info *info_out) {
           const sgb_envelope &E = b->envs[N.env_id];
           Q.nc_env = std::max(1, E.nc_fixed);
           Q.env_off = env_total; env_total += align4((int64_t)(N.wl / 2) * Q.nc_env);
-          EnvInst I; I.out_off = Q.env_off; I.env_id = N.env_id; I.nr = N.wl / 2; I.nc = Q.nc_env; I.col0 = 0;
+          EnvInst I; I.out_off = Q.env_off; I.env_id = N.env_id; I.nr = N.wl / 2; I.nc = Q.nc_env; I.col0 = 0; I.trk_off = -1;
           envinst.push_back(I);
+          if (!contour_fits(E.mouth_n, E.mouth_method, Q.nc_env, 16000.0, true, 0.0, true, 1.0,
+                            b->h_anchors.data() + 2 * E.mouth_off)) b->call_status[c] = SGB_ERR_SYNTH;
         }
         FftJob J; memset(&J, 0, sizeof J);
         J.in_off = N.u_off; J.out_off = Q.raw_off; J.env_off = Q.env_off; J.plan = Q.fft_plan; J.nc = Q.nc;
@@ -828,6 +924,42 @@ int sgb_batch_run(sgb_batch *b, sgb_run_info *info_out) {
   b->total_out = out_total;
   info.n_failed = n_failed;
   for (int c = 0; c < NC; c++) info.total_samples += b->call_len[c];
+  R.sound_total = sound_total; R.filt_total = filt_total; R.env_total = env_total; R.out_total = out_total;
+  R.noise_total = noise_total; R.launches = launches;
+  R.begun = true;
+  return SGB_OK;
+}
+
+int sgb_batch_run_finish(sgb_batch *b, sgb_run_info *info_out) {
+  if (!b) return fail(SGB_ERR_INVALID, "null batch");
+  if (!b->rs || !b->rs->begun) return fail(SGB_ERR_STATE, "sgb_batch_run_finish before sgb_batch_run_begin");
+  RunState &R = *b->rs;
+  R.begun = false;
+  CK(cudaSetDevice(b->device));
+  cudaStream_t st = b->st;
+  const int S = (int)b->syls.size(), NB = (int)b->bouts.size(), NN = (int)b->noises.size(), NC = (int)b->calls.size();
+  sgb_run_info &info = b->info;
+  const Pools &P = b->pools;
+  const sgb_syllable *d_syl = b->d_syls.as<sgb_syllable>();
+  SylCtrl *d_ctrl = b->d_ctrl.as<SylCtrl>();
+  SylLayout *d_lay = b->d_lay.as<SylLayout>();
+  cudaEvent_t *ev = b->ev;
+  std::vector<EnvInst> &envinst = R.envinst;
+  std::vector<FftJob> &fjobs = R.fjobs, &njobs = R.njobs;
+  PlanTable &PT = R.PT;
+  const int64_t sound_total = R.sound_total, filt_total = R.filt_total, env_total = R.env_total,
+                out_total = R.out_total, noise_total = R.noise_total;
+  int launches = R.launches;
+  for (size_t e = 0; e < b->envs.size(); e++)
+    if (b->envs[e].tracks_given == 3) return fail(SGB_ERR_STATE, "envelope %d: deferred formant tracks were never set", (int)e);
+  if (b->envs_dirty) {     // host-drawn tracks arrived between begin and finish
+    CK(cudaMemcpyAsync(b->d_envs.p, b->envs.data(), sizeof(sgb_envelope) * b->envs.size(), cudaMemcpyHostToDevice, st));
+    CK(b->d_frefs.ensure(sizeof(sgb_formant_ref) * b->frefs.size()));
+    CK(cudaMemcpyAsync(b->d_frefs.p, b->frefs.data(), sizeof(sgb_formant_ref) * b->frefs.size(), cudaMemcpyHostToDevice, st));
+    CK(b->d_formants_late.ensure(8 * std::max<size_t>(b->late_rows.size(), 4)));
+    CK(cudaMemcpyAsync(b->d_formants_late.p, b->late_rows.data(), 8 * b->late_rows.size(), cudaMemcpyHostToDevice, st));
+    b->envs_dirty = false;
+  }
 
   std::vector<FftSeg> fsegs, nsegs;
   std::vector<SegGroup> fgroups, ngroups;
@@ -840,7 +972,17 @@ int sgb_batch_run(sgb_batch *b, sgb_run_info *info_out) {
   const int64_t tw_total = (int64_t)tw_host.size(), win_total = (int64_t)win_host.size();
   // ---- upload layout ----
   int max_nc = 0;   // total (instance, column) work items of K4: the kernel runs one CTA per item
-  for (auto &I : envinst) { I.col0 = max_nc; max_nc += I.nc; }
+  int64_t trk_total = 0;
+  for (auto &I : envinst) {
+    I.col0 = max_nc; max_nc += I.nc;
+    const sgb_envelope &E = b->envs[I.env_id];
+    bool moving = false;
+    if (E.tracks_given == 0)
+      for (int f = 0; f < E.n_formants; f++) if (b->frefs[E.formant_off + f].n > 1) moving = true;
+    if (moving) { I.trk_off = trk_total; trk_total += (int64_t)I.nc * E.n_formants * 3; }
+  }
+  CK(b->d_trk.ensure(8 * (size_t)std::max<int64_t>(trk_total, 1)));
+  CK(b->d_mouth.ensure(8 * (size_t)std::max(max_nc, 1)));
   CK(b->d_bl.ensure(sizeof(BoutLayout) * (size_t)NB));
   CK(b->d_place.ensure(sizeof(SylPlace) * (size_t)S));
   CK(b->d_nl.ensure(sizeof(NoiseLayout) * (size_t)std::max(NN, 1)));
@@ -892,10 +1034,13 @@ int sgb_batch_run(sgb_batch *b, sgb_run_info *info_out) {
   }
   CK(cudaEventRecord(ev[5], st)); trace_mark(b, 5);   // assemble (part 1)
   // ---- K4 envelopes (bouts + noises) ----
+  launch_env_tracks(b->d_envinst.as<EnvInst>(), (int)envinst.size(), b->d_envs.as<sgb_envelope>(),
+                    b->d_frefs.as<sgb_formant_ref>(), b->d_formants.as<double>(), b->d_anchors.as<double>(),
+                    b->d_trk.as<double>(), b->d_mouth.as<double>(), st);
   launch_envelope_f32(b->d_envinst.as<EnvInst>(), (int)envinst.size(), max_nc, b->d_envs.as<sgb_envelope>(),
-                      b->d_frefs.as<sgb_formant_ref>(), b->d_formants.as<double>(), b->d_anchors.as<double>(),
-                      b->d_pre.as<double>(), b->d_env.as<float>(), st);
-  if (!envinst.empty()) launches++;
+                      b->d_frefs.as<sgb_formant_ref>(), b->d_formants.as<double>(), b->d_formants_late.as<double>(), b->d_trk.as<double>(),
+                      b->d_mouth.as<double>(), b->d_pre.as<double>(), b->d_env.as<float>(), st);
+  if (!envinst.empty()) launches += 2;
   CK(cudaEventRecord(ev[6], st)); trace_mark(b, 6);
   // ---- K5 noise ----
   if (!nsegs.empty()) {
@@ -954,6 +1099,52 @@ int sgb_batch_run(sgb_batch *b, sgb_run_info *info_out) {
   CK(cudaEventElapsedTime(&ms, ev[0], ev[10])); info.ms[SGB_T_TOTAL] = ms;
   b->have_run = true;
   if (info_out) *info_out = info;
+  return SGB_OK;
+}
+
+int sgb_batch_bout_geometry(sgb_batch *b, int32_t bout, int32_t *nc, int32_t *nint, int32_t *wl, int32_t *sound_len) {
+  if (!b || !b->rs || !(b->rs->begun || b->have_run)) return fail(SGB_ERR_STATE, "no run in progress");
+  if (bout < 0 || bout >= (int)b->bl.size()) return fail(SGB_ERR_INVALID, "bout index");
+  const BoutLayout &L = b->bl[bout];
+  if (nc) *nc = L.nc;
+  if (nint) *nint = L.nint;
+  if (wl) *wl = L.bypass ? 0 : L.wl;
+  if (sound_len) *sound_len = L.sound_len;
+  return SGB_OK;
+}
+
+int sgb_batch_set_tracks(sgb_batch *b, int32_t env, const double *rows, int32_t n_formants, int32_t nc) {
+  if (!b || !b->rs || !b->rs->begun) return fail(SGB_ERR_STATE, "sgb_batch_set_tracks outside run_begin / run_finish");
+  if (env < 0 || env >= (int)b->envs.size() || !rows || nc < 1) return fail(SGB_ERR_INVALID, "bad argument");
+  if (n_formants < 1 || n_formants > 62) return fail(SGB_ERR_UNSUPPORTED, "%d formant tracks (at most 62)", n_formants);
+  sgb_envelope &E = b->envs[env];
+  E.tracks_given = 1;
+  E.n_formants = n_formants;
+  E.formant_off = (int64_t)b->frefs.size();
+  for (int f = 0; f < n_formants; f++) {
+    sgb_formant_ref R;
+    R.off = (int64_t)(b->late_rows.size() / 4) + (int64_t)f * nc;
+    R.n = nc; R.pad = 1;                 // pad = 1: rows live in the late pool
+    b->frefs.push_back(R);
+  }
+  b->late_rows.insert(b->late_rows.end(), rows, rows + (size_t)4 * n_formants * nc);
+  b->envs_dirty = true;
+  return SGB_OK;
+}
+
+int sgb_batch_z_used(sgb_batch *b, int32_t *out) {
+  if (!b || !out) return fail(SGB_ERR_INVALID, "null argument");
+  if (!b->rs || !(b->rs->begun || b->have_run)) return fail(SGB_ERR_STATE, "no run");
+  for (size_t s = 0; s < b->summary.size(); s++) out[s] = b->summary[s].z_used;
+  return SGB_OK;
+}
+
+int sgb_abi_sizes(int32_t *out, int32_t cap) {
+  const int32_t v[] = {(int32_t)sizeof(sgb_syllable), (int32_t)sizeof(sgb_envelope), (int32_t)sizeof(sgb_noise),
+                       (int32_t)sizeof(sgb_bout), (int32_t)sizeof(sgb_call), (int32_t)sizeof(sgb_formant_ref),
+                       (int32_t)sizeof(sgb_batch_desc), (int32_t)sizeof(sgb_run_info), (int32_t)sizeof(sgb_soundgen_args)};
+  if (!out || cap < 9) return fail(SGB_ERR_INVALID, "need room for 9 sizes");
+  for (int i = 0; i < 9; i++) out[i] = v[i];
   return SGB_OK;
 }
 
@@ -1209,7 +1400,7 @@ int sgb_get_spectral_envelope(int32_t nr, int32_t nc, const sgb_envelope *env, c
                               const int32_t *formant_n, const double *mouth_anchors, double *out) {
   if (!env || !out) return fail(SGB_ERR_INVALID, "null argument");
   if (nr < 1 || nc < 1) return fail(SGB_ERR_INVALID, "nr and nc must be positive");
-  if (env->n_formants < 0 || env->n_formants > 30) return fail(SGB_ERR_UNSUPPORTED, "more than 30 formants");
+  if (env->n_formants < 0 || env->n_formants > 62) return fail(SGB_ERR_UNSUPPORTED, "more than 62 formants");
   if (env->n_formants > 0 && (!formants || !formant_n)) return fail(SGB_ERR_INVALID, "formants missing");
   if (env->mouth_n > 0 && !mouth_anchors) return fail(SGB_ERR_INVALID, "mouth anchors missing");
   int nd = 0;
@@ -1223,8 +1414,18 @@ int sgb_get_spectral_envelope(int32_t nr, int32_t nc, const sgb_envelope *env, c
     refs[f].off = rows; refs[f].n = n; refs[f].pad = 0; rows += n;
   }
   E.formant_off = 0; E.mouth_off = 0;
-  EnvInst I; I.out_off = 0; I.env_id = 0; I.nr = nr; I.nc = nc; I.col0 = -1;
-  DBuf dE, dR, dF, dA, dI, dO;
+  EnvInst I; I.out_off = 0; I.env_id = 0; I.nr = nr; I.nc = nc; I.col0 = 0; I.trk_off = -1;
+  int np = 0;
+  if (!E.tracks_given) for (int f = 0; f < E.n_formants; f++) np = std::max(np, (int)refs[f].n);
+  if (np > 1) {
+    if ((double)np + std::exp2(E.smoothLinearFactor) > (double)ENV_MAXK_HOST)
+      return fail(SGB_ERR_UNSUPPORTED, "%d formant time points (+ 2^smoothLinearFactor) exceed the %d knots supported", np, ENV_MAXK_HOST);
+    I.trk_off = 0;
+  }
+  if (E.mouth_n > ENV_MAXK_HOST) return fail(SGB_ERR_UNSUPPORTED, "more than %d mouth anchors", ENV_MAXK_HOST);
+  if (E.mouth_n > 0 && !contour_fits(E.mouth_n, E.mouth_method, nc, 16000.0, true, 0.0, true, 1.0, mouth_anchors))
+    return fail(SGB_ERR_SYNTH, "loess: span is too small (mouthAnchors)");
+  DBuf dE, dR, dF, dA, dI, dO, dT, dM;
   auto run = [&]() -> int {
     CK(dE.ensure(sizeof E)); CK(dR.ensure(sizeof(sgb_formant_ref) * refs.size())); CK(dF.ensure(32 * (size_t)std::max<int64_t>(rows, 1)));
     CK(dA.ensure(16 * (size_t)std::max(1, E.mouth_n))); CK(dI.ensure(sizeof I)); CK(dO.ensure(8 * (size_t)nr * nc));
@@ -1233,14 +1434,17 @@ int sgb_get_spectral_envelope(int32_t nr, int32_t nc, const sgb_envelope *env, c
     if (rows) CK(cudaMemcpy(dF.p, formants, 32 * (size_t)rows, cudaMemcpyHostToDevice));
     if (E.mouth_n) CK(cudaMemcpy(dA.p, mouth_anchors, 16 * (size_t)E.mouth_n, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dI.p, &I, sizeof I, cudaMemcpyHostToDevice));
+    CK(dT.ensure(8 * (size_t)std::max(1, nc * E.n_formants * 3))); CK(dM.ensure(8 * (size_t)nc));
+    launch_env_tracks(dI.as<EnvInst>(), 1, dE.as<sgb_envelope>(), dR.as<sgb_formant_ref>(), dF.as<double>(),
+                      dA.as<double>(), dT.as<double>(), dM.as<double>(), 0);
     launch_envelope_f64(dI.as<EnvInst>(), 1, nc, dE.as<sgb_envelope>(), dR.as<sgb_formant_ref>(), dF.as<double>(),
-                        dA.as<double>(), nullptr, dO.as<double>(), 0);
+                        nullptr, dT.as<double>(), dM.as<double>(), nullptr, dO.as<double>(), 0);
     CK(cudaGetLastError());
     CK(cudaMemcpy(out, dO.p, 8 * (size_t)nr * nc, cudaMemcpyDeviceToHost));
     return SGB_OK;
   };
   int rc = run();
-  dE.release(); dR.release(); dF.release(); dA.release(); dI.release(); dO.release();
+  dE.release(); dR.release(); dF.release(); dA.release(); dI.release(); dO.release(); dT.release(); dM.release();
   return rc;
 }
 

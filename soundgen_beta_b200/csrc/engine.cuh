@@ -93,7 +93,8 @@ struct EnvInst {
   int32_t env_id;
   int32_t nr;
   int32_t nc;
-  int32_t col0;         // first column of this instance in the flat (instance, column) work list; -1: 2-D grid
+  int32_t col0;         // first column of this instance in the flat (instance, column) work list
+  int64_t trk_off;      // doubles into the formant-track scratch (nc x F x 3), -1: formants do not move
 };
 
 

@@ -269,27 +269,18 @@ k_compose(const sgb_syllable *__restrict__ syl, int S, SylCtrl *__restrict__ ctr
 
   // ---- amplitude envelope (source.R:436-448) ----
   if (C.use_ampl) {
-    const double *an = anchors + 2 * sp.ampl_off;
-    const int n = sp.ampl_n;
-    __shared__ double tx[SGB_MAX_RW_KNOTS], vy[SGB_MAX_RW_KNOTS], cb[SGB_MAX_RW_KNOTS],
-        cc[SGB_MAX_RW_KNOTS], cd[SGB_MAX_RW_KNOTS];
-    if (threadIdx.x == 0) {
-      double tmin = an[0], tmax = an[0];
-      for (int i = 1; i < n; i++) { tmin = fmin(tmin, an[2 * i]); tmax = fmax(tmax, an[2 * i]); }
-      for (int i = 0; i < n; i++) {
-        double v = an[2 * i + 1];
-        if (v < 0.0) v = 0.0;
-        vy[i] = v;
-        tx[i] = (an[2 * i] - tmin) / (tmax - tmin);
-      }
-      if (n >= 3) fmm_coef(n, tx, vy, cb, cc, cd);
-    }
+    // getSmoothContour(amplAnchors, len = length(waveform), valueFloor = 0, samplingRate): no ceiling
+    __shared__ ContourTab T;
+    if (threadIdx.x == 0)
+      contour_prepare(&T, anchors + 2 * sp.ampl_off, sp.ampl_n, Lc, sp.samplingRate, true, 0.0, false, 0.0, false,
+                      sp.ampl_method);
     __syncthreads();
+    if (T.status != SGB_OK) {
+      if (threadIdx.x == 0) { C.status = T.status; C.out_len = 0; C.raw_max = 1.0; }
+      return;
+    }
     for (int k = threadIdx.x; k < Lc; k += blockDim.x) {
-      double v;
-      if (n == 1) v = vy[0];
-      else if (n == 2) v = r_seq_at(vy[0], vy[1], Lc, k);
-      else { v = r_spline_at(n, tx, vy, cb, cc, cd, Lc, k); if (v < 0.0) v = 0.0; }
+      double v = contour_eval(&T, Lc, k);
       comp[k] = (float)((double)comp[k] * exp2(v / 10.0));
     }
     __syncthreads();

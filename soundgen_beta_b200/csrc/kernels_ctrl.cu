@@ -24,8 +24,27 @@ k_control(const sgb_syllable *syl, int S, const double *pitch, const double *anc
     return;
   }
   SylArrays A = make_arrays(P, sp, s);
-  const double *pin = pitch + sp.pitch_off;
-  for (int i = threadIdx.x; i < sp.pitch_len; i += blockDim.x) A.pitch[i] = ctrl_vibrato(sp, i + 1, pin[i]);
+  if (sp.pitch_anchor_n > 0) {
+    // pitchContour_syl = getSmoothContour(pitchAnchors, len, samplingRate = pitchSamplingRate, pitchFloor,
+    //                                     pitchCeiling, thisIsPitch = TRUE) * pitchDeltas[s]  (soundgen.R:596-603)
+    __shared__ ContourTab T;
+    if (threadIdx.x == 0)
+      contour_prepare(&T, anchors + 2 * sp.pitch_anchor_off, sp.pitch_anchor_n, sp.pitch_len, sp.pitchSamplingRate,
+                      true, sp.pitchFloor, true, sp.pitchCeiling, true, sp.pitch_method);
+    __syncthreads();
+    if (T.status != SGB_OK) {
+      if (threadIdx.x == 0) {
+        C.status = T.status; C.nGC = 0; C.nEpochs = 0; C.tiles = 0; C.amp_elems = 0; C.wave_elems = 0; C.n_up = 0;
+        C.rows_kept = 0; C.nHarmonics = 0; C.n_jidx = 0; C.z_used = 0; C.use_ampl = 0; C.out_len = 0; C.raw_max = 1.0;
+      }
+      return;
+    }
+    for (int i = threadIdx.x; i < sp.pitch_len; i += blockDim.x)
+      A.pitch[i] = ctrl_vibrato(sp, i + 1, contour_eval(&T, sp.pitch_len, i) * sp.pitch_scale);
+  } else {
+    const double *pin = pitch + sp.pitch_off;
+    for (int i = threadIdx.x; i < sp.pitch_len; i += blockDim.x) A.pitch[i] = ctrl_vibrato(sp, i + 1, pin[i]);
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     ctrl_sequential(sp, anchors, z, A, C);

@@ -7,15 +7,16 @@
 
 #define ENV_THREADS 128
 #define ENV_WARPS (ENV_THREADS / 32)
-#define ENV_MAXF 32        // formants per filter (incl. nasal pole / zero)
+#define ENV_MAXF 64        // formants per filter (incl. stochastic extras and the nasal pole / zero)
 #define ENV_MAXK 64        // knots after the approx() pre-smoothing
 
 template <typename OutT>
 __global__ void __launch_bounds__(ENV_THREADS, 6)
 k_envelope(const EnvInst *__restrict__ inst, const sgb_envelope *__restrict__ envs,
            const sgb_formant_ref *__restrict__ fidx, const double *__restrict__ formants,
-           const double *__restrict__ anchors, const double *__restrict__ pre, OutT *__restrict__ out,
-           int n_flat, int n_items) {
+           const double *__restrict__ formants_late, const double *__restrict__ trk,
+           const double *__restrict__ mouth, const double *__restrict__ pre,
+           OutT *__restrict__ out, int n_flat, int n_items) {
   // work item -> (instance, column): flat list (one item per warp; the instance is found by bisection
   // over col0) or the plain 2-D grid of the stand-alone API call (blockIdx.y = instance)
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -48,34 +49,22 @@ k_envelope(const EnvInst *__restrict__ inst, const sgb_envelope *__restrict__ en
   __shared__ double s_mouth_open[ENV_WARPS], s_mouth_bin[ENV_WARPS];
   double *f_freq = sf_freq[wid], *f_amp = sf_amp[wid], *f_width = sf_width[wid];
   double *g_shape = sg_shape[wid], *g_rate = sg_rate[wid], *g_ref = sg_ref[wid], *g_amp = sg_amp[wid];
-  const int F = min(E.n_formants, ENV_MAXF - 2);
+  const int F = E.n_formants;     // <= ENV_MAXF - 2, checked at upload
 
   // ---- formant values at column c (sourceSpectrum.R:321-344) ----
-  if (lane < F) {
-    const sgb_formant_ref R = fidx[E.formant_off + lane];
-    const double *rows = formants + 4 * R.off;
+  for (int fl = lane; fl < F; fl += 32) {
+    const sgb_formant_ref R = fidx[E.formant_off + fl];
+    const double *rows = (R.pad ? formants_late : formants) + 4 * R.off;
     double val[3];
     if (E.tracks_given) {
       for (int j = 0; j < 3; j++) val[j] = rows[4 * c + 1 + j];
     } else if (R.n <= 1) {
       for (int j = 0; j < 3; j++) val[j] = rows[1 + j];
-    } else {
-      int nPoints = 0;
-      for (int f = 0; f < F; f++) nPoints = max(nPoints, fidx[E.formant_off + f].n);
-      int na = (int)ceil((double)nPoints + exp2(E.smoothLinearFactor));
-      if (na > ENV_MAXK) na = ENV_MAXK;
-      int n = min(R.n, ENV_MAXK);
-      double tx[ENV_MAXK], ty[ENV_MAXK], ax[ENV_MAXK], ay[ENV_MAXK], b[ENV_MAXK], cc[ENV_MAXK], d[ENV_MAXK];
-      for (int i = 0; i < n; i++) tx[i] = rows[4 * i];
-      for (int i = 0; i < na; i++) ax[i] = (double)(i + 1);
-      for (int j = 0; j < 3; j++) {
-        for (int i = 0; i < n; i++) ty[i] = rows[4 * i + 1 + j];
-        for (int i = 0; i < na; i++) ay[i] = r_approx_at(n, tx, ty, na, i);   // approx(y, n = na, x = time)
-        fmm_coef(na, ax, ay, b, cc, d);
-        val[j] = r_spline_at(na, ax, ay, b, cc, d, nc, c);                     // spline(., n = nc)
-      }
+    } else {   // moving formant: evaluated once per instance by k_env_tracks
+      const double *tv = trk + I.trk_off + ((int64_t)c * E.n_formants + fl) * 3;
+      for (int j = 0; j < 3; j++) val[j] = tv[j];
     }
-    f_freq[lane] = val[0]; f_amp[lane] = val[1]; f_width[lane] = val[2];
+    f_freq[fl] = val[0]; f_amp[fl] = val[1]; f_width[fl] = val[2];
   }
   __syncwarp();
 
@@ -86,7 +75,7 @@ k_envelope(const EnvInst *__restrict__ inst, const sgb_envelope *__restrict__ en
     if (F > 0) {
       const double bin_width = E.samplingRate / 2.0 / (double)nr;
       if (E.mouth_n > 0) {
-        mo = contour_at(anchors + 2 * E.mouth_off, E.mouth_n, nc, c, 0.0, 1.0);
+        mo = mouth[I.col0 + c];
         if (mo < E.mouthOpenThres) mo = 0.0;
         mb = (mo > 0.0) ? 1.0 : 0.0;
       }
@@ -165,18 +154,69 @@ k_envelope(const EnvInst *__restrict__ inst, const sgb_envelope *__restrict__ en
   }
 }
 
+// Pre-pass, one CTA per envelope instance: the formant tracks (sourceSpectrum.R:321-344:
+// spline(approx(y, n = nPoints + 2^smoothLinearFactor, x = time)$y, n = nc)) and the mouth-opening
+// contour (:436-443) depend on the column only through the evaluation point, so their coefficients
+// are solved once per instance here and k_envelope just reads the per-column values.
+__global__ void __launch_bounds__(ENV_THREADS)
+k_env_tracks(const EnvInst *__restrict__ inst, const sgb_envelope *__restrict__ envs,
+             const sgb_formant_ref *__restrict__ fidx, const double *__restrict__ formants,
+             const double *__restrict__ anchors, double *__restrict__ trk, double *__restrict__ mouth) {
+  const EnvInst I = inst[blockIdx.x];
+  const sgb_envelope E = envs[I.env_id];
+  const int nc = I.nc, F = E.n_formants;
+  __shared__ ContourTab T;
+  if (E.mouth_n > 0 && F > 0 && E.tracks_given != 2) {
+    if (threadIdx.x == 0) {
+      // getSmoothContour(len = nc, mouthAnchors, valueFloor = 0, valueCeiling = 1): samplingRate is
+      // not passed, so the span heuristic sees getSmoothContour's own default of 16000
+      contour_prepare(&T, anchors + 2 * E.mouth_off, E.mouth_n, nc, 16000.0, true, 0.0, true, 1.0, false,
+                      E.mouth_method);     // a failing fit is reported by the host (contour_fits)
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < nc; c += blockDim.x) mouth[I.col0 + c] = (T.status == SGB_OK) ? contour_eval(&T, nc, c) : 0.5;
+  }
+  if (I.trk_off < 0 || E.tracks_given) return;
+  int nPoints = 0;
+  for (int f = 0; f < F; f++) nPoints = max(nPoints, fidx[E.formant_off + f].n);
+  const int na = (int)ceil((double)nPoints + exp2(E.smoothLinearFactor));
+  for (int t = threadIdx.x; t < 3 * F; t += blockDim.x) {
+    const int f = t / 3, j = t % 3;
+    const sgb_formant_ref R = fidx[E.formant_off + f];
+    const double *rows = formants + 4 * R.off;
+    double *dst = trk + I.trk_off + (int64_t)f * 3 + j;
+    if (R.n <= 1) {
+      for (int c = 0; c < nc; c++) dst[(int64_t)c * F * 3] = rows[1 + j];
+      continue;
+    }
+    double tx[ENV_MAXK], ty[ENV_MAXK], ax[ENV_MAXK], ay[ENV_MAXK], b[ENV_MAXK], cc[ENV_MAXK], d[ENV_MAXK];
+    const int n = R.n;                                   // n, na <= ENV_MAXK, checked at upload
+    for (int i = 0; i < n; i++) { tx[i] = rows[4 * i]; ty[i] = rows[4 * i + 1 + j]; }
+    for (int i = 0; i < na; i++) { ax[i] = (double)(i + 1); ay[i] = r_approx_at(n, tx, ty, na, i); }
+    fmm_coef(na, ax, ay, b, cc, d);
+    for (int c = 0; c < nc; c++) dst[(int64_t)c * F * 3] = r_spline_at(na, ax, ay, b, cc, d, nc, c);
+  }
+}
+
+void launch_env_tracks(const EnvInst *inst, int n_inst, const sgb_envelope *envs, const sgb_formant_ref *fidx,
+                       const double *formants, const double *anchors, double *trk, double *mouth,
+                       cudaStream_t st) {
+  if (n_inst <= 0) return;
+  k_env_tracks<<<n_inst, ENV_THREADS, 0, st>>>(inst, envs, fidx, formants, anchors, trk, mouth);
+}
+
 void launch_envelope_f32(const EnvInst *inst, int n_inst, int max_nc, const sgb_envelope *envs,
-                         const sgb_formant_ref *fidx, const double *formants, const double *anchors,
-                         const double *pre, float *out, cudaStream_t st) {
+                         const sgb_formant_ref *fidx, const double *formants, const double *formants_late,
+                         const double *trk, const double *mouth, const double *pre, float *out, cudaStream_t st) {
   if (n_inst <= 0 || max_nc <= 0) return;
   // max_nc carries the TOTAL number of (instance, column) work items here: one warp each
-  k_envelope<float><<<(max_nc + ENV_WARPS - 1) / ENV_WARPS, ENV_THREADS, 0, st>>>(inst, envs, fidx, formants, anchors, pre,
+  k_envelope<float><<<(max_nc + ENV_WARPS - 1) / ENV_WARPS, ENV_THREADS, 0, st>>>(inst, envs, fidx, formants, formants_late, trk, mouth, pre,
                                                                            out, n_inst, max_nc);
 }
 void launch_envelope_f64(const EnvInst *inst, int n_inst, int max_nc, const sgb_envelope *envs,
-                         const sgb_formant_ref *fidx, const double *formants, const double *anchors,
-                         const double *pre, double *out, cudaStream_t st) {
+                         const sgb_formant_ref *fidx, const double *formants, const double *formants_late,
+                         const double *trk, const double *mouth, const double *pre, double *out, cudaStream_t st) {
   if (n_inst <= 0 || max_nc <= 0) return;
   dim3 g((max_nc + ENV_WARPS - 1) / ENV_WARPS, n_inst);
-  k_envelope<double><<<g, ENV_THREADS, 0, st>>>(inst, envs, fidx, formants, anchors, pre, out, 0, 0);
+  k_envelope<double><<<g, ENV_THREADS, 0, st>>>(inst, envs, fidx, formants, formants_late, trk, mouth, pre, out, 0, 0);
 }

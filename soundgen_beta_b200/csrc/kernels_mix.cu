@@ -20,10 +20,16 @@ k_noise_final(const sgb_noise *__restrict__ noises, const NoiseLayout *__restric
   int lf = (int)floor(N.attackLen * N.samplingRate / 1000.0);
   if (lf < 2) lf = 0;
   if (lf > L) lf = L;
-  const double *an = anchors + 2 * N.anchor_off;
+  // breathingStrength = getSmoothContour(len, noiseAnchors, floor -120, ceiling 40, samplingRate)
+  __shared__ ContourTab T;
+  if (N.strength_pre_off < 0) {
+    if (threadIdx.x == 0)
+      contour_prepare(&T, anchors + 2 * N.anchor_off, N.anchor_n, L, N.samplingRate, true, -120.0, true, 40.0,
+                      false, N.anchor_method);
+    __syncthreads();
+  }
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < L; k += gridDim.x * blockDim.x) {
-    double c = (N.strength_pre_off >= 0) ? pre[N.strength_pre_off + k]
-                                         : contour_at(an, N.anchor_n, L, k, -120.0, 40.0);
+    double c = (N.strength_pre_off >= 0) ? pre[N.strength_pre_off + k] : contour_eval(&T, L, k);
     double v = (double)src[k] / (double)mx * exp2(c / 10.0);
     if (lf > 0) {
       if (k < lf) v = v * r_seq_at(0.0, 1.0, lf, k);
@@ -47,10 +53,17 @@ k_sound_mix(const sgb_bout *__restrict__ bouts, const BoutLayout *__restrict__ b
   const BoutLayout L = bl[b];
   float *snd = sound + L.sound_off;
   const bool has_env = (B.aglobal_n > 0);
-  const double *an = anchors + 2 * B.aglobal_off;
   bool any_noise = false;
   for (int n = B.noise_begin; n < B.noise_end; n++) if (noises[n].mix == 0) any_noise = true;
   if (!any_noise && !has_env) return;
+  // amplEnvelope = getSmoothContour(amplAnchorsGlobal, len = length(sound), 0, -throwaway, samplingRate)
+  __shared__ ContourTab T;
+  if (has_env) {
+    if (threadIdx.x == 0)
+      contour_prepare(&T, anchors + 2 * B.aglobal_off, B.aglobal_n, L.sound_len, B.samplingRate, true, 0.0, true,
+                      -B.throwaway, false, B.aglobal_method);
+    __syncthreads();
+  }
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < L.sound_len; k += gridDim.x * blockDim.x) {
     float v = snd[k];
     for (int n = B.noise_begin; n < B.noise_end; n++) {
@@ -59,7 +72,7 @@ k_sound_mix(const sgb_bout *__restrict__ bouts, const BoutLayout *__restrict__ b
       if (rel >= 0 && rel < noises[n].len) v = v + noise_fin[nl[n].raw_off + rel];
     }
     if (has_env) {
-      double e = contour_at(an, B.aglobal_n, L.sound_len, k, 0.0, -B.throwaway);
+      double e = contour_eval(&T, L.sound_len, k);
       v = (float)((double)v * e);
     }
     snd[k] = v;

@@ -1,9 +1,10 @@
 """Synthetic, seeded parameter sets for the BASELINE.json configs.
 
-Each generator returns a list of keyword dicts for `soundgen()` / `BatchBuilder.add_soundgen`;
-the host-drawn random buffers ride along as `z` (list of normal streams, one per voiced
-syllable) and `u` (list of uniform buffers, one per noise segment).  numpy PCG64,
-seed = 20260000 + cfg (+ rank offset), so every run of a config sees the same sounds.
+Each generator returns a list of keyword dicts for `soundgen()` / `BatchBuilder.add_soundgen`.
+cfg1-3 (temperature 0): host-drawn random buffers ride along as `z` (list of normal streams, one per
+voiced syllable) and `u` (list of uniform buffers, one per noise segment), numpy PCG64 with
+seed = 20260000 + cfg (+ rank offset).  cfg0 and cfg4 carry `seed`: the call draws everything from R's
+own stream after set.seed(seed), as the reference would.
 """
 from __future__ import annotations
 
@@ -40,10 +41,10 @@ def noise_uniform_count(length, wl, overlap=75):
     return (wl // 2) * host.seq_by_count(1.0, float(length) + wl, h)
 
 
-def config0():
-    """soundgen() defaults with one 1000 ms syllable at 16 kHz; the 4 default pitch anchors use
-    loess in R, so the in-container variant uses the 2-anchor call of SURVEY.md Appendix B."""
-    return [dict(sylLen=1000, pitchAnchors=[100, 150], temperature=0, addSilence=100)]
+def config0(n=1, seed=1):
+    """The literal reference call `set.seed(k); soundgen(sylLen = 1000)`: every default, i.e. the
+    4-anchor loess pitch contour, temperature 0.025, vowel 'a' formants, 16 kHz."""
+    return [dict(sylLen=1000, seed=seed + i) for i in range(n)]
 
 
 def config1(n=1024, seed=20260001):
@@ -98,28 +99,18 @@ def config3(n=8192, seed=20260003):
     return out
 
 
-def config4(n=65536, seed=20260004):
-    """datagen sweep: call i uses preset (i mod 33) in the order of R/presets.R.  In the reference each
-    call runs with its preset's own temperature under set.seed(i); that host-side stochastic stage needs
-    R's RNG, so here temperature = 0 and the anchors with 3-10 points are evaluated with the FMM spline
-    instead of loess (contour_method='spline').  What still varies from call to call are the random
-    streams (jitter / shimmer normals, noise uniforms), drawn per call from PCG64(seed + i)."""
+def config4(n=65536, seed=0):
+    """datagen sweep: call i = `set.seed(seed + i); eval(parse(text = preset[i mod 33]))` in the order of
+    R/presets.R:156-410, each preset with its own temperature, loess contours, stochastic formants."""
     from . import presets
     ps = presets.load()
     out = []
     for i in range(n):
         _, _, kw = ps[i % len(ps)]
         kw = dict(kw)
-        kw.update(temperature=0, contour_method='spline', seed=seed + i)
+        kw.update(seed=seed + i)
         out.append(kw)
     return out
-
-
-def streams(seed, dtype=np.float64):
-    """(z, u) callables for soundgen(): independent PCG64 streams of normals and uniforms."""
-    rz = np.random.default_rng([seed, 1])
-    ru = np.random.default_rng([seed, 2])
-    return (lambda n: rz.standard_normal(n)), (lambda n: ru.random(n).astype(dtype, copy=False))
 
 
 CONFIGS = {0: config0, 1: config1, 2: config2, 3: config3, 4: config4}
@@ -127,5 +118,5 @@ NAMES = {0: 'cfg0 soundgen() defaults, 1 x 1000 ms @ 16 kHz',
          1: 'cfg1 voiced batch, 1024 x 500 ms @ 44.1 kHz',
          2: 'cfg2 noise-heavy batch, 4096 x 2 s @ 22.05 kHz',
          3: 'cfg3 harmonic-rich batch, 8192 x 1 s @ 48 kHz',
-         4: 'cfg4 datagen sweep over the 33 bundled presets (temperature 0, spline contours)'}
+         4: 'cfg4 datagen sweep over the 33 bundled presets, set.seed(i) each'}
 SAMPLING_RATE = {0: 16000, 1: 44100, 2: 22050, 3: 48000, 4: None}   # cfg4: per call

@@ -17,7 +17,7 @@ def test_exports_match_header(built_lib):
     assert declared == set(_abi.EXPORTS), declared ^ set(_abi.EXPORTS)
     for name in declared:
         assert hasattr(built_lib, name), name
-    assert built_lib.sgb_version() == 100
+    assert built_lib.sgb_version() == 200
 
 
 def test_struct_layouts_match(built_lib):

