@@ -116,6 +116,11 @@ class Loess1D:
             if s[j] > tol:
                 coef += (U[:, j] @ eta) / s[j] * Vt[j]
         coef = coef / nrm
+        # a fit through an anchor whose value is exactly 0 is rounding noise of either sign (in R's LINPACK
+        # too) and sourceSpectrum.R:443 asks `mouthOpening > 0` of it: noise below 64 eps of the data scale
+        # is taken as the exact zero it stands for
+        if abs(coef[0]) <= 64 * np.finfo(np.float64).eps * np.max(np.abs(self.y)):
+            coef[0] = 0.0
         return float(coef[0]), float(coef[1])
 
     def ok(self):

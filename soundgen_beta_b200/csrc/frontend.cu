@@ -218,7 +218,9 @@ struct Round {
   std::vector<int> sub_call;        // sub-call -> original call
   std::vector<int> syl_z_drawn;     // normals handed to each syllable (exact count in rng modes 0 / 1)
   std::vector<int> syl_call;
+  int64_t virt_pitch = 0;           // doubles of device-evaluated pitch contours (work pool only)
   void clear() {
+    virt_pitch = 0;
     calls.clear(); bouts.clear(); syls.clear(); noises.clear(); envs.clear(); frefs.clear(); pitch.clear();
     anchors.clear(); formants.clear(); z.clear(); pre.clear(); u64.clear(); u32.clear(); sub_call.clear();
     syl_z_drawn.clear(); syl_call.clear();
@@ -730,8 +732,9 @@ bool emit_bout(sgb_frontend *fe, int ci, int b) {
           for (int i = 0; i < zdrawn; i++) R.z.push_back(g.norm_rand());
         }
       } else {
-        y.pitch_anchor_n = npa;           // evaluated on the device; the pitch pool keeps only the offset space
-        R.pitch.resize(R.pitch.size() + y.pitch_len, 0.0);
+        y.pitch_anchor_n = npa;           // evaluated on the device: its slot lies behind the host pool in the
+        y.pitch_off = -1 - R.virt_pitch;  // device's work pool (offset fixed up once the host pool is complete)
+        R.virt_pitch += y.pitch_len;
       }
       if (!C.use_rng) {
         if (C.zi < C.zbuf.size()) {
@@ -867,6 +870,8 @@ int sgb_frontend_round_begin(sgb_frontend *fe, sgb_batch_desc *D, int32_t *n_sub
     R.calls.push_back(cl);
     R.sub_call.push_back(ci);
   }
+  for (auto &y : R.syls)
+    if (y.kind == 1 && y.pitch_off < 0) y.pitch_off = (int64_t)R.pitch.size() + (-1 - y.pitch_off);
   *n_subcalls = (int)R.calls.size();
   memset(D, 0, sizeof *D);
   if (R.calls.empty()) return SGB_OK;

@@ -105,6 +105,12 @@ SGB_HD void loess_local(int n, const double *x, const double *y, int q, double s
   loess_minnorm3(q, b, eta, coef);
   *val = coef[0] / nrm[0];
   *slope = coef[1] / nrm[1];
+  // A fit through an anchor whose value is exactly 0 comes out as rounding noise of either sign (in R's
+  // LINPACK as well), and getSpectralEnvelope asks `mouthOpening > 0` of it (sourceSpectrum.R:443): noise
+  // below 64 eps of the data scale is taken as the exact zero it stands for.
+  double ymax = 0.0;
+  for (int i = 0; i < n; i++) ymax = fmax(ymax, fabs(y[i]));
+  if (fabs(*val) <= 64.0 * 2.220446049250313e-16 * ymax) *val = 0.0;
 }
 
 // x ascending and distinct, n <= LOESS_MAXP

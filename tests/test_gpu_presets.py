@@ -27,15 +27,24 @@ def oracle_call(kw):
 def test_all_presets_match_the_oracle():
     calls = workloads.config4(n=33)
     outs, st = sg.soundgen_batch(calls, out_dtype=np.float64)
-    assert np.all(st == 0), st
-    worst = 0.0
-    for (spk, name, _), kw, y in zip(presets.load(), calls, outs):
+    worst, odd = 0.0, []
+    for (spk, name, _), kw, y, s1 in zip(presets.load(), calls, outs, st):
+        if s1 == -3:
+            # A wiggled syllable shorter than two windows: soundgen.R:743 clamps the window to floor(length / 2),
+            # and an ODD window is reported as unsupported (seewave's istft rebuilds a spectrum of wl - 1 points
+            # there and recycles it against a window of wl points).  The oracle stops at the same place.
+            with pytest.raises(ValueError):
+                oracle_call(kw)
+            odd.append(name)
+            continue
+        assert s1 == 0, (spk, name, s1)
         ref = oracle_call(kw)
         assert y.size == ref.size, (spk, name, y.size, ref.size)
         err = float(np.max(np.abs(y - ref)) / np.max(np.abs(ref)))
         worst = max(worst, err)
         assert err < TOL, (spk, name, err)
-    print('worst preset error %.2e of peak' % worst)
+    assert len(odd) <= 2, odd          # Duck: 110 ms syllables against a 50 ms window
+    print('worst preset error %.2e of peak; odd clamped windows: %s' % (worst, odd))
 
 
 def test_presets_at_temperature_zero_with_spline_contours():
@@ -52,7 +61,7 @@ def test_ragged_batch_of_unrelated_calls():
     """One batch mixing sampling rates, window lengths, voiced / unvoiced / multi-bout calls, host-drawn and
     caller-drawn streams: every call must come out as if it had been run alone (the oracle runs them one by one)."""
     ps = {(s, n): kw for s, n, kw in presets.load()}
-    picks = [('Cat', 'Hiss'), ('Misc', 'Seagull'), ('M1', 'Sigh'), ('Cat', 'Purr'), ('Misc', 'Duck')]
+    picks = [('Cat', 'Hiss'), ('Misc', 'Seagull'), ('M1', 'Sigh'), ('Cat', 'Purr'), ('Cat', 'Scream')]   # Scream: 2 bouts, 2 rounds
     calls = [dict(ps[p], seed=900 + i) for i, p in enumerate(picks)]
     calls += workloads.config1(n=2) + workloads.config3(n=1) + workloads.config0()
     outs, st = sg.soundgen_batch(calls, out_dtype=np.float64)

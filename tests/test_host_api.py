@@ -39,7 +39,9 @@ def test_builder_layout():
     assert b0.lead_silence == 1600 and b0.tail_silence == 0 and b1.lead_silence == 1600 and b1.tail_silence == 1600
     assert t['syls'][0].pause_after == 1616 and t['syls'][2].pause_after == 0   # gap = pauseLen + 1 ms (utilities_soundgen.R:546-549)
     assert t['noises'][0].len == 4800 and t['noises'][0].insertion == 1 - 800   # 50 ms pre-aspiration (soundgen.R:522-528)
-    assert d.n_calls == 1 and d.n_pitch == 6 * 700
+    # no draw count depends on the pitch contour here: it is evaluated on the device from the two anchors
+    assert d.n_calls == 1 and d.n_pitch == 0 and t['syls'][0].pitch_anchor_n == 2
+    assert [y.pitch_off for y in t['syls']] == [700 * i for i in range(6)] and t['syls'][5].pitch_len == 700
 
 
 def test_range_check_and_unsupported():
