@@ -38,6 +38,7 @@ void launch_envelope_f32(const EnvInst *, int, int, const sgb_envelope *, const 
 void launch_envelope_f64(const EnvInst *, int, int, const sgb_envelope *, const sgb_formant_ref *, const double *,
                          const double *, const double *, const double *, const double *, double *, cudaStream_t);
 size_t stft_smem_bytes(int n, double h_in, double h_out, int mode);
+size_t stft_smem_bytes_spec(int n, double h_in, double h_out, int mode, int spec);
 cudaError_t launch_stft(int mode, int u_is_float, int spec, const FftSeg *, int, const FftJob *, const FftPlan *,
                         const float2 *, const float *, const float *, const void *, const float *, float *, int *,
                         size_t, cudaStream_t);
@@ -634,7 +635,7 @@ struct PlanTable {
 struct SegGroup { int spec, begin, end; size_t smem; };
 static void make_segs(const std::vector<FftJob> &jobs, const std::vector<FftPlan> &plans, int mode,
                       std::vector<FftSeg> &segs, std::vector<SegGroup> &groups) {
-  const int target = 2 * 148;
+  const int target = 4 * 148;
   int per_job = 1;
   if ((int)jobs.size() < target && !jobs.empty()) per_job = (target + (int)jobs.size() - 1) / (int)jobs.size();
   std::vector<int> spec_of(plans.size());
@@ -644,7 +645,7 @@ static void make_segs(const std::vector<FftJob> &jobs, const std::vector<FftPlan
     for (int j = 0; j < (int)jobs.size(); j++) {
       if (spec_of[jobs[j].plan] != sp) continue;
       const FftPlan &pl = plans[jobs[j].plan];
-      gr.smem = std::max(gr.smem, stft_smem_bytes(pl.n, pl.h_in, pl.h_out, mode));
+      gr.smem = std::max(gr.smem, stft_smem_bytes_spec(pl.n, pl.h_in, pl.h_out, mode, sp));
       int nc = jobs[j].nc;
       int nseg = std::max(1, std::min(per_job, nc / 8));
       int fr = (nc + nseg - 1) / nseg;
@@ -1503,7 +1504,7 @@ int sgb_filter(const double *sound, int64_t len, const double *envelope, int32_t
     k_fill_int<<<1, 32>>>(dMax.as<int>(), 4, ORDERED_NEG_INF);
     CK(launch_stft(0, 0, groups[0].spec, dSg.as<FftSeg>(), (int)segs.size(), dJ.as<FftJob>(), dPl.as<FftPlan>(),
                    dTw.as<float2>(), dWin.as<float>(), dS.as<float>(), nullptr, dE.as<float>(), dO.as<float>(),
-                   dMax.as<int>(), smem, 0));
+                   dMax.as<int>(), groups[0].smem, 0));
     CK(cudaDeviceSynchronize());
     int mi;
     CK(cudaMemcpy(&mi, dMax.p, 4, cudaMemcpyDeviceToHost));
