@@ -82,6 +82,118 @@ class ClockSampler(threading.Thread):
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
+def find_r():
+    """Rscript with the reference package installed (baseline/_ref as an R library, or the site library)?
+    Returns (rscript, lib) or None.  Probed at run time: the build image has no R, a GPU box may."""
+    import shutil
+    rs = shutil.which('Rscript')
+    if not rs:
+        return None
+    lib = os.path.join(ROOT, 'baseline', '_ref')
+    code = ('.libPaths(c("%s", .libPaths())); suppressMessages(library(soundgen)); cat(R.version.string)' % lib)
+    try:
+        out = subprocess.run([rs, '-e', code], capture_output=True, text=True, timeout=120)
+        if out.returncode == 0 and 'R version' in out.stdout:
+            return rs, lib, out.stdout.strip()
+    except Exception:
+        pass
+    return None
+
+
+def r_value(v):
+    if v is None:
+        return 'NA'
+    if isinstance(v, str):
+        return "'%s'" % v
+    if isinstance(v, (tuple, list)) and len(v) == 2 and np.ndim(v[0]) == 1 and np.ndim(v[1]) == 1 and not np.isscalar(v[0]):
+        return 'list(time = c(%s), value = c(%s))' % (', '.join(repr(float(x)) for x in v[0]),
+                                                       ', '.join(repr(float(x)) for x in v[1]))
+    if isinstance(v, (list, tuple)) and len(v) and np.ndim(v[0]) == 2:      # formants: list of (k, 4) arrays
+        fs = []
+        for i, f in enumerate(v):
+            f = np.asarray(f, dtype=np.float64)
+            cols = ['%s = c(%s)' % (nm, ', '.join(repr(float(x)) for x in f[:, j]))
+                    for j, nm in enumerate(('time', 'freq', 'amp', 'width'))]
+            fs.append('f%d = list(%s)' % (i + 1, ', '.join(cols)))
+        return 'list(%s)' % ', '.join(fs)
+    if np.ndim(v) == 1:
+        return 'c(%s)' % ', '.join(repr(float(x)) for x in v)
+    return repr(float(v)) if not isinstance(v, (bool, np.bool_)) else ('TRUE' if v else 'FALSE')
+
+
+def r_call_string(kw):
+    """The soundgen() call of one workload item as R source (the reference draws its own random numbers)."""
+    kw = {k: v for k, v in kw.items() if k not in ('z', 'u', 'contour_method', 'device_pitch')}
+    seed = kw.pop('seed', None)
+    args = ', '.join('%s = %s' % (k, r_value(v)) for k, v in kw.items())
+    return ('{set.seed(%d); ' % seed if seed is not None else '{') + 'length(soundgen(%s, play = FALSE))}' % args
+
+
+def run_r_reference(rinfo, calls, cores, srs):
+    """Times the reference's own soundgen() over `calls` with mclapply on `cores` cores."""
+    rs, lib, version = rinfo
+    import tempfile
+    src = ['.libPaths(c("%s", .libPaths()))' % lib, 'suppressMessages(library(soundgen))', 'library(parallel)',
+           'calls <- list(' + ',\n'.join('function() %s' % r_call_string(kw) for kw in calls) + ')',
+           't0 <- proc.time()[["elapsed"]]',
+           'n <- unlist(mclapply(calls, function(f) suppressWarnings(f()), mc.cores = %d))' % cores,
+           'cat(proc.time()[["elapsed"]] - t0, paste(n, collapse = " "))']
+    with tempfile.NamedTemporaryFile('w', suffix='.R', delete=False) as f:
+        f.write('\n'.join(src))
+    out = subprocess.run([rs, f.name], capture_output=True, text=True, timeout=1500)
+    if out.returncode != 0:
+        raise RuntimeError(out.stderr[-500:])
+    tok = out.stdout.split()
+    secs = float(tok[0])
+    lens = np.array([float(x) for x in tok[1:]])
+    return float(np.sum(lens / srs[:lens.size])) / secs, version
+
+
+def oracle_arts_partials(arts):
+    """(reference, dense) partial-samples of one call from the oracle's artefacts: rows the reference keeps
+    per epoch (all-zero rows dropped, R/subharmonics.R:83-84) vs the dense rows_kept (n + 1) + n the device sums."""
+    ref = dense = 0
+    for a in arts:
+        gu = a.gc_upsampled
+        for e, (st, en) in enumerate(np.asarray(a.epochs).reshape(-1, 2)):
+            ne = int(gu[en] - gu[st - 1] + 1)
+            n = int(a.nSubharm[st - 1]) if a.nSubharm is not None else 0
+            ref += ne * len(a.epoch_rows[e])
+            dense += ne * (a.rows_kept * (n + 1) + n if n > 0 else a.rows_kept)
+    return ref, dense
+
+
+def parity_sample(calls, outs, idx):
+    """Checks the calls `idx` of the timed batch against the CPU oracle: max |err| / peak, SNR in dB and the
+    ratio dense / reference partial-samples (for the K1 roofline numerator)."""
+    from oracle import soundgen_oracle as so
+    from oracle.soundgen_call import soundgen as osg
+    worst, snr_min, pref, pdense, bad_len = 0.0, float('inf'), 0, 0, 0
+    for i in idx:
+        kw = dict(calls[i])
+        z, u = kw.pop('z', None), kw.pop('u', None)
+        kw.pop('device_pitch', None)
+        if 'seed' in kw:
+            from oracle.rrng import RRng
+            rng = RRng(kw.pop('seed'))
+        else:
+            rng = so.RStream(z=np.concatenate(z) if z else None, u=np.concatenate(u) if u else None)
+        ref, arts, _ = osg(rng=rng, want_artefacts=True, **kw)
+        y = np.asarray(outs[i], dtype=np.float64)
+        if y.size != ref.size:
+            bad_len += 1
+            continue
+        err = y - ref
+        worst = max(worst, float(np.max(np.abs(err)) / np.max(np.abs(ref))))
+        snr_min = min(snr_min, float(10 * np.log10(np.sum(ref ** 2) / max(np.sum(err ** 2), 1e-300))))
+        a, b = oracle_arts_partials(arts)
+        pref += a
+        pdense += b
+    return {'calls_checked': len(idx), 'length_mismatches': bad_len, 'max_err_of_peak': worst,
+            'snr_db_min': snr_min, 'checker': 'numpy restatement of the R reference (parity unpinned: no R here)',
+            'dense_over_reference_partials': (pdense / pref) if pref else None}
+
+
 def oracle_one(kw):
     """One soundgen() call through the CPU oracle; returns (seconds of audio, samples)."""
     from oracle import soundgen_oracle as so
@@ -109,6 +221,27 @@ def run_reference(args, rank, world):
     if args.config == 4:
         per_step = max(per_step, 33)
     calls = workloads.CONFIGS[args.config](n=per_step)
+    rinfo = find_r()
+    if rinfo is not None:
+        try:
+            srs = np.array([float(kw.get('samplingRate', 16000)) for kw in calls])
+            t0 = time.perf_counter()
+            vals = [run_r_reference(rinfo, calls, cores, srs) for _ in range(max(1, args.steps))]
+            dt = time.perf_counter() - t0
+            val = float(np.mean([v for v, _ in vals]))
+            line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus,
+                    'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / max(1, args.steps) * 1e3,
+                    'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+                    'data': 'synthetic', 'gpu_launches': 0,
+                    'config': {'workload': workloads.NAMES[args.config], 'calls_per_step': len(calls)},
+                    'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': 'reference',
+                                     'sample': '%d calls per step through the R package itself (%s), mclapply'
+                                               % (len(calls), vals[0][1])},
+                    'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+            print(json.dumps(line), flush=True)
+            return
+        except Exception as e:      # fall back to the port, saying why
+            print('R reference failed (%s); timing the numpy restatement instead' % str(e)[:200], file=sys.stderr)
     with mp.Pool(cores) as pool:
         for _ in range(args.warmup):
             pool.map(oracle_one, calls[:cores])
@@ -139,6 +272,8 @@ def main():
     ap.add_argument('--config', type=int, default=3)
     ap.add_argument('--batch', type=int, default=0, help='calls per GPU per step (default: the config size)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-parity', action='store_true', help='skip the oracle check of a sample of the timed batch')
+    ap.add_argument('--parity-calls', type=int, default=16)
     ap.add_argument('--pipeline', type=int, default=8,
                     help='sub-batches (handles / CUDA streams) of the end-to-end measurement')
     ap.add_argument('--runners', type=int, default=3,
@@ -180,8 +315,10 @@ def main():
             builder.add_soundgen(**kw)
 
     bb = sg.BatchBuilder(u_dtype=np.float32)   # uniforms travel as float32 (halves the PCIe bytes)
+    t_fe = time.perf_counter()
     add_calls(bb, calls)
     desc = bb.build()
+    fe_ms = (time.perf_counter() - t_fe) * 1e3
     sg.pin_desc(desc)   # page-lock the host pools
     bt = sg.Batch()
     bt.upload(desc)
@@ -259,6 +396,14 @@ def main():
     d2h_bytes = d2h_f32
     clocks = sampler.stop()
     stage_ms /= args.steps
+    # ---- parity of the timed batch itself: a random sample of its calls against the CPU oracle ----
+    parity = None
+    if not args.no_parity and rank == 0:
+        offs = np.concatenate(([0], np.cumsum(lens)))
+        bt.fetch(np.float32, out=out)
+        pick = np.random.default_rng(7).choice(len(calls), size=min(args.parity_calls, len(calls)), replace=False)
+        outs_pick = {int(i): out[offs[i]:offs[i + 1]] for i in pick}
+        parity = parity_sample(calls, outs_pick, [int(i) for i in pick])
 
     dt, dt_e2e, audio_total, dt_wav = sharding.aggregate(dist, dt, dt_e2e, audio_s,
                                                          device='cuda' if dist is not None else None, extra=(dt_wav,))
@@ -281,28 +426,43 @@ def main():
     ms_synth = float(stage_ms[_abi.T_NAMES.index('synth')])
     ms_filter = float(stage_ms[_abi.T_NAMES.index('filter')])
     ms_noise = float(stage_ms[_abi.T_NAMES.index('noise')])
-    traffic = None
+    traffic, traffic_f = None, None
     try:
-        tj = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')))
+        tj = json.load(open(os.path.join(ROOT, 'profiles', 'r02_traffic.json')))
         key = 'cfg%d_%d' % (args.config, len(calls))
         traffic = tj.get(key, {}).get('k_synth', {}).get('dram_bytes_per_launch')
+        traffic_f = tj.get(key, {}).get('k_stft_filter', {}).get('dram_bytes_per_launch')
     except Exception:
         pass
+    # K1's algorithmic work: 6 flop per partial-sample the REFERENCE sums (rows that survive the all-zero
+    # pruning of R/subharmonics.R:83-84).  The device sums dense rows (harmonics and sub-harmonics share one
+    # index, dead rows included); the ratio dense / reference is measured on the parity sample of this batch.
+    nominal_fp32 = 148 * 128 * 2 * 1.965e9 / 1e12          # 74.4 TFLOP/s: SMs x FP32 lanes x FMA x max clock
+    ratio = (parity or {}).get('dense_over_reference_partials') or None
     roofline = None
     if ms_synth > 0 and info.synth_partials > 0:
-        ach = 6.0 * info.synth_partials / (ms_synth * 1e-3) / 1e12
+        dense = 6.0 * info.synth_partials / (ms_synth * 1e-3) / 1e12
+        ach = dense / ratio if ratio else dense
         roofline = {'kernel': 'k_synth', 'bound': 'fp32', 'achieved': ach, 'peak': fp32.value,
                     'unit': 'TFLOP/s', 'frac': ach / fp32.value if fp32.value else None, 'traffic': traffic,
-                    'peak_source': 'measured in this run: sgb_measure_fp32_peak (FFMA2 chains)',
-                    'algorithmic': '6 flop per partial-sample x %d partial-samples per launch' % info.synth_partials}
+                    'peak_source': 'measured in this run: sgb_measure_fp32_peak (FFMA2 dependency chains); '
+                                   'MEASURED_PEAKS.json has no FP32 figure',
+                    'peak_nominal': nominal_fp32, 'frac_of_nominal': ach / nominal_fp32,
+                    'achieved_dense_rows': dense, 'frac_dense_rows': dense / fp32.value if fp32.value else None,
+                    'dense_over_reference_partials': ratio,
+                    'algorithmic': '6 flop per partial-sample x %d dense partial-samples per launch / %s '
+                                   '(dense / reference rows, from the parity sample)'
+                                   % (info.synth_partials, ('%.3f' % ratio) if ratio else 'n/a')}
     hbm = peaks.get('hbm_gbs', 6650.0)
     roof_filter = None
     if ms_filter > 0 and info.filter_samples > 0:
         ach = 8.0 * info.filter_samples / (ms_filter * 1e-3) / 1e9
-        roof_filter = {'kernel': 'k_stft<filter>', 'bound': 'hbm', 'achieved': ach, 'peak': hbm, 'unit': 'GB/s',
-                       'frac': ach / hbm, 'traffic': None,
+        roof_filter = {'kernel': 'k_stft_reg<filter>', 'bound': 'hbm', 'achieved': ach, 'peak': hbm, 'unit': 'GB/s',
+                       'frac': ach / hbm, 'traffic': traffic_f,
                        'peak_source': 'MEASURED_PEAKS.json' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s',
-                       'algorithmic': '8 B per output sample x %d samples per launch' % info.filter_samples}
+                       'algorithmic': '8 B per output sample x %d samples per launch' % info.filter_samples,
+                       'note': 'the kernel is bound by its shared-memory FFT passes, not by HBM: see '
+                               'profiles/r02_ncu_k_stft_summary.txt (shared-memory wavefronts, issue slots)'}
     if roofline is None:
         roofline = roof_filter
 
@@ -315,7 +475,8 @@ def main():
         tc = time.perf_counter() - tc
         cpu = {'value': a / tc, 'unit': UNIT, 'cores': 1, 'kind': 'port',
                'sample': 'first %d calls of the workload, numpy restatement of the R reference '
-                         '(R is not installed on this image)' % len(sample)}
+                         '(Rscript + the soundgen package probed at run time: %s)'
+                         % (len(sample), 'found, see --impl reference' if find_r() else 'not found')}
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3, 'wall_ms_per_step': dt_wall / args.steps * 1e3,
             'timing': 'cuda events on the launching stream, max over ranks', 'higher_is_better': True,
@@ -325,12 +486,15 @@ def main():
                        'uniforms': 'float32'},
             'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': int(bb.h2d_bytes()),
                     'd2h_bytes_per_step': int(d2h_bytes), 'ms_per_step': dt_e2e / args.steps * 1e3,
-                    'pipeline': npipe, 'runners': args.runners, 'cpus_bound': len(numa_cpus)},
+                    'pipeline': npipe, 'runners': args.runners, 'cpus_bound': len(numa_cpus),
+                    'front_end_ms_per_step': fe_ms, 'note': 'timed from prebuilt descriptions; front_end_ms_per_step = '
+                    'the library host front-end (argument lists -> description) for the same batch, one thread'},
             'e2e_wav16': {'value': audio_total * args.steps / dt_wav, 'unit': UNIT, 'ms_per_step': dt_wav / args.steps * 1e3,
                           'd2h_bytes_per_step': int(d2h_i16),
                           'note': 'same pipeline, waveforms fetched as 16-bit PCM (the savePath / WAV format)'},
             'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline,
-            'roofline_filter': roof_filter, 'cpu_baseline': cpu,
+            'roofline_filter': roof_filter, 'cpu_baseline': cpu, 'parity_sample': parity,
+            'parity_sample_max_err': (parity or {}).get('max_err_of_peak'), 'snr_db': (parity or {}).get('snr_db_min'),
             'stage_ms': {nm: float(v) for nm, v in zip(_abi.T_NAMES, stage_ms)},
             'failed_calls': int(info.n_failed)}
     print(json.dumps(line), flush=True)

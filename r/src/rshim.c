@@ -12,6 +12,8 @@
  *   sg_get_rolloff          <- getRolloff               R/sourceSpectrum.R:71-186
  *   sg_get_spectral_envelope<- getSpectralEnvelope      R/sourceSpectrum.R:417-566 (deterministic part)
  *   sg_filter               <- filter block of soundgen R/soundgen.R:743-807 (+ seewave stft/istft)
+ *   sg_soundgen             <- soundgen() itself        R/soundgen.R:279-849 (host stage in the library's
+ *                              front-end, drawing from R's own stream: .Random.seed goes in and comes back)
  *
  * Build: see src/Makevars (links against libsoundgen_b200.so built by __graft_entry__.build()).
  */
@@ -252,12 +254,211 @@ SEXP sg_filter(SEXP sound, SEXP envelope, SEXP wl, SEXP overlap) {
   return out;
 }
 
+/* ---- soundgen() as one call ------------------------------------------------------------------------
+ * args:     named list of the numeric arguments of soundgen() (R/soundgen.R:208-277) and of tempEffects
+ *           (sylLenDep, formDrift, ...); anything missing takes the reference's default.
+ * anchors:  list of 6: pitchAnchors, pitchAnchorsGlobal, noiseAnchors, mouthAnchors, amplAnchors,
+ *           amplAnchorsGlobal -- each NULL (NA) or a numeric matrix with the columns (time, value).
+ * formants, formantsNoise: NULL (NA) or a list of numeric matrices with the columns (time, freq, amp, width).
+ * opts:     named list: invalidArgAction (0 adjust, 1 abort, 2 ignore), contour_method (0 loess, 1 spline),
+ *           sample_rejection (1 under R >= 3.6 with the default sample.kind).
+ * seed:     .Random.seed (integer, 626: kind code, mti, mt[624]) of a Mersenne-Twister / Inversion session.
+ * Returns list(waveform = numeric, seed = integer(626), status = integer, warnings = character). */
+static void anchor_arg(SEXP m, sgb_anchor_arg *a) {
+  memset(a, 0, sizeof *a);
+  if (Rf_isNull(m)) return;
+  int n = Rf_nrows(m);
+  a->time = REAL(m); a->value = REAL(m) + n; a->n = n;       /* column-major: the time column, then the values */
+}
+static sgb_formant_arg *formant_args(SEXP fl, int *n_out) {
+  *n_out = 0;
+  if (Rf_isNull(fl)) return NULL;
+  int nf = (int)XLENGTH(fl);
+  sgb_formant_arg *f = (sgb_formant_arg *)R_alloc((size_t)nf, sizeof(sgb_formant_arg));
+  for (int i = 0; i < nf; i++) {
+    SEXP m = VECTOR_ELT(fl, i);
+    int n = Rf_nrows(m);
+    f[i].time = REAL(m); f[i].freq = REAL(m) + n; f[i].amp = REAL(m) + 2 * (size_t)n; f[i].width = REAL(m) + 3 * (size_t)n;
+    f[i].n_time = f[i].n_freq = f[i].n_amp = f[i].n_width = n;
+  }
+  *n_out = nf;
+  return f;
+}
+
+static void fill_args(SEXP args, SEXP anchors, SEXP formants, SEXP formantsNoise, SEXP opts, sgb_soundgen_args *out) {
+  sgb_soundgen_args a;
+  memset(&a, 0, sizeof a);
+#define A(f, d) a.f = num(args, #f, d)
+  A(repeatBout, 1); A(nSyl, 1); A(sylLen, 300); A(pauseLen, 200); A(temperature, 0.025); A(maleFemale, 0);
+  A(creakyBreathy, 0); A(nonlinBalance, 0); A(nonlinDep, 50); A(jitterLen, 1); A(jitterDep, 3); A(vibratoFreq, 5);
+  A(vibratoDep, 0); A(shimmerDep, 0); A(attackLen, 50); A(rolloff, -12); A(rolloffOct, -12); A(rolloffKHz, -6);
+  A(rolloffParab, 0); A(rolloffParabHarm, 3); A(rolloffLip, 6); A(formantDep, 1); A(formantDepStoch, 30);
+  A(vocalTract, 15.5); A(subFreq, 100); A(subDep, 100); A(shortestEpoch, 300); A(amDep, 0); A(amFreq, 30);
+  A(amShape, 0); A(rolloffNoise, -14); A(samplingRate, 16000); A(windowLength, 50); A(overlap, 75);
+  A(addSilence, 100); A(pitchFloor, 50); A(pitchCeiling, 3500); A(pitchSamplingRate, 3500); A(throwaway, -120);
+#undef A
+  static const char *te[8] = {"sylLenDep", "formDrift", "formDisp", "pitchDriftDep", "pitchDriftFreq",
+                              "pitchAnchorsDep", "noiseAnchorsDep", "amplAnchorsDep"};
+  for (int i = 0; i < 8; i++) a.tempEffects[i] = num(args, te[i], R_NaN);
+  if (XLENGTH(anchors) != 6) Rf_error("soundgen_b200: `anchors` must be a list of 6");
+  sgb_anchor_arg *slots[6] = {&a.pitchAnchors, &a.pitchAnchorsGlobal, &a.noiseAnchors, &a.mouthAnchors,
+                              &a.amplAnchors, &a.amplAnchorsGlobal};
+  for (int i = 0; i < 6; i++) anchor_arg(VECTOR_ELT(anchors, i), slots[i]);
+  a.formants = formant_args(formants, &a.n_formants);
+  a.formantsNoise = formant_args(formantsNoise, &a.n_formantsNoise);
+  a.invalidArgAction = (int)num(opts, "invalidArgAction", 0);
+  a.contour_method = (int)num(opts, "contour_method", 0);
+  a.sample_rejection = (int)num(opts, "sample_rejection", 0);
+  a.device_pitch = 1;
+  *out = a;
+}
+
+SEXP sg_soundgen(SEXP args, SEXP anchors, SEXP formants, SEXP formantsNoise, SEXP opts, SEXP seed) {
+  sgb_soundgen_args a;
+  fill_args(args, anchors, formants, formantsNoise, opts, &a);
+  if (XLENGTH(seed) != 626) Rf_error("soundgen_b200: .Random.seed of a Mersenne-Twister session (626 integers) expected");
+  a.rng_mode = 1;
+  a.rng_state = INTEGER(seed) + 1;
+
+  sgb_frontend *fe = NULL;
+  sgb_batch *b = NULL;
+  int rc = sgb_frontend_create(&fe, 0);
+  if (rc >= 0) rc = sgb_frontend_add(fe, &a);
+  if (rc >= 0) rc = sgb_batch_create(&b);
+  double *wave = NULL;
+  int64_t total = 0;
+  while (rc >= 0) {                       /* one round per bout whose stochastic filter needs the device's frame count */
+    sgb_batch_desc d;
+    int32_t nsub = 0;
+    rc = sgb_frontend_round_begin(fe, &d, &nsub);
+    if (rc < 0 || nsub == 0) break;
+    if ((rc = sgb_batch_upload(b, &d)) < 0) break;
+    if ((rc = sgb_batch_run_begin(b)) < 0) break;
+    if ((rc = sgb_frontend_resolve(fe, b)) < 0) break;
+    if ((rc = sgb_batch_run_finish(b, NULL)) < 0) break;
+    if ((rc = sgb_frontend_round_end(fe, b)) < 0) break;
+    int64_t len = 0;
+    if ((rc = sgb_batch_lengths(b, &len)) < 0) break;
+    double *grown = (double *)R_alloc((size_t)(total + len + 1), sizeof(double));
+    if (total) memcpy(grown, wave, sizeof(double) * (size_t)total);
+    wave = grown;
+    if (len > 0 && (rc = sgb_batch_fetch_f64(b, wave + total, len)) < 0) break;
+    total += len;
+  }
+  int32_t status = 0;
+  int32_t state[625];
+  char warn[1024];
+  warn[0] = 0;
+  if (rc >= 0) {
+    sgb_frontend_status(fe, &status);
+    sgb_frontend_rng_state(fe, 0, state);
+    strncpy(warn, sgb_frontend_warnings(fe, 0), sizeof warn - 1);
+    warn[sizeof warn - 1] = 0;
+  }
+  char msg[512];
+  msg[0] = 0;
+  if (rc < 0) { strncpy(msg, sgb_last_error(), sizeof msg - 1); msg[sizeof msg - 1] = 0; }
+  if (b) sgb_batch_destroy(b);
+  if (fe) sgb_frontend_destroy(fe);
+  if (rc < 0) Rf_error("soundgen_b200: %s", msg);
+  if (status == SGB_ERR_SYNTH) Rf_error("Failed to generate the new syllable!");   /* soundgen.R:624-626 */
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 4));
+  SEXP w = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)total));
+  if (total) memcpy(REAL(w), wave, sizeof(double) * (size_t)total);
+  SEXP sd = PROTECT(Rf_allocVector(INTSXP, 626));
+  INTEGER(sd)[0] = INTEGER(seed)[0];
+  memcpy(INTEGER(sd) + 1, state, sizeof state);
+  SEXP wn = PROTECT(Rf_allocVector(STRSXP, 1));
+  SET_STRING_ELT(wn, 0, Rf_mkChar(warn));
+  SET_VECTOR_ELT(out, 0, w);
+  SET_VECTOR_ELT(out, 1, sd);
+  SET_VECTOR_ELT(out, 2, Rf_ScalarInteger(status));
+  SET_VECTOR_ELT(out, 3, wn);
+  SEXP nm = PROTECT(Rf_allocVector(STRSXP, 4));
+  SET_STRING_ELT(nm, 0, Rf_mkChar("waveform")); SET_STRING_ELT(nm, 1, Rf_mkChar("seed"));
+  SET_STRING_ELT(nm, 2, Rf_mkChar("status")); SET_STRING_ELT(nm, 3, Rf_mkChar("warnings"));
+  Rf_setAttrib(out, R_NamesSymbol, nm);
+  UNPROTECT(5);
+  return out;
+}
+
+/* soundgen_batch(): calls = list of list(args, anchors, formants, formantsNoise) as for sg_soundgen, seeds =
+ * integer vector (call i runs as after set.seed(seeds[i])).  All calls go through the device as ONE batch
+ * (plus one more round per bout whose stochastic filter waits for the device's frame count).
+ * Returns a list of numeric waveforms; a call the reference would stop() on comes back as NULL. */
+SEXP sg_soundgen_batch(SEXP calls, SEXP opts, SEXP seeds) {
+  const int n = (int)XLENGTH(calls);
+  if (XLENGTH(seeds) != n) Rf_error("soundgen_b200: one seed per call expected");
+  sgb_frontend *fe = NULL;
+  sgb_batch *b = NULL;
+  int rc = sgb_frontend_create(&fe, 0);
+  for (int i = 0; i < n && rc >= 0; i++) {
+    SEXP c = VECTOR_ELT(calls, i);
+    sgb_soundgen_args a;
+    fill_args(VECTOR_ELT(c, 0), VECTOR_ELT(c, 1), VECTOR_ELT(c, 2), VECTOR_ELT(c, 3), opts, &a);
+    a.rng_mode = 0;
+    a.seed = (uint32_t)INTEGER(seeds)[i];
+    rc = sgb_frontend_add(fe, &a);
+  }
+  if (rc >= 0) rc = sgb_batch_create(&b);
+  double **part = (double **)R_alloc((size_t)n + 1, sizeof(double *));
+  int64_t *plen = (int64_t *)R_alloc((size_t)n + 1, sizeof(int64_t));
+  for (int i = 0; i < n; i++) { part[i] = NULL; plen[i] = 0; }
+  while (rc >= 0) {
+    sgb_batch_desc d;
+    int32_t nsub = 0;
+    rc = sgb_frontend_round_begin(fe, &d, &nsub);
+    if (rc < 0 || nsub == 0) break;
+    if ((rc = sgb_batch_upload(b, &d)) < 0) break;
+    if ((rc = sgb_batch_run_begin(b)) < 0) break;
+    if ((rc = sgb_frontend_resolve(fe, b)) < 0) break;
+    if ((rc = sgb_batch_run_finish(b, NULL)) < 0) break;
+    if ((rc = sgb_frontend_round_end(fe, b)) < 0) break;
+    int64_t *lens = (int64_t *)R_alloc((size_t)nsub, sizeof(int64_t));
+    int32_t *owner = (int32_t *)R_alloc((size_t)nsub, sizeof(int32_t));
+    if ((rc = sgb_batch_lengths(b, lens)) < 0) break;
+    if ((rc = sgb_frontend_round_calls(fe, owner)) < 0) break;
+    int64_t total = 0;
+    for (int k = 0; k < nsub; k++) total += lens[k];
+    double *all = (double *)R_alloc((size_t)total + 1, sizeof(double));
+    if (total > 0 && (rc = sgb_batch_fetch_f64(b, all, total)) < 0) break;
+    int64_t off = 0;
+    for (int k = 0; k < nsub; k++) {       /* append this round's piece to its call */
+      const int c = owner[k];
+      double *grown = (double *)R_alloc((size_t)(plen[c] + lens[k]) + 1, sizeof(double));
+      if (plen[c]) memcpy(grown, part[c], sizeof(double) * (size_t)plen[c]);
+      memcpy(grown + plen[c], all + off, sizeof(double) * (size_t)lens[k]);
+      part[c] = grown; plen[c] += lens[k]; off += lens[k];
+    }
+  }
+  int32_t *status = (int32_t *)R_alloc((size_t)n + 1, sizeof(int32_t));
+  if (rc >= 0) rc = sgb_frontend_status(fe, status);
+  char msg[512];
+  msg[0] = 0;
+  if (rc < 0) { strncpy(msg, sgb_last_error(), sizeof msg - 1); msg[sizeof msg - 1] = 0; }
+  if (b) sgb_batch_destroy(b);
+  if (fe) sgb_frontend_destroy(fe);
+  if (rc < 0) Rf_error("soundgen_b200: %s", msg);
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, n));
+  for (int i = 0; i < n; i++) {
+    if (status[i] != 0) continue;                       /* stays NULL */
+    SEXP w = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)plen[i]));
+    if (plen[i]) memcpy(REAL(w), part[i], sizeof(double) * (size_t)plen[i]);
+    SET_VECTOR_ELT(out, i, w);
+    UNPROTECT(1);
+  }
+  UNPROTECT(1);
+  return out;
+}
+
 static const R_CallMethodDef call_methods[] = {
     {"sg_generate_harmonics", (DL_FUNC)&sg_generate_harmonics, 4},
     {"sg_generate_noise", (DL_FUNC)&sg_generate_noise, 6},
     {"sg_get_rolloff", (DL_FUNC)&sg_get_rolloff, 11},
     {"sg_get_spectral_envelope", (DL_FUNC)&sg_get_spectral_envelope, 7},
     {"sg_filter", (DL_FUNC)&sg_filter, 4},
+    {"sg_soundgen", (DL_FUNC)&sg_soundgen, 6},
+    {"sg_soundgen_batch", (DL_FUNC)&sg_soundgen_batch, 3},
     {NULL, NULL, 0}};
 
 void R_init_soundgen(DllInfo *dll) {

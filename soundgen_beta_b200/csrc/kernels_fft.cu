@@ -148,7 +148,7 @@ __device__ __forceinline__ void pass_prime(XIn x, float2 *__restrict__ y, int N,
     // forward: X_j = P - i Q, X_{r-j} = P + i Q; inverse: the other way round
     const float2 lo = make_float2(P.x + Q.y, P.y - Q.x), hi = make_float2(P.x - Q.y, P.y + Q.x);
     const float2 Xj = (DIR < 0) ? lo : hi, Xr = (DIR < 0) ? hi : lo;
-    int t1 = (p * s * jj) % N, t2 = (p * s * (r - jj)) % N;
+    const int t1 = p * s * jj, t2 = p * s * (r - jj);      // p s < N / r, so both stay below N
     float2 w1 = tw[t1], w2 = tw[t2];
     if (DIR > 0) { w1.y = -w1.y; w2.y = -w2.y; }
     put(yo + jj * s, cmul(Xj, w1));
@@ -509,7 +509,7 @@ __device__ __forceinline__ int frame_out_start(const FftPlan &pl, int k) {
 
 // MODE 0: filter (K2).  MODE 1: noise (K5), UT = uniform dtype.
 template <int MODE, typename UT, int SPEC>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 4)
 k_stft(const FftSeg *__restrict__ segs, const FftJob *__restrict__ jobs, const FftPlan *__restrict__ plans,
        const float2 *__restrict__ twpool, const float *__restrict__ winpool,
        const float *__restrict__ in_f, const UT *__restrict__ in_u, const float *__restrict__ envpool,

@@ -1,5 +1,6 @@
-/* TEST-ONLY stand-in for R's headers: just enough declarations to syntax-check r/src/rshim.c
- * on a machine without R (tests/test_rshim_syntax.py).  Not used by any build. */
+/* TEST-ONLY stand-in for R's headers: the declarations r/src/rshim.c needs, implemented by
+ * tests/rstub/fake_r.c so that the shim can be compiled AND executed on a machine without R
+ * (tests/test_rshim_syntax.py, tests/test_rshim_exec.py).  Not used by any product build. */
 #ifndef RSTUB_R_H
 #define RSTUB_R_H
 #include <stddef.h>
@@ -9,7 +10,7 @@ typedef ptrdiff_t R_xlen_t;
 typedef void *(*DL_FUNC)(void);
 typedef struct _DllInfo DllInfo;
 typedef struct { const char *name; DL_FUNC fun; int numArgs; } R_CallMethodDef;
-extern SEXP R_NamesSymbol, R_NilValue, R_DimNamesSymbol;
+extern SEXP R_NamesSymbol, R_NilValue, R_DimNamesSymbol, R_DimSymbol;
 extern double R_NaN;
 enum { INTSXP = 13, REALSXP = 14, STRSXP = 16, VECSXP = 19 };
 SEXP Rf_getAttrib(SEXP, SEXP); SEXP Rf_setAttrib(SEXP, SEXP, SEXP);
