@@ -30,7 +30,9 @@ def inputs():
            'filter_sound': np.sin(np.arange(4000) * 0.05) * np.linspace(0.2, 1, 4000), 'filter_env': np.ones(400),
            'harm_pitch': np.linspace(120, 180, 1050), 'harm_z': r.standard_normal(2200),
            'noise_u': r.random(400 * 19),
-           'seed': [403] + RRng(1).state()}           # .Random.seed after set.seed(1): kind code 403 (MT + Inversion)
+           # .Random.seed after set.seed(1): kind code 403 (Mersenne-Twister + Inversion), then mti and mt[] as R
+           # stores them: signed 32-bit integers
+           'seed': [403] + list(np.array(RRng(1).state(), dtype=np.uint32).astype(np.int32))}
     return rec
 
 
