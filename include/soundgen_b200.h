@@ -306,6 +306,8 @@ void sgb_frontend_destroy(sgb_frontend *fe);
 /* Registers one soundgen() call (copies its arguments); returns the call index or an error.
  * The host stage up to the bout loop (validation, hyper-parameters, rbinom draws) runs here. */
 int  sgb_frontend_add(sgb_frontend *fe, const sgb_soundgen_args *args);
+/* n calls that differ only in their seed (rng_mode 0): returns the index of the first. */
+int  sgb_frontend_add_seeded(sgb_frontend *fe, const sgb_soundgen_args *args, const uint32_t *seeds, int32_t n);
 /* Builds the description of the next round.  One round covers every call that still has bouts
  * to generate, up to and including the first bout whose main filter has to be drawn after the
  * device has run (stochastic moving formants): most batches need exactly one round.

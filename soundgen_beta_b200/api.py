@@ -45,6 +45,8 @@ DEFAULT_FORMANTS = [dict(time=0, freq=860, amp=30, width=120),
 
 def _formant_rows(f):
     """one formant (dict/list/array) -> (k,4) array time, freq, amp, width"""
+    if isinstance(f, np.ndarray) and f.ndim == 2 and f.shape[1] == 4 and f.dtype == np.float64:
+        return f
     if isinstance(f, dict):
         cols = [np.atleast_1d(np.asarray(f[k], dtype=np.float64)) for k in ('time', 'freq', 'amp', 'width')]
         n = max(c.size for c in cols)
@@ -76,13 +78,13 @@ def _anchor_arg(a, keep):
         t, v = a
     else:
         t, v = None, a
-    v = np.ascontiguousarray(np.atleast_1d(v), dtype=np.float64)
-    if v.size == 0 or np.all(np.isnan(v)):
+    v = np.ascontiguousarray(v, dtype=np.float64).reshape(-1)
+    if v.size == 0 or (v[0] != v[0] and np.all(np.isnan(v))):
         return A
     keep.append(v)
     A.value, A.n = v.ctypes.data, v.size
     if t is not None:
-        t = np.ascontiguousarray(np.atleast_1d(t), dtype=np.float64)
+        t = np.ascontiguousarray(t, dtype=np.float64).reshape(-1)
         keep.append(t)
         A.time = t.ctypes.data
     return A
@@ -112,6 +114,7 @@ _ANCHOR_DEFAULTS = dict(pitchAnchors=((0, .1, .9, 1), (100, 150, 135, 100)), pit
                         noiseAnchors=((0, 300), (-120, -120)), mouthAnchors=((0, 1), (.5, .5)), amplAnchors=None,
                         amplAnchorsGlobal=None)
 _ACTIONS = {'adjust': 0, 'abort': 1, 'ignore': 2}
+_DEFAULT_FORMANT_ARGS = None
 _METHODS = {'loess': _abi.SGB_CONTOUR_LOESS, 'spline': _abi.SGB_CONTOUR_SPLINE}
 
 
@@ -139,16 +142,18 @@ class FrontEnd:
 
     def add(self, seed=None, z=None, u=None, contour_method='loess', warn=None, invalidArgAction='adjust',
             formants='default', formantsNoise=None, tempEffects=None, device_pitch=True, rng_state=None,
-            sample_kind='Rounding', **kw):
+            sample_kind='Rounding', seeds=None, **kw):
+        """One soundgen() call; with `seeds` (a sequence) the same argument list once per seed."""
         keep = []
         A = _abi.SoundgenArgs()
         for k, d in SOUNDGEN_DEFAULTS.items():
-            v = kw.pop(k, d)
+            v = kw.pop(k, d) if k in kw else d
             if v is None:
                 v = float('nan')
-            elif not isinstance(v, (int, float, np.integer, np.floating)):
+            try:
+                setattr(A, k, v)
+            except TypeError:
                 raise TypeError('%s must be numeric' % k)
-            setattr(A, k, float(v))
         for k, d in _ANCHOR_DEFAULTS.items():
             setattr(A, k, _anchor_arg(kw.pop(k, d), keep))
         if kw:
@@ -158,10 +163,17 @@ class FrontEnd:
         for i, k in enumerate(_abi.TEMP_EFFECTS):
             A.tempEffects[i] = float(te.get(k, float('nan')))
         if isinstance(formants, str) and formants == 'default':
-            formants = DEFAULT_FORMANTS
-        elif isinstance(formants, str):
-            formants = host.convert_string_to_formants(formants)     # soundgen.R:384-386
-        fl = _formant_list(formants)
+            global _DEFAULT_FORMANT_ARGS
+            if _DEFAULT_FORMANT_ARGS is None:
+                k0 = []
+                _DEFAULT_FORMANT_ARGS = (_formant_args(_formant_list(DEFAULT_FORMANTS), k0), k0)
+            A.formants = C.cast(_DEFAULT_FORMANT_ARGS[0], C.c_void_p)
+            A.n_formants = len(DEFAULT_FORMANTS)
+            fl = None
+        else:
+            if isinstance(formants, str):
+                formants = host.convert_string_to_formants(formants)     # soundgen.R:384-386
+            fl = _formant_list(formants)
         if fl:
             A.formants = C.cast(_formant_args(fl, keep), C.c_void_p)
             A.n_formants = len(fl)
@@ -193,7 +205,12 @@ class FrontEnd:
                 un = np.array([np.size(q) for q in ul], dtype=np.int64)
                 keep += [uc, un]
                 A.u, A.u_len, A.n_u = uc.ctypes.data, un.ctypes.data, len(ul)
-        rc = self.L.sgb_frontend_add(self.h, C.byref(A))
+        if seeds is not None:
+            sd = np.ascontiguousarray(np.asarray(seeds, dtype=np.int64) & 0xFFFFFFFF, dtype=np.uint32)
+            A.rng_mode = 0
+            rc = self.L.sgb_frontend_add_seeded(self.h, C.byref(A), sd.ctypes.data, sd.size)
+        else:
+            rc = self.L.sgb_frontend_add(self.h, C.byref(A))
         if rc < 0:
             msg = self.L.sgb_last_error().decode()
             if rc == _abi.SGB_ERR_INVALID and 'must be between' in msg:
@@ -201,7 +218,7 @@ class FrontEnd:
             if rc == _abi.SGB_ERR_UNSUPPORTED:
                 raise NotImplementedError(msg)
             raise SoundgenError(rc, msg)
-        self.n_calls = rc + 1
+        self.n_calls = rc + (1 if seeds is None else len(seeds))
         if warn is not None:
             w = self.L.sgb_frontend_warnings(self.h, rc).decode()
             if w:

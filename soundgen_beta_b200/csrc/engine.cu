@@ -778,6 +778,14 @@ int sgb_batch_run_begin(sgb_batch *b) {
   int n_failed = 0;
 
   auto get_plan = [&](int n, double overlap) -> int { return PT.get(n, overlap); };
+  // what an envelope instance of nr x nc reads from the pools must lie inside them (a malformed description
+  // must fail its call, not read out of bounds on the device)
+  auto env_ok = [&](const sgb_envelope &E, int nr, int nc) -> bool {
+    if (E.tracks_given == 2) return E.formant_off >= 0 && E.formant_off + (int64_t)nr * std::max(1, E.nc_fixed) <= b->n_pre;
+    if (E.tracks_given == 1)
+      for (int f = 0; f < E.n_formants; f++) if (b->frefs[E.formant_off + f].n < nc) return false;
+    return true;
+  };
 
   std::vector<int64_t> syl_pos, npos, fpos;   // reused across bouts (no allocation per bout)
   for (int c = 0; c < NC; c++) {
@@ -846,6 +854,9 @@ int sgb_batch_run_begin(sgb_batch *b) {
           L.filt_len = (int32_t)std::floor(wl + (L.nc - 1) * h_out);
           L.fft_plan = get_plan(wl, B.overlap);
           if (L.fft_plan < 0) { b->call_status[c] = SGB_ERR_UNSUPPORTED; L.bypass = 1; }
+          else if (b->envs[B.env_id].tracks_given != 3 && !env_ok(b->envs[B.env_id], wl / 2, L.nint)) {
+            b->call_status[c] = SGB_ERR_INVALID; L.bypass = 1;
+          }
         }
       }
       if (L.bypass) { L.filt_len = L.sound_len; L.nc = 0; L.nint = 0; }
@@ -855,6 +866,7 @@ int sgb_batch_run_begin(sgb_batch *b) {
         L.env_off = env_total; env_total += align4((int64_t)(L.wl / 2) * L.nint);
         EnvInst I; I.out_off = L.env_off; I.env_id = B.env_id; I.nr = L.wl / 2; I.nc = L.nint; I.col0 = 0; I.trk_off = -1;
         envinst.push_back(I);
+
         if (!contour_fits(b->envs[B.env_id].mouth_n, b->envs[B.env_id].mouth_method, L.nint, 16000.0, true, 0.0, true, 1.0,
                           b->h_anchors.data() + 2 * b->envs[B.env_id].mouth_off)) b->call_status[c] = SGB_ERR_SYNTH;
         FftJob J; memset(&J, 0, sizeof J);
@@ -901,7 +913,9 @@ int sgb_batch_run_begin(sgb_batch *b) {
         Q.fft_plan = get_plan(N.wl, N.overlap);
         Q.env_off = -1; Q.nc_env = 0;
         if (Q.fft_plan < 0) { b->call_status[c] = SGB_ERR_UNSUPPORTED; continue; }
-        if (N.env_id >= 0) {
+        if (N.env_id >= 0 && !env_ok(b->envs[N.env_id], N.wl / 2, std::max(1, b->envs[N.env_id].nc_fixed))) {
+          b->call_status[c] = SGB_ERR_INVALID;        // the noise is generated unfiltered; the call is reported
+        } else if (N.env_id >= 0) {
           const sgb_envelope &E = b->envs[N.env_id];
           Q.nc_env = std::max(1, E.nc_fixed);
           Q.env_off = env_total; env_total += align4((int64_t)(N.wl / 2) * Q.nc_env);

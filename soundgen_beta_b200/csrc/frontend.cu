@@ -551,6 +551,22 @@ int sgb_frontend_add(sgb_frontend *fe, const sgb_soundgen_args *args) {
   return (int)fe->calls.size() - 1;
 }
 
+/* n calls that differ only in their seed (call i = set.seed(seeds[i]); soundgen(<args>)): the data-generation
+ * sweep registers one preset a few thousand times without crossing the binding once per call. */
+int sgb_frontend_add_seeded(sgb_frontend *fe, const sgb_soundgen_args *args, const uint32_t *seeds, int32_t n) {
+  if (!fe || !args || !seeds || n < 1) return ffail(SGB_ERR_INVALID, "bad argument");
+  if (args->rng_mode != 0) return ffail(SGB_ERR_INVALID, "sgb_frontend_add_seeded needs rng_mode 0");
+  int first = -1;
+  for (int i = 0; i < n; i++) {
+    sgb_soundgen_args a = *args;
+    a.seed = seeds[i];
+    int rc = sgb_frontend_add(fe, &a);
+    if (rc < 0) return rc;
+    if (i == 0) first = rc;
+  }
+  return first;
+}
+
 }  // extern "C"
 
 namespace {
@@ -782,8 +798,18 @@ bool emit_bout(sgb_frontend *fe, int ci, int b) {
       const int64_t nu = (int64_t)(N.wl / 2) * seq_by_count(1.0, (double)N.len + N.wl, h);
       N.u_off = fe->u_is_float ? (int64_t)R.u32.size() : (int64_t)R.u64.size();
       if (C.use_rng) {
-        if (fe->u_is_float) { R.u32.reserve(R.u32.size() + nu); for (int64_t i = 0; i < nu; i++) R.u32.push_back((float)g.unif_rand()); }
-        else { R.u64.reserve(R.u64.size() + nu); for (int64_t i = 0; i < nu; i++) R.u64.push_back(g.unif_rand()); }
+        // (no reserve(size + nu) here: an exact-size reserve per segment would re-copy the whole pool every time)
+        if (fe->u_is_float) {
+          const size_t o = R.u32.size();
+          R.u32.resize(o + (size_t)nu);           // geometric growth; filled in place
+          float *dst = R.u32.data() + o;
+          for (int64_t i = 0; i < nu; i++) dst[i] = (float)g.unif_rand();
+        } else {
+          const size_t o = R.u64.size();
+          R.u64.resize(o + (size_t)nu);
+          double *dst = R.u64.data() + o;
+          for (int64_t i = 0; i < nu; i++) dst[i] = g.unif_rand();
+        }
       } else {
         bool ok = fe->u_is_float ? (C.ui < C.ubuf32.size() && (int64_t)C.ubuf32[C.ui].size() >= nu)
                                  : (C.ui < C.ubuf.size() && (int64_t)C.ubuf[C.ui].size() >= nu);
