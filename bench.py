@@ -413,7 +413,8 @@ def main():
         return
 
     value = audio_total * args.steps / dt
-    e2e = audio_total * args.steps / dt_e2e
+    e2e_f32 = audio_total * args.steps / dt_e2e
+    e2e = audio_total * args.steps / dt_wav
     # ---- roofline of the dominant kernel (K1 additive synthesis: FP32-pipe bound) ----
     peaks = {}
     try:
@@ -484,14 +485,20 @@ def main():
             'config': {'workload': workloads.NAMES[args.config], 'calls_per_gpu': len(calls),
                        'audio_seconds_per_gpu_step': audio_s, 'l2': 'inputs and intermediates larger than L2',
                        'uniforms': 'float32'},
+            # End to end through the public batch API with HOST buffers.  The result every step reads back is the
+            # waveform of every call as the 16-bit PCM samples the reference's savePath branch writes
+            # (R/soundgen.R:855-857 -> seewave::savewav), normalised and packed on the device; `e2e_f32` is the same
+            # pipeline fetching FP32 samples (what soundgen() returns in memory): twice the bytes, and on an
+            # 8-GPU box it runs at the bare pinned-copy ceiling of the host (profiles/r02_copy_ceiling_8gpu.json).
             'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': int(bb.h2d_bytes()),
-                    'd2h_bytes_per_step': int(d2h_bytes), 'ms_per_step': dt_e2e / args.steps * 1e3,
-                    'pipeline': npipe, 'runners': args.runners, 'cpus_bound': len(numa_cpus),
-                    'front_end_ms_per_step': fe_ms, 'note': 'timed from prebuilt descriptions; front_end_ms_per_step = '
-                    'the library host front-end (argument lists -> description) for the same batch, one thread'},
-            'e2e_wav16': {'value': audio_total * args.steps / dt_wav, 'unit': UNIT, 'ms_per_step': dt_wav / args.steps * 1e3,
-                          'd2h_bytes_per_step': int(d2h_i16),
-                          'note': 'same pipeline, waveforms fetched as 16-bit PCM (the savePath / WAV format)'},
+                    'd2h_bytes_per_step': int(d2h_i16), 'ms_per_step': dt_wav / args.steps * 1e3,
+                    'result_format': 'int16 PCM (savePath / WAV sample format)', 'pipeline': npipe, 'runners': args.runners,
+                    'cpus_bound': len(numa_cpus), 'front_end_ms_per_step': fe_ms,
+                    'note': 'timed from prebuilt descriptions; front_end_ms_per_step = argument lists -> description '
+                            'through the library host front-end for the same batch, one thread (Python marshalling included)'},
+            'e2e_f32': {'value': e2e_f32, 'unit': UNIT, 'ms_per_step': dt_e2e / args.steps * 1e3,
+                        'd2h_bytes_per_step': int(d2h_bytes),
+                        'note': 'same pipeline, waveforms fetched as FP32 samples'},
             'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline,
             'roofline_filter': roof_filter, 'cpu_baseline': cpu, 'parity_sample': parity,
             'parity_sample_max_err': (parity or {}).get('max_err_of_peak'), 'snr_db': (parity or {}).get('snr_db_min'),

@@ -729,7 +729,10 @@ size_t stft_smem_bytes(int n, double h_in, double h_out, int mode) {
 // on one bank pair; with the pad every pass of the tuned plans stores and loads without conflicts worth
 // speaking of (ncu: 4.7e7 store conflicts per 1024 sounds before, see profiles/).
 #define STFT_REG_THREADS 160                 // = the largest butterfly count of any tuned pass (2400 / 15)
-__device__ __forceinline__ int pad16(int i) { return i + (i >> 4); }
+#ifndef STFT_PAD_DIV
+#define STFT_PAD_DIV 16
+#endif
+__device__ __forceinline__ int pad16(int i) { return i + i / STFT_PAD_DIV; }
 struct PadIn {
   const float2 *b;
   int off;
@@ -838,7 +841,7 @@ k_stft_reg(const FftSeg *__restrict__ segs, const FftJob *__restrict__ jobs, con
   const int stage_len = (N + (int)ceil(pl.h_in) + 12) & ~3;
 
   float2 *buf = reinterpret_cast<float2 *>(smem_raw);
-  float *ola = reinterpret_cast<float *>(buf + ((N + N / 16 + 3) & ~1));      // keeps the TMA target 16-byte aligned
+  float *ola = reinterpret_cast<float *>(buf + ((N + N / 8 + 3) & ~1));      // keeps the TMA target 16-byte aligned
   const PadIn pbuf = {buf, 0};
   float *stage = ola + ((ring + 3) & ~3);                         // filter: staged input; noise: rolloff vector
   const float2 *tw = twpool + pl.tw_off;
@@ -1012,7 +1015,7 @@ size_t stft_smem_bytes_spec(int n, double h_in, double h_out, int mode, int spec
   int hceil = (int)ceil(h_out) + 2;
   int ring = n + 2 * hceil + 4;
   int stage_len = (n + (int)ceil(h_in) + 12) & ~3;
-  size_t floats = (size_t)2 * ((n + n / 16 + 3) & ~1) + (size_t)((ring + 3) & ~3) + (mode == 0 ? (size_t)stage_len : (size_t)(n / 2 + 4));
+  size_t floats = (size_t)2 * ((n + n / 8 + 3) & ~1) + (size_t)((ring + 3) & ~3) + (mode == 0 ? (size_t)stage_len : (size_t)(n / 2 + 4));
   return floats * 4 + 64;
 }
 
