@@ -37,6 +37,8 @@ struct SylCtrl {
   int32_t use_ampl;      // amplAnchors active
   int32_t out_len;       // length of the composed syllable (after cross-fades)
   int32_t tiles;         // K1 tiles
+  int32_t tiles_tc;      // units of the tensor-core K1 (intervals of approx() over all epochs)
+  int32_t pad_tc;
   int64_t amp_elems;     // doubles in the amplitude matrices
   int64_t wave_elems;    // floats of epoch waveform scratch
   double  parab_a, parab_b, parab_c;

@@ -163,7 +163,7 @@ SGB_HD void ctrl_sequential(const sgb_syllable &sp, const double *anchors, const
   int zi = 0;
   C.status = SGB_OK;
   C.nEpochs = 0; C.n_jidx = 0; C.vf_active = 0; C.rows_kept = 0; C.nHarmonics = 0;
-  C.n_up = 0; C.out_len = 0; C.tiles = 0; C.amp_elems = 0; C.wave_elems = 0; C.raw_max = 0.0;
+  C.n_up = 0; C.out_len = 0; C.tiles = 0; C.tiles_tc = 0; C.pad_tc = 0; C.amp_elems = 0; C.wave_elems = 0; C.raw_max = 0.0;
 
   // getGlottalCycles (R/utilities_soundgen.R:477-486)
   int G = 0;
@@ -468,6 +468,10 @@ SGB_HD void ctrl_sizes(SylArrays &A, SylCtrl &C, int tile) {
   C.amp_elems = amp;
   C.wave_elems = wave;
   C.tiles = tiles;
+  // tensor-core work list: one unit per interval of approx() of every epoch
+  int tc = 0;
+  for (int e = 0; e < C.nEpochs; e++) tc += C.ep_end[e] - C.ep_start[e];
+  C.tiles_tc = tc;
 }
 
 // Exact (double) amplitude of dense row j (1-based multiple of f0/(nsub+1)) at

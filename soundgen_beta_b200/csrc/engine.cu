@@ -27,6 +27,9 @@ void launch_fp32_peak(float2 *, int, int, int);
 #define ENV_MAXK_HOST 64
 void launch_synth(const SynthTile *, int, const sgb_syllable *, const SylCtrl *, const SylLayout *, const Pools &,
                   const float4 *, float *, int *, cudaStream_t);
+void launch_build_tiles_tc(const sgb_syllable *, const SylCtrl *, int, const SylLayout *, const Pools &, TcUnit *, cudaStream_t);
+cudaError_t launch_synth_tc(const TcUnit *, int, const Pools &, const float4 *, float *, int *, cudaStream_t);
+int synth_tc_timeout_flag();
 void launch_compose(const sgb_syllable *, int, SylCtrl *, const SylLayout *, const Pools &, const double *,
                     const float *, float *, const double *, const double *, const int *, cudaStream_t);
 void launch_place_voiced(const sgb_syllable *, int, const SylCtrl *, const SylLayout *, const SylPlace *,
@@ -174,7 +177,7 @@ struct sgb_batch {
   HBuf h_calltab;
   DBuf d_pcm, d_calltab;
   DBuf d_amp, d_amp32, d_wave, d_raw, d_sound, d_voiced, d_filt, d_noise_raw, d_noise_fin, d_env, d_out, d_out64;
-  DBuf d_trk, d_mouth, d_formants_late;
+  DBuf d_trk, d_mouth, d_formants_late, d_tiles_tc;
   struct RunState *rs = nullptr;     // state carried from run_begin to run_finish
   std::vector<double> late_rows;     // host-drawn formant tracks set between begin and finish
   bool envs_dirty = false;
@@ -362,7 +365,7 @@ void sgb_batch_destroy(sgb_batch *b) {
                  &b->d_totals, &b->d_summary, &b->d_tiles, &b->d_epmax, &b->p_pitch_w, &b->d_amp, &b->d_amp32, &b->d_wave, &b->d_raw,
                  &b->d_sound, &b->d_voiced, &b->d_filt, &b->d_noise_raw, &b->d_noise_fin, &b->d_env, &b->d_out,
                  &b->d_out64, &b->d_bl, &b->d_place, &b->d_nl, &b->d_envinst, &b->d_plans, &b->d_tw, &b->d_win,
-                 &b->d_fjobs, &b->d_njobs, &b->d_fsegs, &b->d_nsegs, &b->d_max, &b->d_trk, &b->d_mouth, &b->d_formants_late};
+                 &b->d_fjobs, &b->d_njobs, &b->d_fsegs, &b->d_nsegs, &b->d_max, &b->d_trk, &b->d_mouth, &b->d_formants_late, &b->d_tiles_tc};
   for (auto d : all) d->release();
   for (auto &d : b->p_i32) d.release();
   for (auto &d : b->p_f64) d.release();
@@ -740,9 +743,22 @@ int sgb_batch_run_begin(sgb_batch *b) {
   CK(cudaEventRecord(ev[2], st)); trace_mark(b, 2);
   // ---- K1 synthesis ----
   CK(cudaMemsetAsync(b->d_epmax.p, 0, 4 * (size_t)S * SGB_MAX_EPOCHS, st));
-  launch_synth(b->d_tiles.as<SynthTile>(), (int)n_tiles, d_syl, d_ctrl, d_lay, P, b->d_amp32.as<float4>(),
-               b->d_wave.as<float>(), b->d_epmax.as<int>(), st);
-  if (n_tiles > 0) launches++;
+  // SGB_SYNTH=ffma selects the FP32-pipe kernel of round 1 (blocked Clenshaw on FFMA2); the default is the
+  // tensor-core kernel (tcgen05 kind::tf32, 3xTF32, TMEM accumulators)
+  static const bool use_tc = [] { const char *e = getenv("SGB_SYNTH"); return !(e && !strcmp(e, "ffma")); }();
+  const int64_t n_tiles_tc = tot[7];
+  if (use_tc) {
+    if (n_tiles_tc > 2000000000LL) return fail(SGB_ERR_UNSUPPORTED, "batch too large: %lld synthesis tiles", (long long)n_tiles_tc);
+    CK(b->d_tiles_tc.ensure(sizeof(TcUnit) * (size_t)std::max<int64_t>(n_tiles_tc, 1)));
+    launch_build_tiles_tc(d_syl, d_ctrl, S, d_lay, P, b->d_tiles_tc.as<TcUnit>(), st);
+    CK(launch_synth_tc(b->d_tiles_tc.as<TcUnit>(), (int)n_tiles_tc, P, b->d_amp32.as<float4>(), b->d_wave.as<float>(),
+                       b->d_epmax.as<int>(), st));
+    if (n_tiles_tc > 0) launches += 2;
+  } else {
+    launch_synth(b->d_tiles.as<SynthTile>(), (int)n_tiles, d_syl, d_ctrl, d_lay, P, b->d_amp32.as<float4>(),
+                 b->d_wave.as<float>(), b->d_epmax.as<int>(), st);
+    if (n_tiles > 0) launches++;
+  }
   CK(cudaEventRecord(ev[3], st)); trace_mark(b, 3);
   // ---- K6 compose ----
   launch_compose(d_syl, S, d_ctrl, d_lay, P, b->d_amp.as<double>(), b->d_wave.as<float>(), b->d_raw.as<float>(),
@@ -1099,6 +1115,7 @@ int sgb_batch_run_finish(sgb_batch *b, sgb_run_info *info_out) {
   b->where = 0;
   CK(cudaGetLastError());
   if (stft_timeout_flag()) return fail(SGB_ERR_CUDA, "k_stft: a staged (TMA) frame load did not complete");
+  if (synth_tc_timeout_flag()) return fail(SGB_ERR_CUDA, "k_synth_tc: a tensor-core completion barrier never flipped");
   info.kernel_launches = launches;
   float ms;
   CK(cudaEventElapsedTime(&ms, ev[0], ev[1])); info.ms[SGB_T_CONTROL] = ms;

@@ -42,12 +42,21 @@ struct SylLayout {
   int64_t wave_off;    // floats, into the epoch-waveform pool
   int64_t raw_off;     // floats, into the composed-syllable pool (capacity n_up + 2)
   int32_t tile_off;    // first K1 tile
-  int32_t pad;
+  int32_t pad;         // first tile slot of the tensor-core K1 work list
 };
 
 // One K1 tile: SYNTH_TILE samples of one epoch.  gi_lo / a_lo are the amplitude interval and the
 // spline piece of the tile's first sample (the warps scan forward from there).
 struct SynthTile { int32_t syl; int32_t epoch; int32_t k0; int32_t gi_lo; int32_t a_lo; int32_t pad[3]; };
+// One unit of the tensor-core K1: the samples [kbeg, kend) of one epoch that lie in ONE interval of approx()
+// (one amplitude column), with everything the kernel needs so that it never touches SylCtrl.
+struct TcUnit {
+  int64_t col_off;      // first float4 of the interval's column in the amplitude table (row j - 1)
+  int64_t wave_off;     // sample 0 of the epoch in the wave buffer
+  int64_t pc_off;       // the syllable's first spline piece
+  double x_first, by, x_last, inv_sr_np1;
+  int32_t Ne, kbeg, kend, xg, xn, a_lo, G, J, epmax_idx, pad;
+};
 
 // Host-computed layout of one bout (after syllable lengths are known).
 struct BoutLayout {

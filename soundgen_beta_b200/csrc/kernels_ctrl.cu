@@ -119,7 +119,7 @@ k_control(const sgb_syllable *syl, int S, const double *pitch, const double *anc
     C.rows_kept = kept;
     if (kept < 1) C.status = SGB_ERR_SYNTH;
     ctrl_sizes(A, C, SYNTH_TILE);
-    if (C.status != SGB_OK) { C.tiles = 0; C.amp_elems = 0; C.wave_elems = 0; }
+    if (C.status != SGB_OK) { C.tiles = 0; C.tiles_tc = 0; C.amp_elems = 0; C.wave_elems = 0; }
   }
 }
 
@@ -131,33 +131,34 @@ __device__ inline int64_t raw_cap(const SylCtrl &C) {
 }
 __global__ void __launch_bounds__(1024)
 k_scan_sizes(const SylCtrl *ctrl, int S, SylLayout *lay, int64_t *totals) {
-  __shared__ int64_t part[5][1024];
+  __shared__ int64_t part[6][1024];
   const int t = threadIdx.x, nt = blockDim.x;
   const int per = (S + nt - 1) / nt;
   const int lo = min(S, t * per), hi = min(S, lo + per);
-  int64_t a = 0, w = 0, tl = 0, r = 0, failed = 0;
+  int64_t a = 0, w = 0, tl = 0, r = 0, failed = 0, tc = 0;
   for (int s = lo; s < hi; s++) {
     const SylCtrl &C = ctrl[s];
     bool ok = (C.status == SGB_OK);
     if (!ok) failed++;
-    a += ok ? C.amp_elems : 0; w += ok ? C.wave_elems : 0; tl += ok ? C.tiles : 0;
+    a += ok ? C.amp_elems : 0; w += ok ? C.wave_elems : 0; tl += ok ? C.tiles : 0; tc += ok ? C.tiles_tc : 0;
     r += raw_cap(C);
   }
+  part[5][t] = tc;
   part[0][t] = a; part[1][t] = w; part[2][t] = tl; part[3][t] = r; part[4][t] = failed;
   __syncthreads();
-  if (t < 5) {   // serial scan of <= 1024 partials per quantity: negligible
+  if (t < 6) {   // serial scan of <= 1024 partials per quantity: negligible
     int64_t run = 0;
     for (int i = 0; i < nt; i++) { int64_t v = part[t][i]; part[t][i] = run; run += v; }
-    totals[t == 4 ? 6 : t] = run;
+    totals[t == 4 ? 6 : (t == 5 ? 7 : t)] = run;
   }
   __syncthreads();
-  a = part[0][t]; w = part[1][t]; tl = part[2][t]; r = part[3][t];
+  a = part[0][t]; w = part[1][t]; tl = part[2][t]; r = part[3][t]; tc = part[5][t];
   for (int s = lo; s < hi; s++) {
     const SylCtrl &C = ctrl[s];
     bool ok = (C.status == SGB_OK);
     lay[s].amp_off = a; lay[s].wave_off = w; lay[s].tile_off = (int32_t)tl; lay[s].raw_off = r;
-    lay[s].pad = 0;
-    a += ok ? C.amp_elems : 0; w += ok ? C.wave_elems : 0; tl += ok ? C.tiles : 0;
+    lay[s].pad = (int32_t)tc;
+    a += ok ? C.amp_elems : 0; w += ok ? C.wave_elems : 0; tl += ok ? C.tiles : 0; tc += ok ? C.tiles_tc : 0;
     r += raw_cap(C);
   }
 }

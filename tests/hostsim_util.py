@@ -12,7 +12,7 @@ MAXE = 128
 class SylCtrl(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ['status', 'nGC', 'nHarmonics', 'rows_kept', 'nEpochs', 'n_up',
                                           'n_jidx', 'z_used', 'parab_harm', 'any_oct', 'vf_active',
-                                          'use_ampl', 'out_len', 'tiles']] + \
+                                          'use_ampl', 'out_len', 'tiles', 'tiles_tc', 'pad_tc']] + \
                [('amp_elems', C.c_int64), ('wave_elems', C.c_int64), ('parab_a', C.c_double),
                 ('parab_b', C.c_double), ('parab_c', C.c_double), ('raw_max', C.c_double)] + \
                [(n, C.c_int32 * MAXE) for n in ['ep_start', 'ep_end', 'ep_nsub', 'ep_rows', 'ep_zc1', 'ep_zc2']] + \
