@@ -21,7 +21,9 @@
 // Phase: as in the FMA kernel, FP64 closed form per spline piece (K0's quartic), re-anchored at every knot.
 // Numerics: scripts/micro/k1_umma.cu; the GPU parity tests run through this kernel.
 #include "engine.cuh"
+#include <cuda_fp16.h>
 #include <cstdlib>
+#include <cstdio>
 
 #define TC_KR 16                         // rows per block = K of the contraction
 #define TC_NB 32                         // blocks per chunk
@@ -58,6 +60,17 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float *v) {
                  "=r"(r[30]), "=r"(r[31]) : "r"(taddr));
 }
 
+// -DTC_PROF: wall-clock shares of the kernel's phases as one worker warp sees them (printed per launch)
+#ifdef TC_PROF
+__device__ unsigned long long g_tc_prof[16];
+#define TP_DECL long long prof[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long t0_ = clock64();
+#define TP(i) { long long t_ = clock64(); if (tid == 64) prof[i] += t_ - t0_; t0_ = t_; }
+#define TP_END if (tid == 64) for (int i = 0; i < 10; i++) atomicAdd(&g_tc_prof[i], (unsigned long long)prof[i]);
+#else
+#define TP_DECL
+#define TP(i)
+#define TP_END
+#endif
 __device__ int g_tc_timeout = 0;          // an MMA completion barrier that never flipped (reported by the host)
 int synth_tc_timeout_flag() { int v = 0; cudaMemcpyFromSymbol(&v, g_tc_timeout, sizeof v); return v; }
 
@@ -129,18 +142,71 @@ __global__ void k_build_units_tc(const sgb_syllable *syl, const SylCtrl *ctrl, i
   while (t < t_end) units[t++] = Z;
 }
 
-#define TC_PASS_ROWS 512                          // rows of one pass: 32 blocks of KR
-#define TC_B_PASSES 2                             // passes whose amplitude operand is resident (1024 rows)
-#define TC_BP_BYTES (64 * TC_KR * 4)              // one amplitude image of a pass: 64 columns (Y, dY of 32 blocks) x KR
-#define TC_SMEM (4 * TC_A_BYTES + TC_B_PASSES * 2 * TC_BP_BYTES)
+#define TC_PASS_BLOCKS 24                         // blocks of one pass: N = 48 accumulator columns for C and for S
+#define TC_PASS_ROWS (TC_PASS_BLOCKS * TC_KR)     // 384 rows
+#define TC_B_PASSES 3                             // passes whose amplitude operand is resident (1152 rows)
+#define TC_MAX_ROWS (TC_B_PASSES * TC_PASS_ROWS)
+#define TC_IMG_BYTES (2 * TC_PASS_BLOCKS * TC_KR * 2)  // one FP16 amplitude image of a pass: 48 columns (Y, dY of 24 blocks) x KR
+#define TC_SMEM (TC_B_PASSES * 2 * TC_IMG_BYTES)
+#define TC_NPC 4                                  // spline pieces staged per unit (an interval spans two or three)
+// instruction descriptor of kind::f16: FP16 x FP16 -> FP32, both operands K-major, M 128
+#define TC_IDESC(N) ((1u << 4) | ((uint32_t)((N) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24))
+// TMEM columns of a CTA (128): the trig operand (A of the MMAs: lane = sample, one column = rows m, m + 1 in FP16)
+// and the accumulators
+#define TC_COL_CH 0
+#define TC_COL_CL 8
+#define TC_COL_SH 16
+#define TC_COL_SL 24
+#define TC_COL_C 32
+#define TC_COL_S 80
+
+// FP16, K-major, no swizzle: a core matrix is 8 rows x 16 bytes (8 values of K); K = 16 is two of them, 128 B apart
+// (LBO); the next 8 rows are 256 B further (SBO)
+__device__ __forceinline__ uint64_t tc_desc16(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)(128 >> 4) << 16;
+  d |= (uint64_t)(256 >> 4) << 32;
+  d |= (uint64_t)1 << 46;                 // descriptor version of sm_100
+  return d;
+}
+__device__ __forceinline__ int tc_off16(int n, int k) { return (n >> 3) * 256 + (k >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2; }
+// D[tmem] (+)= A[tmem] . B[smem]
+__device__ __forceinline__ void tc_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}\n"
+               :: "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0) : "memory");
+}
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t *r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+// x = hi + lo in FP16 (22 significant bits; lo may be subnormal: absolute error <= 2^-25)
+__device__ __forceinline__ void tc_split16(float2 x, uint32_t &hi, uint32_t &lo) {
+  const __half2 h = __floats2half2_rn(x.x, x.y);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x.x - hf.x, x.y - hf.y);
+  hi = *reinterpret_cast<const uint32_t *>(&h);
+  lo = *reinterpret_cast<const uint32_t *>(&l);
+}
+// One accumulator chain of a pass: {hi hi, lo hi, hi lo}, then the commit that arrives on the mbarrier.  Two threads
+// issue (one for C, one for S): an MMA costs its issuing thread 60-90 cycles, whatever its size (scripts/micro/mma_rate.cu).
+__device__ __forceinline__ void tc_issue_chain(uint32_t tmem_d, uint32_t tmem_a_hi, uint32_t tmem_a_lo, uint64_t descB, int nb,
+                                               uint32_t bar_addr) {
+  const uint32_t idesc = TC_IDESC(2 * nb);
+  tc_mma_ts(tmem_d, tmem_a_hi, descB, idesc, 0u);
+  tc_mma_ts(tmem_d, tmem_a_lo, descB, idesc, 1u);
+  tc_mma_ts(tmem_d, tmem_a_hi, descB + (uint64_t)(TC_IMG_BYTES >> 4), idesc, 1u);
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar_addr) : "memory");
+}
 
 __global__ void __launch_bounds__(128, 4)
 k_synth_tc(const TcUnit *__restrict__ units, int nunits, const double *__restrict__ pc, const float4 *__restrict__ amp,
            float *__restrict__ wave, int *__restrict__ epmax) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t *sA = smem;                       // cos_hi, cos_lo, sin_hi, sin_lo
-  uint8_t *sB = smem + 4 * TC_A_BYTES;      // per resident pass: hi, lo
+  extern __shared__ __align__(1024) uint8_t sB[];        // per resident pass: hi, lo images of the amplitude operand
   __shared__ uint64_t bar;
+  __shared__ double spc[TC_NPC * SYNTH_PC];   // the unit's first spline pieces {knot, c0..c4}
+  __shared__ float smax[4];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp == 0) {
@@ -148,7 +214,7 @@ k_synth_tc(const TcUnit *__restrict__ units, int nunits, const double *__restric
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(tc_smem_u32(&bar)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 2;" :: "r"(tc_smem_u32(&bar)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
@@ -156,38 +222,71 @@ k_synth_tc(const TcUnit *__restrict__ units, int nunits, const double *__restric
   asm volatile("tcgen05.fence::after_thread_sync;");
   const uint32_t tmem_base = tmem_base_s;
   const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-  const uint32_t aB = tc_smem_u32(sA), bB = tc_smem_u32(sB), barA = tc_smem_u32(&bar);
+  const uint64_t descB = tc_desc16(tc_smem_u32(sB));
+  const uint32_t barA = tc_smem_u32(&bar);
+  const bool issuer = lane == 0 && warp < 2;         // warp 0: the C chain, warp 1: the S chain
+  const uint32_t my_d = tmem_base + (warp == 0 ? TC_COL_C : TC_COL_S);
+  const uint32_t my_ahi = tmem_base + (warp == 0 ? TC_COL_CH : TC_COL_SH), my_alo = tmem_base + (warp == 0 ? TC_COL_CL : TC_COL_SL);
   uint32_t phase = 0u;
   bool dead = false;
+  TP_DECL
 
   for (int ui = blockIdx.x; ui < nunits && !dead; ui += gridDim.x) {
     const TcUnit U = units[ui];
     if (U.kend <= U.kbeg) continue;
+    TP(0)
     const int J = U.J;
     const float4 *__restrict__ col = amp + U.col_off;               // {Y, Y, dY, dY} of the interval, row j - 1
     const double *__restrict__ pcs = pc + SYNTH_PC * U.pc_off;
     const int x_first_i = (int)U.x_first;
     const float inv_dx = __frcp_rn((float)(U.xn - U.xg));
     const int nrows = J + 1;                                        // rows j = 0 (zero) .. J
-    const int nsuper = (nrows + TC_B_PASSES * TC_PASS_ROWS - 1) / (TC_B_PASSES * TC_PASS_ROWS);
+    const int nsuper = (nrows + TC_MAX_ROWS - 1) / TC_MAX_ROWS;
 
     for (int sp = 0; sp < nsuper; sp++) {
-      const int row0 = sp * TC_B_PASSES * TC_PASS_ROWS;
-      const int rows_here = min(nrows - row0, TC_B_PASSES * TC_PASS_ROWS);
+      const int row0 = sp * TC_MAX_ROWS;
+      const int rows_here = min(nrows - row0, TC_MAX_ROWS);
       const int blocks_here = ((rows_here + TC_KR - 1) / TC_KR + 7) & ~7;    // N = 2 x blocks is a multiple of 16
-      // ---- amplitude operand: rows row0 .. row0 + 16 blocks_here - 1 ----
-      for (int r = tid; r < blocks_here * TC_KR; r += 128) {
-        const int j = row0 + r;
-        float y = 0.f, dy = 0.f;
-        if (j >= 1 && j <= J) { const float4 q = __ldg(&col[j - 1]); y = q.x; dy = q.z; }
-        const int p = r / TC_PASS_ROWS, rr = r % TC_PASS_ROWS, b = rr / TC_KR, m = rr % TC_KR;
-        uint32_t yh, yl, dh, dl;
-        tc_split(y, yh, yl); tc_split(dy, dh, dl);
-        uint8_t *hi = sB + p * (2 * TC_BP_BYTES) + tc_off(2 * b, m), *lo = hi + TC_BP_BYTES;
-        *reinterpret_cast<uint32_t *>(hi) = yh; *reinterpret_cast<uint32_t *>(hi + 16) = dh;
-        *reinterpret_cast<uint32_t *>(lo) = yl; *reinterpret_cast<uint32_t *>(lo + 16) = dl;
+      if (sp == 0 && tid < TC_NPC * SYNTH_PC) {        // pieces a_lo .. a_lo + 3 (the syllable has G of them)
+        const int pi = min(U.a_lo + tid / SYNTH_PC, U.G - 1);
+        spc[tid] = __ldg(&pcs[SYNTH_PC * pi + tid % SYNTH_PC]);
       }
-      const int npass = (blocks_here * TC_KR + TC_PASS_ROWS - 1) / TC_PASS_ROWS;
+      // ---- amplitude operand: rows row0 .. row0 + 16 blocks_here - 1, scaled by a power of two so that the largest
+      // |Y|, |dY| sits in [2^14, 2^15): hi + lo in FP16 then carry 22 bits of every value down to 2^-39 of the largest ----
+      float yv[TC_MAX_ROWS / 128], dv[TC_MAX_ROWS / 128];
+      float mx = 0.f;
+#pragma unroll
+      for (int i = 0; i < TC_MAX_ROWS / 128; i++) {
+        const int j = row0 + tid + 128 * i;
+        yv[i] = 0.f; dv[i] = 0.f;
+        if (tid + 128 * i < blocks_here * TC_KR && j >= 1 && j <= J) { const float4 q = __ldg(&col[j - 1]); yv[i] = q.x; dv[i] = q.z; }
+        mx = fmaxf(mx, fmaxf(fabsf(yv[i]), fabsf(dv[i])));
+      }
+#pragma unroll
+      for (int of = 16; of > 0; of >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, of));
+      if (lane == 0) smax[warp] = mx;
+      __syncthreads();
+      mx = fmaxf(fmaxf(smax[0], smax[1]), fmaxf(smax[2], smax[3]));
+      const int ex = (mx > 0.f && mx < 3.0e38f) ? ilogbf(mx) : 14;
+      const float scale = scalbnf(1.0f, 14 - ex), unscale = scalbnf(1.0f, ex - 14);
+#pragma unroll
+      for (int i = 0; i < TC_MAX_ROWS / 128; i++) {
+        const int r = tid + 128 * i;
+        if (r < blocks_here * TC_KR) {
+          const int p = r / TC_PASS_ROWS, rr = r % TC_PASS_ROWS, b = rr / TC_KR, m = rr % TC_KR;
+          const float ys = yv[i] * scale, ds = dv[i] * scale;
+          const __half yh = __float2half_rn(ys), dh = __float2half_rn(ds);
+          const __half yl = __float2half_rn(ys - __half2float(yh)), dl = __float2half_rn(ds - __half2float(dh));
+          // accumulator columns of a block pair: {Y_2q, Y_2q+1, dY_2q, dY_2q+1} (register pairs for the packed epilogue)
+          uint8_t *hi = sB + p * (2 * TC_IMG_BYTES) + tc_off16(4 * (b >> 1) + (b & 1), m), *lo = hi + TC_IMG_BYTES;
+          *reinterpret_cast<__half *>(hi) = yh; *reinterpret_cast<__half *>(hi + 32) = dh;
+          *reinterpret_cast<__half *>(lo) = yl; *reinterpret_cast<__half *>(lo + 32) = dl;
+        }
+      }
+      const int npass = (blocks_here + TC_PASS_BLOCKS - 1) / TC_PASS_BLOCKS;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();                               // spc, sB
+      TP(1)
 
       for (int k0 = U.kbeg; k0 < U.kend && !dead; k0 += TC_TILE) {
         // ---- this thread's sample: interval weight and phase ----
@@ -196,106 +295,105 @@ k_synth_tc(const TcUnit *__restrict__ units, int nunits, const double *__restric
         const double v = (k >= U.Ne - 1) ? U.x_last : (U.x_first + (double)k * U.by);
         const float ww = (float)(v - (double)U.xg) * inv_dx;
         const double u = (double)(x_first_i + k);
-        int a = U.a_lo;
-        while (a < U.G - 1 && u >= pcs[SYNTH_PC * (a + 1)]) a++;
-        const double *pp = pcs + SYNTH_PC * a;
-        const double M = u - pp[0];
-        const double ph = fma(fma(fma(fma(pp[5], M, pp[4]), M, pp[3]), M, pp[2]), M, pp[1]);
+        int a = 0;                               // piece: largest a with knot <= u; staged ones first
+        const int na = min(TC_NPC, U.G - U.a_lo);
+        while (a < na - 1 && u >= spc[SYNTH_PC * (a + 1)]) a++;
+        double p0 = spc[SYNTH_PC * a], p1 = spc[SYNTH_PC * a + 1], p2 = spc[SYNTH_PC * a + 2], p3 = spc[SYNTH_PC * a + 3],
+               p4 = spc[SYNTH_PC * a + 4], p5 = spc[SYNTH_PC * a + 5];
+        if (a == TC_NPC - 1) {                   // rare: the interval reaches past the staged pieces
+          int ag = U.a_lo + a;
+          while (ag < U.G - 1 && u >= pcs[SYNTH_PC * (ag + 1)]) ag++;
+          const double *pp = pcs + SYNTH_PC * ag;
+          p0 = pp[0]; p1 = pp[1]; p2 = pp[2]; p3 = pp[3]; p4 = pp[4]; p5 = pp[5];
+        }
+        const double M = u - p0;
+        const double ph = fma(fma(fma(fma(p5, M, p4), M, p3), M, p2), M, p1);
         double x = ph * U.inv_sr_np1;             // integr / (nSubharm + 1), in cycles
         x -= floor(x);
-        // ---- trig operand rows: cos / sin (m theta'), m < KR, hi + lo ----
+        TP(2)
+        // ---- trig operand rows: cos / sin (m theta'), m < KR, hi + lo in FP16, into this thread's TMEM lane; even and
+        // odd m are two packed FP32 chains and share a column ----
         {
           float s1, c1;
           sincospif(2.0f * (float)x, &s1, &c1);
-          float cm = 1.f, sm = 0.f;
+          const float c2 = fmaf(c1, c1, -(s1 * s1)), s2 = 2.0f * s1 * c1;        // e^{2 i theta'}
+          const float2 C2 = make_float2(c2, c2), S2 = make_float2(s2, s2), nS2 = make_float2(-s2, -s2);
+          float2 cm = make_float2(1.f, c1), sm = make_float2(0.f, s1);            // rows m, m + 1
+          uint32_t ch[8], cl[8], sh[8], sl[8];
 #pragma unroll
-          for (int k4 = 0; k4 < TC_KR / 4; k4++) {
-            uint32_t ch[4], cl[4], sh[4], sl[4];
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-              tc_split(cm, ch[q], cl[q]); tc_split(sm, sh[q], sl[q]);
-              const float c = cm * c1 - sm * s1, sn = cm * s1 + sm * c1; cm = c; sm = sn;
-            }
-            const int of = tc_off(tid, 4 * k4);
-            *reinterpret_cast<uint4 *>(sA + 0 * TC_A_BYTES + of) = make_uint4(ch[0], ch[1], ch[2], ch[3]);
-            *reinterpret_cast<uint4 *>(sA + 1 * TC_A_BYTES + of) = make_uint4(cl[0], cl[1], cl[2], cl[3]);
-            *reinterpret_cast<uint4 *>(sA + 2 * TC_A_BYTES + of) = make_uint4(sh[0], sh[1], sh[2], sh[3]);
-            *reinterpret_cast<uint4 *>(sA + 3 * TC_A_BYTES + of) = make_uint4(sl[0], sl[1], sl[2], sl[3]);
+          for (int h = 0; h < TC_KR / 2; h++) {
+            tc_split16(cm, ch[h], cl[h]); tc_split16(sm, sh[h], sl[h]);
+            const float2 nc = __ffma2_rn(cm, C2, __fmul2_rn(sm, nS2)), ns = __ffma2_rn(cm, S2, __fmul2_rn(sm, C2));
+            cm = nc; sm = ns;
           }
+          tc_st8(lane_addr + TC_COL_CH, ch); tc_st8(lane_addr + TC_COL_CL, cl);
+          tc_st8(lane_addr + TC_COL_SH, sh); tc_st8(lane_addr + TC_COL_SL, sl);
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         }
-        float zc, zs;                            // z = e^{i KR theta'}
-        { double q = x * (double)TC_KR; q -= floor(q); sincospif(2.0f * (float)q, &zs, &zc); }
-        float acc = (sp > 0 && live) ? wave[U.wave_off + k] : 0.f;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        TP(3)
         asm volatile("tcgen05.fence::before_thread_sync;");
         __syncthreads();
-        asm volatile("tcgen05.fence::after_thread_sync;");
+        if (issuer) {
+          asm volatile("tcgen05.fence::after_thread_sync;");
+          tc_issue_chain(my_d, my_ahi, my_alo, descB, min(blocks_here, TC_PASS_BLOCKS), barA);
+        }
+        TP(4)
+        // in the shadow of the first MMAs: z = e^{i KR theta'}, z^2, the pass rotation P = e^{i 384 theta'}, E = e^{i row0 theta'}
+        float zc, zs;
+        { double q = x * (double)TC_KR; q -= floor(q); sincospif(2.0f * (float)q, &zs, &zc); }
+        const float zc2 = fmaf(zc, zc, -(zs * zs)), zs2 = 2.0f * zs * zc;
+        const float2 z2c = make_float2(zc2, zc2), z2s = make_float2(zs2, zs2), nz2s = make_float2(-zs2, -zs2);
+        const float2 ww2 = make_float2(ww, ww);
+        float ec = 1.f, es = 0.f, pc_ = 1.f, ps_ = 0.f;
+        if (npass > 1) { double q = x * (double)TC_PASS_ROWS; q -= floor(q); sincospif(2.0f * (float)q, &ps_, &pc_); }
+        float acc = 0.f, prev = 0.f;
+        if (sp > 0) {
+          double q = x * (double)row0; q -= floor(q); sincospif(2.0f * (float)q, &es, &ec);
+          if (live) prev = wave[U.wave_off + k];
+        }
 
         for (int p = 0; p < npass; p++) {
-          const int nb = min(blocks_here - p * (TC_PASS_ROWS / TC_KR), TC_PASS_ROWS / TC_KR);   // blocks of this pass: 8 .. 32
-          if (tid == 0) {
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * nb) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            const uint32_t bP = bB + p * (2 * TC_BP_BYTES);
-#pragma unroll
-            for (int ks = 0; ks < 2; ks++)
-#pragma unroll
-              for (int t3 = 0; t3 < 3; t3++) {
-                const int ah = (t3 == 1) ? 1 : 0, bh = (t3 == 2) ? 1 : 0;
-                const uint32_t acc_flag = (ks | t3) ? 1u : 0u;
-                const uint64_t bd = tc_desc(bP + bh * TC_BP_BYTES + ks * 256);
-                tc_mma(tmem_base, tc_desc(aB + (0 + ah) * TC_A_BYTES + ks * 256), bd, idesc, acc_flag);
-                tc_mma(tmem_base + 64, tc_desc(aB + (2 + ah) * TC_A_BYTES + ks * 256), bd, idesc, acc_flag);
-              }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(barA) : "memory");
-          }
-          uint32_t ok = 0;
-          unsigned long long polls = 0;
+          const int nb = min(blocks_here - p * TC_PASS_BLOCKS, TC_PASS_BLOCKS);   // 8, 16 or 24 blocks
+          uint32_t ok = 0, polls = 0;
           while (!ok) {
             asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.b32 %0, 1, 0, p;\n}\n"
                          : "=r"(ok) : "r"(barA), "r"(phase) : "memory");
-            if (!ok && ++polls > (1ull << 24)) { g_tc_timeout = 1; dead = true; break; }
+            if (!ok && ++polls > (1u << 24)) { g_tc_timeout = 1; dead = true; break; }
           }
           phase ^= 1u;
+          TP(5)
           asm volatile("tcgen05.fence::after_thread_sync;");
-          // ---- R = sum_b z^b (S_b - i C_b), Horner from the top block ----
-          float Rr = 0.f, Ri = 0.f;
-          int b0 = nb;
-          if (b0 & 8) {                          // tail group of 8 blocks
-            b0 -= 8;
+          // ---- R = sum_b z^b (S_b - i C_b): Horner in z^2 from the top, even and odd blocks as the two halves of
+          // packed FP32 pairs; Q = -Im R ----
+          float2 Rr = make_float2(0.f, 0.f), Q = make_float2(0.f, 0.f);
+          for (int g = nb / 8 - 1; g >= 0; g--) {          // 8 blocks = 16 accumulator columns of C and of S
             float Cv[16], Sv[16];
-            tc_ld16(lane_addr + 2 * b0, Cv); tc_ld16(lane_addr + 64 + 2 * b0, Sv);
+            tc_ld16(lane_addr + TC_COL_C + 16 * g, Cv); tc_ld16(lane_addr + TC_COL_S + 16 * g, Sv);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int b = 7; b >= 0; b--) {
-              const float Cc = fmaf(ww, Cv[2 * b + 1], Cv[2 * b]), Ss = fmaf(ww, Sv[2 * b + 1], Sv[2 * b]);
-              const float nr = fmaf(Rr, zc, fmaf(-Ri, zs, Ss)), ni = fmaf(Rr, zs, fmaf(Ri, zc, -Cc));
-              Rr = nr; Ri = ni;
+            for (int q = 3; q >= 0; q--) {
+              const float2 Cc = __ffma2_rn(ww2, make_float2(Cv[4 * q + 2], Cv[4 * q + 3]), make_float2(Cv[4 * q], Cv[4 * q + 1]));
+              const float2 Ss = __ffma2_rn(ww2, make_float2(Sv[4 * q + 2], Sv[4 * q + 3]), make_float2(Sv[4 * q], Sv[4 * q + 1]));
+              const float2 nr = __ffma2_rn(Rr, z2c, __ffma2_rn(Q, z2s, Ss)), nq = __ffma2_rn(Rr, nz2s, __ffma2_rn(Q, z2c, Cc));
+              Rr = nr; Q = nq;
             }
-          }
-          while (b0 > 0) {
-            b0 -= 16;
-            float Cv[32], Sv[32];
-            tc_ld32(lane_addr + 2 * b0, Cv); tc_ld32(lane_addr + 64 + 2 * b0, Sv);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int b = 15; b >= 0; b--) {
-              const float Cc = fmaf(ww, Cv[2 * b + 1], Cv[2 * b]), Ss = fmaf(ww, Sv[2 * b + 1], Sv[2 * b]);
-              const float nr = fmaf(Rr, zc, fmaf(-Ri, zs, Ss)), ni = fmaf(Rr, zs, fmaf(Ri, zc, -Cc));
-              Rr = nr; Ri = ni;
-            }
-          }
-          const int jb = row0 + p * TC_PASS_ROWS;             // first row of the pass
-          if (jb == 0) acc += Rr;
-          else {
-            float rs, rc;
-            double q = x * (double)jb; q -= floor(q);
-            sincospif(2.0f * (float)q, &rs, &rc);
-            acc = fmaf(rc, Rr, fmaf(-rs, Ri, acc));
           }
           asm volatile("tcgen05.fence::before_thread_sync;");
-          __syncthreads();                                    // TMEM (and, after the last pass, the trig operand) is free
-          asm volatile("tcgen05.fence::after_thread_sync;");
+          __syncthreads();                       // the accumulators are free
+          if (issuer && p + 1 < npass) {
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            tc_issue_chain(my_d, my_ahi, my_alo, descB + (uint64_t)(((p + 1) * 2 * TC_IMG_BYTES) >> 4),
+                           min(blocks_here - (p + 1) * TC_PASS_BLOCKS, TC_PASS_BLOCKS), barA);
+          }
+          TP(6)
+          // R = R_even + z R_odd;  acc += Re (E R)
+          const float Rre = fmaf(zc, Rr.y, fmaf(zs, Q.y, Rr.x));            // zc Rr_o - zs Ri_o, Ri_o = -Q_o
+          const float Rim = fmaf(zs, Rr.y, fmaf(-zc, Q.y, -Q.x));           // zs Rr_o + zc Ri_o + Ri_e
+          acc = fmaf(ec, Rre, fmaf(-es, Rim, acc));
+          const float ne = fmaf(ec, pc_, -(es * ps_)), nsn = fmaf(ec, ps_, es * pc_); ec = ne; es = nsn;
+          TP(7)
         }
+        acc = fmaf(acc, unscale, prev);
         if (live) wave[U.wave_off + k] = acc;
         if (sp == nsuper - 1) {      // max |w| of the epoch (tolerance of the zero-crossing searches in K6)
           float m = live ? fabsf(acc) : 0.0f;
@@ -303,9 +401,12 @@ k_synth_tc(const TcUnit *__restrict__ units, int nunits, const double *__restric
           for (int of = 16; of > 0; of >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, of));
           if (lane == 0 && m > 0.0f) atomicMax(&epmax[U.epmax_idx], float_to_ordered(m));
         }
+        TP(8)
       }
+      __syncthreads();               // sB, spc, smax are rewritten next: all MMAs completed above, every thread is past its reads
     }
   }
+  TP_END
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(128));
 }
@@ -328,5 +429,18 @@ cudaError_t launch_synth_tc(const TcUnit *units, int n_units, const Pools &P, co
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = std::min(n_units, 4 * sms);               // persistent: four CTAs (4 x 128 TMEM columns) per SM
   k_synth_tc<<<grid, 128, TC_SMEM, st>>>(units, n_units, P.pc, amp, wave, epmax);
+#ifdef TC_PROF
+  {
+    cudaStreamSynchronize(st);
+    unsigned long long h[16], z[16] = {};
+    cudaMemcpyFromSymbol(h, g_tc_prof, sizeof h);
+    cudaMemcpyToSymbol(g_tc_prof, z, sizeof z);
+    double tot = 0;
+    for (int i = 0; i < 10; i++) tot += (double)h[i];
+    fprintf(stderr, "tcprof grid %d:", grid);
+    for (int i = 0; i < 10; i++) fprintf(stderr, " %d:%.1f%%", i, 100.0 * h[i] / tot);
+    fprintf(stderr, " cyc/cta %.0f\n", tot / grid);
+  }
+#endif
   return cudaGetLastError();
 }
