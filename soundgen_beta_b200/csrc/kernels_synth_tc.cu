@@ -288,12 +288,10 @@ k_synth_tc(const TcUnit *__restrict__ units, int nunits, const double *__restric
       __syncthreads();                               // spc, sB
       TP(1)
 
-      for (int k0 = U.kbeg; k0 < U.kend && !dead; k0 += TC_TILE) {
-        // ---- this thread's sample: interval weight and phase ----
-        const bool live = k0 + tid < U.kend;
-        const int k = live ? k0 + tid : k0;
+      // phase of sample k of the unit: FP64 closed form of the spline piece; returns integr / (nSubharm + 1) in cycles
+      auto sample_phase = [&](int k, float &ww_out) -> double {
         const double v = (k >= U.Ne - 1) ? U.x_last : (U.x_first + (double)k * U.by);
-        const float ww = (float)(v - (double)U.xg) * inv_dx;
+        ww_out = (float)(v - (double)U.xg) * inv_dx;
         const double u = (double)(x_first_i + k);
         int a = 0;                               // piece: largest a with knot <= u; staged ones first
         const int na = min(TC_NPC, U.G - U.a_lo);
@@ -308,8 +306,19 @@ k_synth_tc(const TcUnit *__restrict__ units, int nunits, const double *__restric
         }
         const double M = u - p0;
         const double ph = fma(fma(fma(fma(p5, M, p4), M, p3), M, p2), M, p1);
-        double x = ph * U.inv_sr_np1;             // integr / (nSubharm + 1), in cycles
-        x -= floor(x);
+        const double x = ph * U.inv_sr_np1;
+        return x - floor(x);
+      };
+      float ww_n;
+      double x_n = sample_phase(min(U.kbeg + tid, U.kend - 1), ww_n);
+      float unit_max = 0.f;
+
+      for (int k0 = U.kbeg; k0 < U.kend && !dead; k0 += TC_TILE) {
+        // ---- this thread's sample: interval weight and phase (computed one tile ahead, in the shadow of the MMAs) ----
+        const bool live = k0 + tid < U.kend;
+        const int k = live ? k0 + tid : k0;
+        const float ww = ww_n;
+        const double x = x_n;
         TP(2)
         // ---- trig operand rows: cos / sin (m theta'), m < KR, hi + lo in FP16, into this thread's TMEM lane; even and
         // odd m are two packed FP32 chains and share a column ----
@@ -351,6 +360,7 @@ k_synth_tc(const TcUnit *__restrict__ units, int nunits, const double *__restric
           double q = x * (double)row0; q -= floor(q); sincospif(2.0f * (float)q, &es, &ec);
           if (live) prev = wave[U.wave_off + k];
         }
+        if (k0 + TC_TILE < U.kend) x_n = sample_phase(min(k0 + TC_TILE + tid, U.kend - 1), ww_n);
 
         for (int p = 0; p < npass; p++) {
           const int nb = min(blocks_here - p * TC_PASS_BLOCKS, TC_PASS_BLOCKS);   // 8, 16 or 24 blocks
@@ -366,17 +376,25 @@ k_synth_tc(const TcUnit *__restrict__ units, int nunits, const double *__restric
           // ---- R = sum_b z^b (S_b - i C_b): Horner in z^2 from the top, even and odd blocks as the two halves of
           // packed FP32 pairs; Q = -Im R ----
           float2 Rr = make_float2(0.f, 0.f), Q = make_float2(0.f, 0.f);
-          for (int g = nb / 8 - 1; g >= 0; g--) {          // 8 blocks = 16 accumulator columns of C and of S
-            float Cv[16], Sv[16];
-            tc_ld16(lane_addr + TC_COL_C + 16 * g, Cv); tc_ld16(lane_addr + TC_COL_S + 16 * g, Sv);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          float Cv[2][16], Sv[2][16];                      // 8 blocks = 16 accumulator columns of C and of S, two in flight
+          int g = nb / 8 - 1;
+          tc_ld16(lane_addr + TC_COL_C + 16 * g, Cv[0]); tc_ld16(lane_addr + TC_COL_S + 16 * g, Sv[0]);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int it = 0; it < TC_PASS_BLOCKS / 8; it++) {
+            const int cur = it & 1;
+            if (g - it < 0) break;
+            if (g - it - 1 >= 0) {
+              tc_ld16(lane_addr + TC_COL_C + 16 * (g - it - 1), Cv[cur ^ 1]); tc_ld16(lane_addr + TC_COL_S + 16 * (g - it - 1), Sv[cur ^ 1]);
+            }
 #pragma unroll
             for (int q = 3; q >= 0; q--) {
-              const float2 Cc = __ffma2_rn(ww2, make_float2(Cv[4 * q + 2], Cv[4 * q + 3]), make_float2(Cv[4 * q], Cv[4 * q + 1]));
-              const float2 Ss = __ffma2_rn(ww2, make_float2(Sv[4 * q + 2], Sv[4 * q + 3]), make_float2(Sv[4 * q], Sv[4 * q + 1]));
+              const float2 Cc = __ffma2_rn(ww2, make_float2(Cv[cur][4 * q + 2], Cv[cur][4 * q + 3]), make_float2(Cv[cur][4 * q], Cv[cur][4 * q + 1]));
+              const float2 Ss = __ffma2_rn(ww2, make_float2(Sv[cur][4 * q + 2], Sv[cur][4 * q + 3]), make_float2(Sv[cur][4 * q], Sv[cur][4 * q + 1]));
               const float2 nr = __ffma2_rn(Rr, z2c, __ffma2_rn(Q, z2s, Ss)), nq = __ffma2_rn(Rr, nz2s, __ffma2_rn(Q, z2c, Cc));
               Rr = nr; Q = nq;
             }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           }
           asm volatile("tcgen05.fence::before_thread_sync;");
           __syncthreads();                       // the accumulators are free
@@ -395,13 +413,13 @@ k_synth_tc(const TcUnit *__restrict__ units, int nunits, const double *__restric
         }
         acc = fmaf(acc, unscale, prev);
         if (live) wave[U.wave_off + k] = acc;
-        if (sp == nsuper - 1) {      // max |w| of the epoch (tolerance of the zero-crossing searches in K6)
-          float m = live ? fabsf(acc) : 0.0f;
-#pragma unroll
-          for (int of = 16; of > 0; of >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, of));
-          if (lane == 0 && m > 0.0f) atomicMax(&epmax[U.epmax_idx], float_to_ordered(m));
-        }
+        if (live) unit_max = fmaxf(unit_max, fabsf(acc));
         TP(8)
+      }
+      if (sp == nsuper - 1) {        // max |w| of the epoch (tolerance of the zero-crossing searches in K6)
+#pragma unroll
+        for (int of = 16; of > 0; of >>= 1) unit_max = fmaxf(unit_max, __shfl_xor_sync(0xffffffffu, unit_max, of));
+        if (lane == 0 && unit_max > 0.0f) atomicMax(&epmax[U.epmax_idx], float_to_ordered(unit_max));
       }
       __syncthreads();               // sB, spc, smax are rewritten next: all MMAs completed above, every thread is past its reads
     }
