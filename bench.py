@@ -415,7 +415,10 @@ def main():
     value = audio_total * args.steps / dt
     e2e_f32 = audio_total * args.steps / dt_e2e
     e2e = audio_total * args.steps / dt_wav
-    # ---- roofline of the dominant kernel (K1 additive synthesis: FP32-pipe bound) ----
+    # ---- roofline of the dominant kernel: K1 additive synthesis ----
+    # Default build: k_synth_tc, the harmonic sum as an FP16 x FP16 -> FP32 contraction on tcgen05 (two-term
+    # split of both operands, three products): bound "tensor".  SGB_SYNTH=ffma selects the round-1 FP32-pipe
+    # kernel (blocked Clenshaw on FFMA2), whose roofline is the FP32 pipe.
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
@@ -424,6 +427,8 @@ def main():
     import ctypes
     fp32 = ctypes.c_double(0)
     L.sgb_measure_fp32_peak(ctypes.byref(fp32))
+    use_tc = os.environ.get('SGB_SYNTH', 'tc') != 'ffma'
+    kname = 'k_synth_tc' if use_tc else 'k_synth'
     ms_synth = float(stage_ms[_abi.T_NAMES.index('synth')])
     ms_filter = float(stage_ms[_abi.T_NAMES.index('filter')])
     ms_noise = float(stage_ms[_abi.T_NAMES.index('noise')])
@@ -431,7 +436,7 @@ def main():
     try:
         tj = json.load(open(os.path.join(ROOT, 'profiles', 'r02_traffic.json')))
         key = 'cfg%d_%d' % (args.config, len(calls))
-        traffic = tj.get(key, {}).get('k_synth', {}).get('dram_bytes_per_launch')
+        traffic = tj.get(key, {}).get(kname, {}).get('dram_bytes_per_launch')
         traffic_f = tj.get(key, {}).get('k_stft_filter', {}).get('dram_bytes_per_launch')
     except Exception:
         pass
@@ -444,16 +449,33 @@ def main():
     if ms_synth > 0 and info.synth_partials > 0:
         dense = 6.0 * info.synth_partials / (ms_synth * 1e-3) / 1e12
         ach = dense / ratio if ratio else dense
-        roofline = {'kernel': 'k_synth', 'bound': 'fp32', 'achieved': ach, 'peak': fp32.value,
-                    'unit': 'TFLOP/s', 'frac': ach / fp32.value if fp32.value else None, 'traffic': traffic,
-                    'peak_source': 'measured in this run: sgb_measure_fp32_peak (FFMA2 dependency chains); '
-                                   'MEASURED_PEAKS.json has no FP32 figure',
-                    'peak_nominal': nominal_fp32, 'frac_of_nominal': ach / nominal_fp32,
-                    'achieved_dense_rows': dense, 'frac_dense_rows': dense / fp32.value if fp32.value else None,
-                    'dense_over_reference_partials': ratio,
-                    'algorithmic': '6 flop per partial-sample x %d dense partial-samples per launch / %s '
-                                   '(dense / reference rows, from the parity sample)'
-                                   % (info.synth_partials, ('%.3f' % ratio) if ratio else 'n/a')}
+        algo = ('6 flop per partial-sample x %d dense partial-samples per launch / %s (dense / reference rows, '
+                'from the parity sample)' % (info.synth_partials, ('%.3f' % ratio) if ratio else 'n/a'))
+        if use_tc:
+            tpeak = peaks.get('bf16_tflops_sustained', 1400.0)      # timed inside a long step: the sustained figure
+            # executed on the tensor cores: {cos, sin} x {hi hi, lo hi, hi lo} x {Y, dY} = 12 MAC per dense
+            # partial-sample (row padding to 128 rows and sample padding to 128 per tile not counted)
+            executed = 24.0 * info.synth_partials / (ms_synth * 1e-3) / 1e12
+            roofline = {'kernel': kname, 'bound': 'tensor', 'achieved': ach, 'peak': tpeak, 'unit': 'TFLOP/s',
+                        'frac': ach / tpeak, 'traffic': traffic,
+                        'peak_source': ('MEASURED_PEAKS.json bf16_tflops_sustained (of measured)' if 'bf16_tflops_sustained' in peaks
+                                        else 'fallback 1400 TFLOP/s sustained (of fallback)'),
+                        'executed_tensor_tflops': executed, 'frac_executed': executed / tpeak,
+                        'fp32_pipe_peak': fp32.value, 'frac_of_fp32_pipe': ach / fp32.value if fp32.value else None,
+                        'achieved_dense_rows': dense, 'dense_over_reference_partials': ratio, 'algorithmic': algo,
+                        'note': 'achieved = the reference\'s 6 flop per partial-sample over the kernel time; the kernel '
+                                'executes 4x that on the tensor cores (executed_tensor_tflops) and is bound by the '
+                                'issue -> commit -> wait round trip of its small MMAs (about 500 cycles per 384-row '
+                                'pass, profiles/r02_mma_rate_micro.txt), not by tensor throughput; frac_of_fp32_pipe '
+                                '> 1 is why it left the FP32 pipe (round-1 kernel: SGB_SYNTH=ffma, 0.62 of that peak)'}
+        else:
+            roofline = {'kernel': kname, 'bound': 'fp32', 'achieved': ach, 'peak': fp32.value,
+                        'unit': 'TFLOP/s', 'frac': ach / fp32.value if fp32.value else None, 'traffic': traffic,
+                        'peak_source': 'measured in this run: sgb_measure_fp32_peak (FFMA2 dependency chains); '
+                                       'MEASURED_PEAKS.json has no FP32 figure',
+                        'peak_nominal': nominal_fp32, 'frac_of_nominal': ach / nominal_fp32,
+                        'achieved_dense_rows': dense, 'frac_dense_rows': dense / fp32.value if fp32.value else None,
+                        'dense_over_reference_partials': ratio, 'algorithmic': algo}
     hbm = peaks.get('hbm_gbs', 6650.0)
     roof_filter = None
     if ms_filter > 0 and info.filter_samples > 0:
@@ -481,7 +503,7 @@ def main():
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3, 'wall_ms_per_step': dt_wall / args.steps * 1e3,
             'timing': 'cuda events on the launching stream, max over ranks', 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 (f64 phase / control)', 'data': 'synthetic',
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 (f64 phase / control; K1 products as FP16 hi + lo pairs, FP32 accumulate)', 'data': 'synthetic',
             'config': {'workload': workloads.NAMES[args.config], 'calls_per_gpu': len(calls),
                        'audio_seconds_per_gpu_step': audio_s, 'l2': 'inputs and intermediates larger than L2',
                        'uniforms': 'float32'},
