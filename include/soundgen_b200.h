@@ -104,7 +104,10 @@ typedef struct sgb_envelope {
                             host ran the stochastic block sourceSpectrum.R:346-415);
                             2: a literal filter matrix (wl/2 x nc_fixed doubles, column-major)
                             at offset `formant_off` of the `pre` pool, e.g. generateNoise's
-                            filterNoise argument (R/source.R:66-68, :95-101)            */
+                            filterNoise argument (R/source.R:66-68, :95-101);
+                            3: deferred -- the tracks need the bout's STFT frame count, which
+                            the device decides: they arrive through sgb_batch_set_tracks()
+                            between sgb_batch_run_begin() and sgb_batch_run_finish()     */
   int64_t formant_off;   /* offset into `formant_index` (one {off,n} entry per formant) */
   int32_t mouth_n;       /* mouthAnchors: number of anchors, 0 = NA                   */
   int32_t nc_fixed;      /* >0: number of columns; 0: one column per STFT frame       */

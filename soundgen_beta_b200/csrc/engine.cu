@@ -27,7 +27,8 @@ void launch_fp32_peak(float2 *, int, int, int);
 #define ENV_MAXK_HOST 64
 void launch_synth(const SynthTile *, int, const sgb_syllable *, const SylCtrl *, const SylLayout *, const Pools &,
                   const float4 *, float *, int *, cudaStream_t);
-void launch_build_tiles_tc(const sgb_syllable *, const SylCtrl *, int, const SylLayout *, const Pools &, TcUnit *, cudaStream_t);
+void launch_build_tiles_tc(const sgb_syllable *, const SylCtrl *, int, const SylLayout *, const Pools &, TcUnit *, SynthTile *, int, int,
+                           cudaStream_t);
 cudaError_t launch_synth_tc(const TcUnit *, int, const Pools &, const float4 *, float *, int *, cudaStream_t);
 int synth_tc_timeout_flag();
 void launch_compose(const sgb_syllable *, int, SylCtrl *, const SylLayout *, const Pools &, const double *,
@@ -87,6 +88,14 @@ static int fail(int code, const char *fmt, ...) {
       cudaGetLastError();   /* a reported error must not resurface in a later, unrelated call */ \
       return fail(SGB_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); \
     }                                                                                          \
+  } while (0)
+
+// a launch with an invalid configuration only shows in cudaGetLastError(): name the kernel instead of letting
+// the next checked call inherit it
+#define CKL(what)                                                                                   \
+  do {                                                                                              \
+    cudaError_t e_ = cudaGetLastError();                                                            \
+    if (e_ != cudaSuccess) return fail(SGB_ERR_CUDA, "%s: launch failed: %s", what, cudaGetErrorString(e_)); \
   } while (0)
 
 struct SylSummary { int32_t status, out_len, n_up, nGC, z_used, pad; };
@@ -716,6 +725,7 @@ int sgb_batch_run_begin(sgb_batch *b) {
   CK(cudaMemsetAsync(d_tot, 0, 64, st));
   launch_control(d_syl, S, b->d_pitch.as<double>(), b->d_anchors.as<double>(), b->d_z.as<double>(), P, d_ctrl, d_lay,
                  d_tot, st);
+  CKL("launch_control");
   launches += 2;
   CK(b->h_tot.ensure(64));
   CK(b->h_summary.ensure(sizeof(SylSummary) * (size_t)S));
@@ -739,30 +749,41 @@ int sgb_batch_run_begin(sgb_batch *b) {
   // ---- K3 amplitude matrices ----
   launch_tiles_amp(d_syl, S, d_ctrl, d_lay, P, b->d_tiles.as<SynthTile>(), d_tot, b->d_amp.as<double>(),
                    b->d_amp32.as<float4>(), st);
+  CKL("launch_tiles_amp");
   launches += 2;
   CK(cudaEventRecord(ev[2], st)); trace_mark(b, 2);
   // ---- K1 synthesis ----
   CK(cudaMemsetAsync(b->d_epmax.p, 0, 4 * (size_t)S * SGB_MAX_EPOCHS, st));
-  // SGB_SYNTH=ffma selects the FP32-pipe kernel of round 1 (blocked Clenshaw on FFMA2); the default is the
-  // tensor-core kernel (tcgen05 kind::tf32, 3xTF32, TMEM accumulators)
-  static const bool use_tc = [] { const char *e = getenv("SGB_SYNTH"); return !(e && !strcmp(e, "ffma")); }();
+  // K1.  Epochs with many rows go to the tensor-core kernel (tcgen05 kind::f16, FP16 hi + lo operands, TMEM
+  // accumulators): per 128-sample tile it pays a fixed price (16 trig rows per sample, one MMA round trip per 384
+  // rows), which the FP32-pipe kernel of round 1 (blocked Clenshaw on FFMA2, one step per row) undercuts when an
+  // epoch has few rows.  SGB_SYNTH=ffma / tc force one kernel; SGB_SYNTH_MIN_ROWS moves the switch.
+  static const int tc_min_rows = [] {
+    const char *e = getenv("SGB_SYNTH");
+    if (e && !strcmp(e, "ffma")) return 1 << 30;
+    if (e && !strcmp(e, "tc")) return 0;
+    const char *m = getenv("SGB_SYNTH_MIN_ROWS");
+    return m ? atoi(m) : 224;
+  }();
   const int64_t n_tiles_tc = tot[7];
-  if (use_tc) {
-    if (n_tiles_tc > 2000000000LL) return fail(SGB_ERR_UNSUPPORTED, "batch too large: %lld synthesis tiles", (long long)n_tiles_tc);
+  if (tc_min_rows < (1 << 30)) {
+    if (n_tiles_tc > 2000000000LL) return fail(SGB_ERR_UNSUPPORTED, "batch too large: %lld synthesis units", (long long)n_tiles_tc);
     CK(b->d_tiles_tc.ensure(sizeof(TcUnit) * (size_t)std::max<int64_t>(n_tiles_tc, 1)));
-    launch_build_tiles_tc(d_syl, d_ctrl, S, d_lay, P, b->d_tiles_tc.as<TcUnit>(), st);
+    launch_build_tiles_tc(d_syl, d_ctrl, S, d_lay, P, b->d_tiles_tc.as<TcUnit>(), b->d_tiles.as<SynthTile>(), (int)n_tiles, tc_min_rows, st);
+    CKL("launch_build_tiles_tc");
     CK(launch_synth_tc(b->d_tiles_tc.as<TcUnit>(), (int)n_tiles_tc, P, b->d_amp32.as<float4>(), b->d_wave.as<float>(),
                        b->d_epmax.as<int>(), st));
-    if (n_tiles_tc > 0) launches += 2;
-  } else {
+    if (n_tiles_tc > 0) launches += 2 + (tc_min_rows > 0 ? 1 : 0);
+  }
+  if (tc_min_rows > 0) {
     launch_synth(b->d_tiles.as<SynthTile>(), (int)n_tiles, d_syl, d_ctrl, d_lay, P, b->d_amp32.as<float4>(),
                  b->d_wave.as<float>(), b->d_epmax.as<int>(), st);
+    CKL("launch_synth");
     if (n_tiles > 0) launches++;
   }
-  CK(cudaEventRecord(ev[3], st)); trace_mark(b, 3);
-  // ---- K6 compose ----
   launch_compose(d_syl, S, d_ctrl, d_lay, P, b->d_amp.as<double>(), b->d_wave.as<float>(), b->d_raw.as<float>(),
                  b->d_anchors.as<double>(), b->d_pitch.as<double>(), b->d_epmax.as<int>(), st);
+  CKL("launch_compose");
   k_summary<<<(S + 255) / 256, 256, 0, st>>>(d_ctrl, S, b->d_summary.as<SylSummary>());
   launches += 2;
   b->summary.resize(S);
@@ -1058,6 +1079,7 @@ int sgb_batch_run_finish(sgb_batch *b, sgb_run_info *info_out) {
   // ---- voiced syllables -> sound ----
   launch_place_voiced(d_syl, S, d_ctrl, d_lay, b->d_place.as<SylPlace>(), P, b->d_raw.as<float>(),
                       b->d_sound.as<float>(), chunks, st);
+  CKL("launch_place_voiced");
   launches++;
   if (b->keep_voiced) {
     CK(b->d_voiced.ensure(4 * (size_t)(sound_total + 64)));
@@ -1068,24 +1090,30 @@ int sgb_batch_run_finish(sgb_batch *b, sgb_run_info *info_out) {
   launch_env_tracks(b->d_envinst.as<EnvInst>(), (int)envinst.size(), b->d_envs.as<sgb_envelope>(),
                     b->d_frefs.as<sgb_formant_ref>(), b->d_formants.as<double>(), b->d_anchors.as<double>(),
                     b->d_trk.as<double>(), b->d_mouth.as<double>(), st);
+  CKL("launch_env_tracks");
   launch_envelope_f32(b->d_envinst.as<EnvInst>(), (int)envinst.size(), max_nc, b->d_envs.as<sgb_envelope>(),
                       b->d_frefs.as<sgb_formant_ref>(), b->d_formants.as<double>(), b->d_formants_late.as<double>(), b->d_trk.as<double>(),
                       b->d_mouth.as<double>(), b->d_pre.as<double>(), b->d_env.as<float>(), st);
+  CKL("launch_envelope_f32");
   if (!envinst.empty()) launches += 2;
   CK(cudaEventRecord(ev[6], st)); trace_mark(b, 6);
   // ---- K5 noise ----
   if (!nsegs.empty()) {
     for (auto &gr : ngroups) {
       if (gr.smem > 226 * 1024) return fail(SGB_ERR_UNSUPPORTED, "noise window too long for shared memory (%zu bytes)", gr.smem);
-      CK(launch_stft(1, b->u_is_float, gr.spec, b->d_nsegs.as<FftSeg>() + gr.begin, gr.end - gr.begin,
-                     b->d_njobs.as<FftJob>(), b->d_plans.as<FftPlan>(), b->d_tw.as<float2>(), b->d_win.as<float>(),
-                     nullptr, b->d_u.p, b->d_env.as<float>(), b->d_noise_raw.as<float>(), b->d_max.as<int>(),
-                     gr.smem, st));
+      cudaError_t le = launch_stft(1, b->u_is_float, gr.spec, b->d_nsegs.as<FftSeg>() + gr.begin, gr.end - gr.begin,
+                                   b->d_njobs.as<FftJob>(), b->d_plans.as<FftPlan>(), b->d_tw.as<float2>(), b->d_win.as<float>(),
+                                   nullptr, b->d_u.p, b->d_env.as<float>(), b->d_noise_raw.as<float>(), b->d_max.as<int>(),
+                                   gr.smem, st);
+      if (le != cudaSuccess)
+        return fail(SGB_ERR_CUDA, "noise STFT launch failed (plan group %d, %d segments, %zu bytes of shared memory): %s", gr.spec,
+                    gr.end - gr.begin, gr.smem, cudaGetErrorString(le));
       launches++;
     }
     launch_noise_final(b->d_noises.as<sgb_noise>(), NN, b->d_nl.as<NoiseLayout>(), b->d_anchors.as<double>(),
                        b->d_pre.as<double>(), b->d_max.as<int>(), NB, b->d_noise_raw.as<float>(),
                        b->d_noise_fin.as<float>(), 16, st);
+    CKL("launch_noise_final");
     launches += 1;
   }
   CK(cudaEventRecord(ev[7], st)); trace_mark(b, 7);
@@ -1093,6 +1121,7 @@ int sgb_batch_run_finish(sgb_batch *b, sgb_run_info *info_out) {
   launch_sound_mix(b->d_bouts.as<sgb_bout>(), NB, b->d_bl.as<BoutLayout>(), b->d_noises.as<sgb_noise>(),
                    b->d_nl.as<NoiseLayout>(), b->d_anchors.as<double>(), b->d_noise_fin.as<float>(),
                    b->d_sound.as<float>(), chunks, st);
+  CKL("launch_sound_mix");
   launches++;
   CK(cudaEventRecord(ev[8], st)); trace_mark(b, 8);
   // ---- K2 filter ----
@@ -1108,6 +1137,7 @@ int sgb_batch_run_finish(sgb_batch *b, sgb_run_info *info_out) {
   launch_finalize(0, b->d_bouts.as<sgb_bout>(), NB, b->d_bl.as<BoutLayout>(), b->d_noises.as<sgb_noise>(),
                   b->d_nl.as<NoiseLayout>(), b->d_sound.as<float>(), b->d_filt.as<float>(),
                   b->d_noise_fin.as<float>(), b->d_max.as<int>(), b->d_out.p, chunks, st);
+  CKL("launch_finalize");
   launches++;
   CK(cudaEventRecord(ev[10], st)); trace_mark(b, 10);
   b->where = 3;
@@ -1469,6 +1499,7 @@ int sgb_get_spectral_envelope(int32_t nr, int32_t nc, const sgb_envelope *env, c
     CK(dT.ensure(8 * (size_t)std::max(1, nc * E.n_formants * 3))); CK(dM.ensure(8 * (size_t)nc));
     launch_env_tracks(dI.as<EnvInst>(), 1, dE.as<sgb_envelope>(), dR.as<sgb_formant_ref>(), dF.as<double>(),
                       dA.as<double>(), dT.as<double>(), dM.as<double>(), 0);
+    CKL("launch_env_tracks");
     launch_envelope_f64(dI.as<EnvInst>(), 1, nc, dE.as<sgb_envelope>(), dR.as<sgb_formant_ref>(), dF.as<double>(),
                         nullptr, dT.as<double>(), dM.as<double>(), nullptr, dO.as<double>(), 0);
     CK(cudaGetLastError());

@@ -307,18 +307,18 @@ __global__ void __launch_bounds__(256)
 k_place_voiced(const sgb_syllable *__restrict__ syl, int S, const SylCtrl *__restrict__ ctrl,
                const SylLayout *__restrict__ lay, const SylPlace *__restrict__ place, Pools P,
                const float *__restrict__ raw, float *__restrict__ sound) {
-  const int s = blockIdx.y;
+  const int s = blockIdx.x;
   const SylCtrl &C = ctrl[s];
   const sgb_syllable &sp = syl[s];
   const int L = place[s].len;
   float *dst = sound + place[s].dst_off;
   const float *src = raw + lay[s].raw_off;
   if (sp.kind == 0 || C.status != SGB_OK) {
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < L; k += gridDim.x * blockDim.x) dst[k] = 0.0f;
+    for (int k = blockIdx.y * blockDim.x + threadIdx.x; k < L; k += gridDim.y * blockDim.x) dst[k] = 0.0f;
     return;
   }
   if (sp.kind == 2) {
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < L; k += gridDim.x * blockDim.x) dst[k] = src[k];
+    for (int k = blockIdx.y * blockDim.x + threadIdx.x; k < L; k += gridDim.y * blockDim.x) dst[k] = src[k];
     return;
   }
   const double inv_max = C.raw_max;
@@ -334,7 +334,7 @@ k_place_voiced(const sgb_syllable *__restrict__ syl, int S, const SylCtrl *__res
   const double *drift = P.drift + o;
   const int G = C.nGC;
 #pragma unroll 4
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < L; k += gridDim.x * blockDim.x) {
+  for (int k = blockIdx.y * blockDim.x + threadIdx.x; k < L; k += gridDim.y * blockDim.x) {
     double v = (double)src[k] / inv_max;
     if (lf > 0) {
       if (k < lf) v = v * r_seq_at(0.0, 1.0, lf, k);                        // fade-in
@@ -364,6 +364,6 @@ void launch_place_voiced(const sgb_syllable *syl, int S, const SylCtrl *ctrl, co
                          const SylPlace *place, const Pools &P, const float *raw, float *sound,
                          int chunks, cudaStream_t st) {
   if (S <= 0) return;
-  dim3 g(chunks, S);
+  dim3 g(S, chunks);   // objects on x: more than 65535 syllables are routine in a preset sweep
   k_place_voiced<<<g, 256, 0, st>>>(syl, S, ctrl, lay, place, P, raw, sound);
 }

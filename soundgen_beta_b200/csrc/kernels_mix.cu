@@ -11,7 +11,7 @@ k_noise_final(const sgb_noise *__restrict__ noises, const NoiseLayout *__restric
               const double *__restrict__ anchors, const double *__restrict__ pre,
               const int *__restrict__ maxpool, int max_base, const float *__restrict__ raw,
               float *__restrict__ fin) {
-  const int n = blockIdx.y;
+  const int n = blockIdx.x;
   const sgb_noise N = noises[n];
   const int L = N.len;
   const float mx = ordered_to_float(maxpool[max_base + n]);
@@ -28,7 +28,7 @@ k_noise_final(const sgb_noise *__restrict__ noises, const NoiseLayout *__restric
                       false, N.anchor_method);
     __syncthreads();
   }
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < L; k += gridDim.x * blockDim.x) {
+  for (int k = blockIdx.y * blockDim.x + threadIdx.x; k < L; k += gridDim.y * blockDim.x) {
     double c = (N.strength_pre_off >= 0) ? pre[N.strength_pre_off + k] : contour_eval(&T, L, k);
     double v = (double)src[k] / (double)mx * exp2(c / 10.0);
     if (lf > 0) {
@@ -48,7 +48,7 @@ k_sound_mix(const sgb_bout *__restrict__ bouts, const BoutLayout *__restrict__ b
             const sgb_noise *__restrict__ noises, const NoiseLayout *__restrict__ nl,
             const double *__restrict__ anchors, const float *__restrict__ noise_fin,
             float *__restrict__ sound) {
-  const int b = blockIdx.y;
+  const int b = blockIdx.x;
   const sgb_bout B = bouts[b];
   const BoutLayout L = bl[b];
   float *snd = sound + L.sound_off;
@@ -64,7 +64,7 @@ k_sound_mix(const sgb_bout *__restrict__ bouts, const BoutLayout *__restrict__ b
                       -B.throwaway, false, B.aglobal_method);
     __syncthreads();
   }
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < L.sound_len; k += gridDim.x * blockDim.x) {
+  for (int k = blockIdx.y * blockDim.x + threadIdx.x; k < L.sound_len; k += gridDim.y * blockDim.x) {
     float v = snd[k];
     for (int n = B.noise_begin; n < B.noise_end; n++) {
       if (noises[n].mix != 0) continue;
@@ -89,7 +89,7 @@ k_finalize(const sgb_bout *__restrict__ bouts, const BoutLayout *__restrict__ bl
            const float *__restrict__ sound, const float *__restrict__ filt,
            const float *__restrict__ noise_fin, const int *__restrict__ maxpool,
            OutT *__restrict__ out) {
-  const int b = blockIdx.y;
+  const int b = blockIdx.x;
   const sgb_bout B = bouts[b];
   const BoutLayout L = bl[b];
   const float *src = L.bypass ? (sound + L.sound_off) : (filt + L.filt_off);
@@ -109,7 +109,7 @@ k_finalize(const sgb_bout *__restrict__ bouts, const BoutLayout *__restrict__ bl
     bmax = 1.0 / (1.0 + exp(-to * slope));
   }
 #pragma unroll 4
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < L.final_len; k += gridDim.x * blockDim.x) {
+  for (int k = blockIdx.y * blockDim.x + threadIdx.x; k < L.final_len; k += gridDim.y * blockDim.x) {
     double v = 0.0;
     int rel = k - L.final_shift;
     if (rel >= 0 && rel < L.filt_len) v = (double)src[rel] / mx;
@@ -134,7 +134,7 @@ void launch_noise_final(const sgb_noise *noises, int n_noise, const NoiseLayout 
                         const double *pre, const int *maxpool, int max_base, const float *raw, float *fin,
                         int chunks, cudaStream_t st) {
   if (n_noise <= 0) return;
-  dim3 g(chunks, n_noise);
+  dim3 g(n_noise, chunks);
   k_noise_final<<<g, 256, 0, st>>>(noises, nl, anchors, pre, maxpool, max_base, raw, fin);
 }
 
@@ -142,7 +142,7 @@ void launch_sound_mix(const sgb_bout *bouts, int n_bouts, const BoutLayout *bl, 
                       const NoiseLayout *nl, const double *anchors, const float *noise_fin, float *sound,
                       int chunks, cudaStream_t st) {
   if (n_bouts <= 0) return;
-  dim3 g(chunks, n_bouts);
+  dim3 g(n_bouts, chunks);
   k_sound_mix<<<g, 256, 0, st>>>(bouts, bl, noises, nl, anchors, noise_fin, sound);
 }
 
@@ -150,7 +150,7 @@ void launch_finalize(int f64, const sgb_bout *bouts, int n_bouts, const BoutLayo
                      const sgb_noise *noises, const NoiseLayout *nl, const float *sound, const float *filt,
                      const float *noise_fin, const int *maxpool, void *out, int chunks, cudaStream_t st) {
   if (n_bouts <= 0) return;
-  dim3 g(chunks, n_bouts);
+  dim3 g(n_bouts, chunks);
   if (f64) k_finalize<double><<<g, 256, 0, st>>>(bouts, bl, noises, nl, sound, filt, noise_fin, maxpool, (double *)out);
   else k_finalize<float><<<g, 256, 0, st>>>(bouts, bl, noises, nl, sound, filt, noise_fin, maxpool, (float *)out);
 }

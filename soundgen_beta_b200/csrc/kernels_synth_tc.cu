@@ -90,7 +90,8 @@ __device__ __forceinline__ void tc_split(float x, uint32_t &hi, uint32_t &lo) {
 
 // Work list: one unit per interval of approx() of every epoch.  One thread per syllable; intervals without
 // samples get kbeg == kend.
-__global__ void k_build_units_tc(const sgb_syllable *syl, const SylCtrl *ctrl, int S, const SylLayout *lay, const Pools P, TcUnit *units) {
+__global__ void k_build_units_tc(const sgb_syllable *syl, const SylCtrl *ctrl, int S, const SylLayout *lay, const Pools P, TcUnit *units,
+                                 int min_rows) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= S) return;
   const SylCtrl &C = ctrl[s];
@@ -131,7 +132,7 @@ __global__ void k_build_units_tc(const sgb_syllable *syl, const SylCtrl *ctrl, i
       U.pc_off = o;
       U.x_first = x_first; U.by = by; U.x_last = x_last;
       U.inv_sr_np1 = 1.0 / (syl[s].samplingRate * (double)(nsub + 1));
-      U.Ne = Ne; U.kbeg = kcur; U.kend = kend; U.xg = gcup[g_first + i]; U.xn = gcup[g_first + i + 1];
+      U.Ne = Ne; U.kbeg = kcur; U.kend = (J >= min_rows) ? kend : kcur;     // few rows: the FP32-pipe kernel's epoch U.xg = gcup[g_first + i]; U.xn = gcup[g_first + i + 1];
       U.a_lo = a; U.G = G; U.J = J; U.epmax_idx = s * SGB_MAX_EPOCHS + e; U.pad = 0;
       if (t < t_end) units[t++] = U;
       kcur = kend;
@@ -429,9 +430,19 @@ k_synth_tc(const TcUnit *__restrict__ units, int nunits, const double *__restric
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(128));
 }
 
-void launch_build_tiles_tc(const sgb_syllable *syl, const SylCtrl *ctrl, int S, const SylLayout *lay, const Pools &P, TcUnit *units, cudaStream_t st) {
+// FP32-pipe tiles of the epochs the tensor-core kernel takes are switched off (syl = -1)
+__global__ void k_mark_tiles_ffma(SynthTile *tiles, int n_tiles, const SylCtrl *ctrl, int min_rows) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tiles) return;
+  const int s = tiles[t].syl;
+  if (s >= 0 && ctrl[s].ep_rows[tiles[t].epoch] >= min_rows) tiles[t].syl = -1;
+}
+
+void launch_build_tiles_tc(const sgb_syllable *syl, const SylCtrl *ctrl, int S, const SylLayout *lay, const Pools &P, TcUnit *units,
+                           SynthTile *tiles_ffma, int n_tiles_ffma, int min_rows, cudaStream_t st) {
   if (S <= 0) return;
-  k_build_units_tc<<<(S + 127) / 128, 128, 0, st>>>(syl, ctrl, S, lay, P, units);
+  k_build_units_tc<<<(S + 127) / 128, 128, 0, st>>>(syl, ctrl, S, lay, P, units, min_rows);
+  if (min_rows > 0 && n_tiles_ffma > 0) k_mark_tiles_ffma<<<(n_tiles_ffma + 255) / 256, 256, 0, st>>>(tiles_ffma, n_tiles_ffma, ctrl, min_rows);
 }
 
 cudaError_t launch_synth_tc(const TcUnit *units, int n_units, const Pools &P, const float4 *amp, float *wave, int *epmax, cudaStream_t st) {

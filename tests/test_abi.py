@@ -36,6 +36,7 @@ def test_sass_has_tma_and_no_library_fft():
     if not sass:
         pytest.skip('cuobjdump unavailable')
     assert 'UBLKCP' in sass            # cp.async.bulk (TMA) staging in the fused filter
+    assert 'UTCHMMA' in sass and 'LDTM' in sass and 'STTM' in sass   # tcgen05.mma / TMEM in the additive synthesis (K1)
     assert 'sm_100a' in sass or 'SM100' in sass.upper() or 'sm_100' in sass
     ldd = subprocess.run(['ldd', so], capture_output=True, text=True).stdout
     assert 'cufft' not in ldd and 'torch' not in ldd
