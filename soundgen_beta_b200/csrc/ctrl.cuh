@@ -449,7 +449,9 @@ SGB_HD bool ctrl_rowkept(const sgb_syllable &sp, const SylArrays &A, const SylCt
 }
 
 // sizes of the dense per-epoch amplitude matrices and of the K1 work list
-SGB_HD void ctrl_sizes(SylArrays &A, SylCtrl &C, int tile) {
+// tc_min_rows: epochs with at least that many rows are synthesised by the tensor-core kernel (work list: one unit
+// per interval of approx()), the others by the FP32-pipe kernel (work list: tiles of `tile` samples)
+SGB_HD void ctrl_sizes(SylArrays &A, SylCtrl &C, int tile, int tc_min_rows = 1 << 30) {
   int64_t amp = 0, wave = 0;
   int tiles = 0;
   for (int e = 0; e < C.nEpochs; e++) {
@@ -463,14 +465,15 @@ SGB_HD void ctrl_sizes(SylArrays &A, SylCtrl &C, int tile) {
     C.ep_wave_off[e] = wave;
     amp += (int64_t)rows * Ge;
     wave += ((int64_t)Ne + 3) & ~(int64_t)3;
-    tiles += (Ne + tile - 1) / tile;
+    if (rows < tc_min_rows) tiles += (Ne + tile - 1) / tile;
   }
   C.amp_elems = amp;
   C.wave_elems = wave;
   C.tiles = tiles;
   // tensor-core work list: one unit per interval of approx() of every epoch
   int tc = 0;
-  for (int e = 0; e < C.nEpochs; e++) tc += C.ep_end[e] - C.ep_start[e];
+  for (int e = 0; e < C.nEpochs; e++)
+    if (C.ep_rows[e] >= tc_min_rows) tc += C.ep_end[e] - C.ep_start[e];
   C.tiles_tc = tc;
 }
 

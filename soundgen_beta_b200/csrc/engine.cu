@@ -27,8 +27,8 @@ void launch_fp32_peak(float2 *, int, int, int);
 #define ENV_MAXK_HOST 64
 void launch_synth(const SynthTile *, int, const sgb_syllable *, const SylCtrl *, const SylLayout *, const Pools &,
                   const float4 *, float *, int *, cudaStream_t);
-void launch_build_tiles_tc(const sgb_syllable *, const SylCtrl *, int, const SylLayout *, const Pools &, TcUnit *, SynthTile *, int, int,
-                           cudaStream_t);
+void launch_build_tiles_tc(const sgb_syllable *, const SylCtrl *, int, const SylLayout *, const Pools &, TcUnit *, cudaStream_t);
+void synth_min_rows_set(int);
 cudaError_t launch_synth_tc(const TcUnit *, int, const Pools &, const float4 *, float *, int *, cudaStream_t);
 int synth_tc_timeout_flag();
 void launch_compose(const sgb_syllable *, int, SylCtrl *, const SylLayout *, const Pools &, const double *,
@@ -723,6 +723,14 @@ int sgb_batch_run_begin(sgb_batch *b) {
 
   // ---- K0 control + size scan ----
   CK(cudaMemsetAsync(d_tot, 0, 64, st));
+  static const int tc_min_rows = [] {
+    const char *e = getenv("SGB_SYNTH");
+    if (e && !strcmp(e, "ffma")) return 1 << 30;
+    if (e && !strcmp(e, "tc")) return 0;
+    const char *m = getenv("SGB_SYNTH_MIN_ROWS");
+    return m ? atoi(m) : 224;
+  }();
+  synth_min_rows_set(tc_min_rows);
   launch_control(d_syl, S, b->d_pitch.as<double>(), b->d_anchors.as<double>(), b->d_z.as<double>(), P, d_ctrl, d_lay,
                  d_tot, st);
   CKL("launch_control");
@@ -758,22 +766,15 @@ int sgb_batch_run_begin(sgb_batch *b) {
   // accumulators): per 128-sample tile it pays a fixed price (16 trig rows per sample, one MMA round trip per 384
   // rows), which the FP32-pipe kernel of round 1 (blocked Clenshaw on FFMA2, one step per row) undercuts when an
   // epoch has few rows.  SGB_SYNTH=ffma / tc force one kernel; SGB_SYNTH_MIN_ROWS moves the switch.
-  static const int tc_min_rows = [] {
-    const char *e = getenv("SGB_SYNTH");
-    if (e && !strcmp(e, "ffma")) return 1 << 30;
-    if (e && !strcmp(e, "tc")) return 0;
-    const char *m = getenv("SGB_SYNTH_MIN_ROWS");
-    return m ? atoi(m) : 224;
-  }();
   const int64_t n_tiles_tc = tot[7];
   if (tc_min_rows < (1 << 30)) {
     if (n_tiles_tc > 2000000000LL) return fail(SGB_ERR_UNSUPPORTED, "batch too large: %lld synthesis units", (long long)n_tiles_tc);
     CK(b->d_tiles_tc.ensure(sizeof(TcUnit) * (size_t)std::max<int64_t>(n_tiles_tc, 1)));
-    launch_build_tiles_tc(d_syl, d_ctrl, S, d_lay, P, b->d_tiles_tc.as<TcUnit>(), b->d_tiles.as<SynthTile>(), (int)n_tiles, tc_min_rows, st);
+    launch_build_tiles_tc(d_syl, d_ctrl, S, d_lay, P, b->d_tiles_tc.as<TcUnit>(), st);
     CKL("launch_build_tiles_tc");
     CK(launch_synth_tc(b->d_tiles_tc.as<TcUnit>(), (int)n_tiles_tc, P, b->d_amp32.as<float4>(), b->d_wave.as<float>(),
                        b->d_epmax.as<int>(), st));
-    if (n_tiles_tc > 0) launches += 2 + (tc_min_rows > 0 ? 1 : 0);
+    if (n_tiles_tc > 0) launches += 2;
   }
   if (tc_min_rows > 0) {
     launch_synth(b->d_tiles.as<SynthTile>(), (int)n_tiles, d_syl, d_ctrl, d_lay, P, b->d_amp32.as<float4>(),
@@ -781,6 +782,8 @@ int sgb_batch_run_begin(sgb_batch *b) {
     CKL("launch_synth");
     if (n_tiles > 0) launches++;
   }
+  CK(cudaEventRecord(ev[3], st)); trace_mark(b, 3);
+  // ---- K6 compose ----
   launch_compose(d_syl, S, d_ctrl, d_lay, P, b->d_amp.as<double>(), b->d_wave.as<float>(), b->d_raw.as<float>(),
                  b->d_anchors.as<double>(), b->d_pitch.as<double>(), b->d_epmax.as<int>(), st);
   CKL("launch_compose");

@@ -8,7 +8,7 @@
                           // part, so what matters is how many syllables are resident per SM
 __global__ void __launch_bounds__(CTRL_THREADS, 16)
 k_control(const sgb_syllable *syl, int S, const double *pitch, const double *anchors, const double *z,
-          Pools P, SylCtrl *ctrl) {
+          Pools P, SylCtrl *ctrl, int tc_min_rows) {
   int s = blockIdx.x;
   if (s >= S) return;
   const sgb_syllable sp = syl[s];
@@ -118,7 +118,7 @@ k_control(const sgb_syllable *syl, int S, const double *pitch, const double *anc
     for (int h = 1; h <= nH; h++) if (A.rowmap[h - 1]) A.rowmap[kept++] = h;
     C.rows_kept = kept;
     if (kept < 1) C.status = SGB_ERR_SYNTH;
-    ctrl_sizes(A, C, SYNTH_TILE);
+    ctrl_sizes(A, C, SYNTH_TILE, tc_min_rows);
     if (C.status != SGB_OK) { C.tiles = 0; C.tiles_tc = 0; C.amp_elems = 0; C.wave_elems = 0; }
   }
 }
@@ -166,7 +166,7 @@ k_scan_sizes(const SylCtrl *ctrl, int S, SylLayout *lay, int64_t *totals) {
 // K1 work list: one thread per syllable writes its (epoch, k0) tiles; also accumulates the
 // algorithmic work counters (rows x samples) used for the K1 roofline.
 __global__ void k_build_tiles(const SylCtrl *ctrl, int S, const SylLayout *lay, const Pools P,
-                              SynthTile *tiles, int64_t *totals) {
+                              SynthTile *tiles, int64_t *totals, int tc_min_rows) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= S) return;
   const SylCtrl &C = ctrl[s];
@@ -185,7 +185,7 @@ __global__ void k_build_tiles(const SylCtrl *ctrl, int S, const SylLayout *lay, 
     const double by = (x_last - x_first) / (double)(Ne - 1);
     const int nknots = g_last - g_first + 1;
     int lo = 0;                                 // amplitude interval of approx(): largest lo <= nknots-2 with knot <= v
-    for (int k0 = 0; k0 < Ne; k0 += SYNTH_TILE) {
+    for (int k0 = 0; k0 < Ne && C.ep_rows[e] < tc_min_rows; k0 += SYNTH_TILE) {     // the other epochs: k_synth_tc
       const double v = (k0 >= Ne - 1) ? x_last : (x_first + (double)k0 * by);
       while (lo < nknots - 2 && v >= (double)gcup[g_first + lo + 1]) lo++;
       const double u = (double)(x_first_i + k0);
@@ -423,14 +423,17 @@ k_rolloff_api(const double *p, int G, int nH, const double *ro, int n_ro, const 
 }
 
 // ---- host launchers (kernels stay private to this translation unit) ----
+static int g_tc_min_rows = 1 << 30;      // K1 dispatch (engine.cu): epochs with >= this many rows go to k_synth_tc
+void synth_min_rows_set(int v) { g_tc_min_rows = v; }
+int synth_min_rows() { return g_tc_min_rows; }
 void launch_control(const sgb_syllable *syl, int S, const double *pitch, const double *anchors, const double *z,
                     const Pools &P, SylCtrl *ctrl, SylLayout *lay, int64_t *totals, cudaStream_t st) {
-  k_control<<<S, CTRL_THREADS, 0, st>>>(syl, S, pitch, anchors, z, P, ctrl);
+  k_control<<<S, CTRL_THREADS, 0, st>>>(syl, S, pitch, anchors, z, P, ctrl, g_tc_min_rows);
   k_scan_sizes<<<1, 1024, 0, st>>>(ctrl, S, lay, totals);
 }
 void launch_tiles_amp(const sgb_syllable *syl, int S, const SylCtrl *ctrl, const SylLayout *lay, const Pools &P,
                       SynthTile *tiles, int64_t *totals, double *amp, float4 *amp32, cudaStream_t st) {
-  k_build_tiles<<<(S + 127) / 128, 128, 0, st>>>(ctrl, S, lay, P, tiles, totals);
+  k_build_tiles<<<(S + 127) / 128, 128, 0, st>>>(ctrl, S, lay, P, tiles, totals, g_tc_min_rows);
   dim3 g(S, S >= 2048 ? 1 : (S >= 256 ? 4 : 16));
   k_amp<<<g, 256, 0, st>>>(syl, S, ctrl, lay, P, amp, amp32);
 }

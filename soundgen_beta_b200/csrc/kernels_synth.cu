@@ -87,7 +87,6 @@ k_synth(const SynthTile *__restrict__ tiles, const sgb_syllable *__restrict__ sy
   __shared__ float4 sStage[SYNTH_WARPS][2][SYNTH_STAGE];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const SynthTile T = tiles[blockIdx.x];
-  if (T.syl < 0) return;               // an epoch that the tensor-core kernel takes (k_mark_tiles_ffma)
   const int s = T.syl, e = T.epoch;
   const SylCtrl &C = ctrl[s];
   const int64_t o = P.gc_off[s];

@@ -112,6 +112,10 @@ __global__ void k_build_units_tc(const sgb_syllable *syl, const SylCtrl *ctrl, i
     const int nknots = g_last - g_first + 1;
     const int nsub = C.vf_active ? C.ep_nsub[e] : 0;
     const int J = C.ep_rows[e];
+    if (J < min_rows) {                    // few rows: the FP32-pipe kernel's epoch (no units were reserved for it)
+      while (a > 0 && (double)gcup[g_last] < kt[a]) a--;
+      continue;
+    }
     auto vfun = [&](int k) { return (k >= Ne - 1) ? x_last : (x_first + (double)k * by); };
     int kcur = 0;
     for (int i = 0; i <= nknots - 2; i++) {
@@ -132,7 +136,8 @@ __global__ void k_build_units_tc(const sgb_syllable *syl, const SylCtrl *ctrl, i
       U.pc_off = o;
       U.x_first = x_first; U.by = by; U.x_last = x_last;
       U.inv_sr_np1 = 1.0 / (syl[s].samplingRate * (double)(nsub + 1));
-      U.Ne = Ne; U.kbeg = kcur; U.kend = (J >= min_rows) ? kend : kcur;     // few rows: the FP32-pipe kernel's epoch U.xg = gcup[g_first + i]; U.xn = gcup[g_first + i + 1];
+      U.Ne = Ne; U.kbeg = kcur; U.kend = kend;
+      U.xg = gcup[g_first + i]; U.xn = gcup[g_first + i + 1];
       U.a_lo = a; U.G = G; U.J = J; U.epmax_idx = s * SGB_MAX_EPOCHS + e; U.pad = 0;
       if (t < t_end) units[t++] = U;
       kcur = kend;
@@ -430,19 +435,11 @@ k_synth_tc(const TcUnit *__restrict__ units, int nunits, const double *__restric
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(128));
 }
 
-// FP32-pipe tiles of the epochs the tensor-core kernel takes are switched off (syl = -1)
-__global__ void k_mark_tiles_ffma(SynthTile *tiles, int n_tiles, const SylCtrl *ctrl, int min_rows) {
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_tiles) return;
-  const int s = tiles[t].syl;
-  if (s >= 0 && ctrl[s].ep_rows[tiles[t].epoch] >= min_rows) tiles[t].syl = -1;
-}
-
+int synth_min_rows();       // kernels_ctrl.cu: the K1 dispatch threshold the work lists were sized with
 void launch_build_tiles_tc(const sgb_syllable *syl, const SylCtrl *ctrl, int S, const SylLayout *lay, const Pools &P, TcUnit *units,
-                           SynthTile *tiles_ffma, int n_tiles_ffma, int min_rows, cudaStream_t st) {
+                           cudaStream_t st) {
   if (S <= 0) return;
-  k_build_units_tc<<<(S + 127) / 128, 128, 0, st>>>(syl, ctrl, S, lay, P, units, min_rows);
-  if (min_rows > 0 && n_tiles_ffma > 0) k_mark_tiles_ffma<<<(n_tiles_ffma + 255) / 256, 256, 0, st>>>(tiles_ffma, n_tiles_ffma, ctrl, min_rows);
+  k_build_units_tc<<<(S + 127) / 128, 128, 0, st>>>(syl, ctrl, S, lay, P, units, synth_min_rows());
 }
 
 cudaError_t launch_synth_tc(const TcUnit *units, int n_units, const Pools &P, const float4 *amp, float *wave, int *epmax, cudaStream_t st) {
