@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "engine.cuh"
+#include "hostpar.h"
 #include <cstdlib>
 
 // ---- kernel launchers defined in the other translation units ----
@@ -48,7 +49,8 @@ cudaError_t launch_stft(int mode, int u_is_float, int spec, const FftSeg *, int,
                         size_t, cudaStream_t);
 int stft_spec_of(int n, const int *radix, int npass);
 void launch_noise_final(const sgb_noise *, int, const NoiseLayout *, const double *, const double *, const int *, int,
-                        const float *, float *, int, cudaStream_t);
+                        const float *, float *, void *, int, cudaStream_t);
+size_t contour_tab_bytes();
 void launch_sound_mix(const sgb_bout *, int, const BoutLayout *, const sgb_noise *, const NoiseLayout *,
                       const double *, const float *, float *, int, cudaStream_t);
 void launch_finalize(int, const sgb_bout *, int, const BoutLayout *, const sgb_noise *, const NoiseLayout *,
@@ -186,7 +188,7 @@ struct sgb_batch {
   HBuf h_calltab;
   DBuf d_pcm, d_calltab;
   DBuf d_amp, d_amp32, d_wave, d_raw, d_sound, d_voiced, d_filt, d_noise_raw, d_noise_fin, d_env, d_out, d_out64;
-  DBuf d_trk, d_mouth, d_formants_late, d_tiles_tc;
+  DBuf d_trk, d_mouth, d_formants_late, d_tiles_tc, d_ntabs;
   struct RunState *rs = nullptr;     // state carried from run_begin to run_finish
   std::vector<double> late_rows;     // host-drawn formant tracks set between begin and finish
   bool envs_dirty = false;
@@ -374,7 +376,7 @@ void sgb_batch_destroy(sgb_batch *b) {
                  &b->d_totals, &b->d_summary, &b->d_tiles, &b->d_epmax, &b->p_pitch_w, &b->d_amp, &b->d_amp32, &b->d_wave, &b->d_raw,
                  &b->d_sound, &b->d_voiced, &b->d_filt, &b->d_noise_raw, &b->d_noise_fin, &b->d_env, &b->d_out,
                  &b->d_out64, &b->d_bl, &b->d_place, &b->d_nl, &b->d_envinst, &b->d_plans, &b->d_tw, &b->d_win,
-                 &b->d_fjobs, &b->d_njobs, &b->d_fsegs, &b->d_nsegs, &b->d_max, &b->d_trk, &b->d_mouth, &b->d_formants_late, &b->d_tiles_tc};
+                 &b->d_fjobs, &b->d_njobs, &b->d_fsegs, &b->d_nsegs, &b->d_max, &b->d_trk, &b->d_mouth, &b->d_formants_late, &b->d_tiles_tc, &b->d_ntabs};
   for (auto d : all) d->release();
   for (auto &d : b->p_i32) d.release();
   for (auto &d : b->p_f64) d.release();
@@ -595,6 +597,7 @@ struct PlanKey {
 // after the span-shrinking loop of smoothContours.R:145-152).  The kernels evaluate the contours; the
 // host runs the same scalar fit once per contour whose length it knows to learn whether the reference
 // call would have stopped.  1, 2 or more than 10 anchors and method 'spline' never fail.
+struct FitCheck { int call, na, method, len; double sr, lo, hi; const double *an; };
 static bool contour_fits(int na, int method, int len, double samplingRate, bool has_lo, double lo, bool has_hi,
                          double hi, const double *an) {
   if (na < 3 || na > 10 || method != SGB_CONTOUR_LOESS || len < 1) return true;
@@ -827,6 +830,13 @@ int sgb_batch_run_begin(sgb_batch *b) {
     return true;
   };
 
+  // loess fits that could stop the reference call: collected here, run on the worker threads after the layout
+  // (a fit is tens of microseconds of FP64; a preset sweep has three or four per call)
+  std::vector<FitCheck> fit_checks;
+  auto fit_later = [&](int call, int na, int method, int len, double sr, double lo, double hi, const double *an) {
+    if (na < 3 || na > 10 || method != SGB_CONTOUR_LOESS || len < 1) return;
+    fit_checks.push_back(FitCheck{call, na, method, len, sr, lo, hi, an});
+  };
   std::vector<int64_t> syl_pos, npos, fpos;   // reused across bouts (no allocation per bout)
   for (int c = 0; c < NC; c++) {
     const sgb_call &CL = b->calls[c];
@@ -871,8 +881,7 @@ int sgb_batch_run_begin(sgb_batch *b) {
       }
       L.sound_len = (int32_t)cur;
       L.voiced_shift = (int32_t)shift;
-      if (!contour_fits(B.aglobal_n, B.aglobal_method, (int)cur, B.samplingRate, true, 0.0, true, -B.throwaway,
-                        b->h_anchors.data() + 2 * B.aglobal_off)) b->call_status[c] = SGB_ERR_SYNTH;
+      fit_later(c, B.aglobal_n, B.aglobal_method, (int)cur, B.samplingRate, 0.0, -B.throwaway, b->h_anchors.data() + 2 * B.aglobal_off);
       L.sound_off = sound_total;
       for (int s = B.syl_begin; s < B.syl_end; s++) b->place[s].dst_off = L.sound_off + shift + syl_pos[s - B.syl_begin];
       for (int n = B.noise_begin; n < B.noise_end; n++)
@@ -907,8 +916,8 @@ int sgb_batch_run_begin(sgb_batch *b) {
         EnvInst I; I.out_off = L.env_off; I.env_id = B.env_id; I.nr = L.wl / 2; I.nc = L.nint; I.col0 = 0; I.trk_off = -1;
         envinst.push_back(I);
 
-        if (!contour_fits(b->envs[B.env_id].mouth_n, b->envs[B.env_id].mouth_method, L.nint, 16000.0, true, 0.0, true, 1.0,
-                          b->h_anchors.data() + 2 * b->envs[B.env_id].mouth_off)) b->call_status[c] = SGB_ERR_SYNTH;
+        fit_later(c, b->envs[B.env_id].mouth_n, b->envs[B.env_id].mouth_method, L.nint, 16000.0, 0.0, 1.0,
+                  b->h_anchors.data() + 2 * b->envs[B.env_id].mouth_off);
         FftJob J; memset(&J, 0, sizeof J);
         J.in_off = L.sound_off; J.out_off = L.filt_off; J.env_off = L.env_off; J.plan = L.fft_plan;
         J.nc = L.nc; J.nint = L.nint; J.xlen = L.filt_len; J.out_len = L.filt_len; J.shift = 0; J.max_slot = bi;
@@ -948,8 +957,8 @@ int sgb_batch_run_begin(sgb_batch *b) {
         Q.nc = seq_by_count(1.0, (double)N.len + N.wl, h_in);
         Q.xlen = (int32_t)std::floor(N.wl + (Q.nc - 1) * h_out);
         match_lengths(Q.xlen, N.len, &Q.pad_len, &Q.trim_start);
-        if (N.strength_pre_off < 0 && !contour_fits(N.anchor_n, N.anchor_method, N.len, N.samplingRate, true, -120.0, true, 40.0,
-                                                    b->h_anchors.data() + 2 * N.anchor_off)) b->call_status[c] = SGB_ERR_SYNTH;
+        if (N.strength_pre_off < 0)
+          fit_later(c, N.anchor_n, N.anchor_method, N.len, N.samplingRate, -120.0, 40.0, b->h_anchors.data() + 2 * N.anchor_off);
         Q.fft_plan = get_plan(N.wl, N.overlap);
         Q.env_off = -1; Q.nc_env = 0;
         if (Q.fft_plan < 0) { b->call_status[c] = SGB_ERR_UNSUPPORTED; continue; }
@@ -961,8 +970,7 @@ int sgb_batch_run_begin(sgb_batch *b) {
           Q.env_off = env_total; env_total += align4((int64_t)(N.wl / 2) * Q.nc_env);
           EnvInst I; I.out_off = Q.env_off; I.env_id = N.env_id; I.nr = N.wl / 2; I.nc = Q.nc_env; I.col0 = 0; I.trk_off = -1;
           envinst.push_back(I);
-          if (!contour_fits(E.mouth_n, E.mouth_method, Q.nc_env, 16000.0, true, 0.0, true, 1.0,
-                            b->h_anchors.data() + 2 * E.mouth_off)) b->call_status[c] = SGB_ERR_SYNTH;
+          fit_later(c, E.mouth_n, E.mouth_method, Q.nc_env, 16000.0, 0.0, 1.0, b->h_anchors.data() + 2 * E.mouth_off);
         }
         FftJob J; memset(&J, 0, sizeof J);
         J.in_off = N.u_off; J.out_off = Q.raw_off; J.env_off = Q.env_off; J.plan = Q.fft_plan; J.nc = Q.nc;
@@ -974,8 +982,18 @@ int sgb_batch_run_begin(sgb_batch *b) {
     }
     b->call_len[c] = clen;
     out_total += clen;          // outputs are packed back to back: one D2H copy fetches them all
-    if (b->call_status[c] != SGB_OK) n_failed++;
   }
+  {
+    std::vector<char> bad(fit_checks.size(), 0);
+    parallel_for((int)fit_checks.size(), [&](int i) {
+      const FitCheck &F = fit_checks[i];
+      bad[i] = !contour_fits(F.na, F.method, F.len, F.sr, true, F.lo, true, F.hi, F.an);
+    });
+    for (size_t i = 0; i < bad.size(); i++)
+      if (bad[i]) b->call_status[fit_checks[i].call] = SGB_ERR_SYNTH;
+  }
+  for (int c = 0; c < NC; c++)
+    if (b->call_status[c] != SGB_OK) n_failed++;
   b->total_out = out_total;
   info.n_failed = n_failed;
   for (int c = 0; c < NC; c++) info.total_samples += b->call_len[c];
@@ -1113,9 +1131,10 @@ int sgb_batch_run_finish(sgb_batch *b, sgb_run_info *info_out) {
                     gr.end - gr.begin, gr.smem, cudaGetErrorString(le));
       launches++;
     }
+    CK(b->d_ntabs.ensure(contour_tab_bytes() * (size_t)NN));
     launch_noise_final(b->d_noises.as<sgb_noise>(), NN, b->d_nl.as<NoiseLayout>(), b->d_anchors.as<double>(),
                        b->d_pre.as<double>(), b->d_max.as<int>(), NB, b->d_noise_raw.as<float>(),
-                       b->d_noise_fin.as<float>(), 16, st);
+                       b->d_noise_fin.as<float>(), b->d_ntabs.p, 16, st);
     CKL("launch_noise_final");
     launches += 1;
   }

@@ -19,6 +19,7 @@
 
 #include "ctrl.cuh"
 #include "rrng.h"
+#include "hostpar.h"
 
 int sgb_fail_msg(int code, const char *msg);   // engine.cu: sets the thread-local error string
 
@@ -204,6 +205,10 @@ struct CallState {
   // deferred main filter of the last bout emitted in the current round
   bool deferred = false;
   int deferred_env = -1, deferred_bout = -1;
+  // a round may be run more than once (a bench step, a retry): every resolve of the same round restarts from the
+  // stream position the first one found, so the same description always yields the same tracks
+  bool resolved = false;
+  RRng rng_pre;
 };
 
 struct Round {
@@ -884,6 +889,7 @@ int sgb_frontend_round_begin(sgb_frontend *fe, sgb_batch_desc *D, int32_t *n_sub
   for (int ci = 0; ci < (int)fe->calls.size(); ci++) {
     CallState &C = fe->calls[ci];
     C.deferred = false;
+    C.resolved = false;
     if (C.next_bout >= C.repeatBout || C.status != SGB_OK) continue;
     sgb_call cl;
     cl.bout_begin = (int)R.bouts.size();
@@ -919,13 +925,23 @@ int sgb_frontend_round_begin(sgb_frontend *fe, sgb_batch_desc *D, int32_t *n_sub
 
 int sgb_frontend_resolve(sgb_frontend *fe, sgb_batch *b) {
   if (!fe || !b) return ffail(SGB_ERR_INVALID, "null argument");
+  struct Job { CallState *C; int ncol, nint; std::vector<double> rows; int nf; };
+  std::vector<Job> jobs;
   for (auto &C : fe->calls) {
     if (!C.deferred) continue;
+    if (C.resolved) C.rng = C.rng_pre;
+    else { C.rng_pre = C.rng; C.resolved = true; }
     int32_t nc = 0, nint = 0, wl = 0, slen = 0;
     int rc = sgb_batch_bout_geometry(b, C.deferred_bout, &nc, &nint, &wl, &slen);
     if (rc != SGB_OK) return rc;
+    Job j; j.C = &C; j.nint = nint; j.nf = 0;
+    j.ncol = std::max(1, nint);        // a bypassed bout has no filter: draw as for one column
+    jobs.push_back(std::move(j));
+  }
+  parallel_for((int)jobs.size(), [&](int i) {
+    Job &J = jobs[i];
+    CallState &C = *J.C;
     const sgb_soundgen_args &a = C.a;
-    const int ncol = std::max(1, nint);        // a bypassed bout has no filter: draw as for one column
     std::vector<Formant> schwa;
     const std::vector<Formant> *fl = &C.formants;
     if (!C.has_formants) {
@@ -934,15 +950,16 @@ int sgb_frontend_resolve(sgb_frontend *fe, sgb_batch *b) {
       schwa.push_back(f); fl = &schwa;
     }
     std::vector<std::vector<double>> up;
-    upsample_formants(*fl, ncol, 1.0, up);
-    if (nint >= 1)    // sum(sound) == 0 skips the filter block, and with it the draws (soundgen.R:736-739)
-      stochastic_formants(C.rng, up, ncol, a.temperature, a.tempEffects[1], a.tempEffects[2], a.formantDep,
+    upsample_formants(*fl, J.ncol, 1.0, up);
+    if (J.nint >= 1)    // sum(sound) == 0 skips the filter block, and with it the draws (soundgen.R:736-739)
+      stochastic_formants(C.rng, up, J.ncol, a.temperature, a.tempEffects[1], a.tempEffects[2], a.formantDep,
                           a.formantDepStoch, C.vocalTract, a.samplingRate, 35400.0);
-    std::vector<double> rows;
-    for (auto &t : up) rows.insert(rows.end(), t.begin(), t.end());
-    rc = sgb_batch_set_tracks(b, C.deferred_env, rows.data(), (int)up.size(), ncol);
+    for (auto &t : up) J.rows.insert(J.rows.end(), t.begin(), t.end());
+    J.nf = (int)up.size();
+  });
+  for (auto &J : jobs) {
+    int rc = sgb_batch_set_tracks(b, J.C->deferred_env, J.rows.data(), J.nf, J.ncol);
     if (rc != SGB_OK) return rc;
-    C.deferred = false;
   }
   return SGB_OK;
 }

@@ -1,0 +1,29 @@
+// Host-side worker threads shared by the front-end and the engine's layout pass.
+#pragma once
+#include <algorithm>
+#include <atomic>
+#include <cstdlib>
+#include <thread>
+#include <vector>
+
+// SGB_FRONTEND_THREADS, default: the hardware's, at most 16.  Calls are independent -- each owns its RNG -- so
+// anything per call can run in parallel; only the order in which results enter the batch is kept serial.
+inline int sgb_host_threads() {
+  static const int n = [] {
+    const char *e = getenv("SGB_FRONTEND_THREADS");
+    int v = e ? atoi(e) : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    return std::max(1, v);
+  }();
+  return n;
+}
+template <typename F>
+inline void parallel_for(int n, F f) {
+  const int T = std::min(sgb_host_threads(), n);
+  if (T <= 1) { for (int i = 0; i < n; i++) f(i); return; }
+  std::atomic<int> next(0);
+  std::vector<std::thread> th;
+  auto work = [&] { for (int i = next.fetch_add(8); i < n; i = next.fetch_add(8)) for (int j = i; j < std::min(n, i + 8); j++) f(j); };
+  for (int t = 1; t < T; t++) th.emplace_back(work);
+  work();
+  for (auto &t : th) t.join();
+}

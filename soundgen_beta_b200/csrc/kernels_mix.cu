@@ -4,11 +4,24 @@
 #include "engine.cuh"
 #include "contour.cuh"
 
+// breathingStrength = getSmoothContour(len, noiseAnchors, floor -120, ceiling 40, samplingRate): the fit (FMM
+// spline or loess: a millisecond of FP64 on one thread) once per noise, one thread each, instead of once per CTA of
+// k_noise_final with 255 threads waiting
+__global__ void k_noise_tabs(const sgb_noise *__restrict__ noises, int n_noise, const double *__restrict__ anchors,
+                             ContourTab *__restrict__ tabs) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_noise) return;
+  const sgb_noise N = noises[n];
+  if (N.strength_pre_off < 0)
+    contour_prepare(&tabs[n], anchors + 2 * N.anchor_off, N.anchor_n, N.len, N.samplingRate, true, -120.0, true, 40.0,
+                    false, N.anchor_method);
+}
+
 // generateNoise tail (R/source.R:70-81,125-131):
-// breathing / max(breathing) * 2^(contour/10), then fadeInOut.  grid (chunks, noises).
+// breathing / max(breathing) * 2^(contour/10), then fadeInOut.  grid (noises, chunks).
 __global__ void __launch_bounds__(256)
 k_noise_final(const sgb_noise *__restrict__ noises, const NoiseLayout *__restrict__ nl,
-              const double *__restrict__ anchors, const double *__restrict__ pre,
+              const ContourTab *__restrict__ tabs, const double *__restrict__ pre,
               const int *__restrict__ maxpool, int max_base, const float *__restrict__ raw,
               float *__restrict__ fin) {
   const int n = blockIdx.x;
@@ -20,12 +33,12 @@ k_noise_final(const sgb_noise *__restrict__ noises, const NoiseLayout *__restric
   int lf = (int)floor(N.attackLen * N.samplingRate / 1000.0);
   if (lf < 2) lf = 0;
   if (lf > L) lf = L;
-  // breathingStrength = getSmoothContour(len, noiseAnchors, floor -120, ceiling 40, samplingRate)
   __shared__ ContourTab T;
   if (N.strength_pre_off < 0) {
-    if (threadIdx.x == 0)
-      contour_prepare(&T, anchors + 2 * N.anchor_off, N.anchor_n, L, N.samplingRate, true, -120.0, true, 40.0,
-                      false, N.anchor_method);
+    static_assert(sizeof(ContourTab) % 8 == 0, "ContourTab is copied as doubles");
+    const double *g = reinterpret_cast<const double *>(&tabs[n]);
+    double *d = reinterpret_cast<double *>(&T);
+    for (int i = threadIdx.x; i < (int)(sizeof(ContourTab) / 8); i += blockDim.x) d[i] = g[i];
     __syncthreads();
   }
   for (int k = blockIdx.y * blockDim.x + threadIdx.x; k < L; k += gridDim.y * blockDim.x) {
@@ -132,11 +145,13 @@ k_finalize(const sgb_bout *__restrict__ bouts, const BoutLayout *__restrict__ bl
 
 void launch_noise_final(const sgb_noise *noises, int n_noise, const NoiseLayout *nl, const double *anchors,
                         const double *pre, const int *maxpool, int max_base, const float *raw, float *fin,
-                        int chunks, cudaStream_t st) {
+                        void *tabs, int chunks, cudaStream_t st) {
   if (n_noise <= 0) return;
+  k_noise_tabs<<<(n_noise + 31) / 32, 32, 0, st>>>(noises, n_noise, anchors, (ContourTab *)tabs);
   dim3 g(n_noise, chunks);
-  k_noise_final<<<g, 256, 0, st>>>(noises, nl, anchors, pre, maxpool, max_base, raw, fin);
+  k_noise_final<<<g, 256, 0, st>>>(noises, nl, (const ContourTab *)tabs, pre, maxpool, max_base, raw, fin);
 }
+size_t contour_tab_bytes() { return sizeof(ContourTab); }
 
 void launch_sound_mix(const sgb_bout *bouts, int n_bouts, const BoutLayout *bl, const sgb_noise *noises,
                       const NoiseLayout *nl, const double *anchors, const float *noise_fin, float *sound,
