@@ -276,6 +276,7 @@ def main():
     ap.add_argument('--parity-calls', type=int, default=16)
     ap.add_argument('--pipeline', type=int, default=8,
                     help='sub-batches (handles / CUDA streams) of the end-to-end measurement')
+    ap.add_argument('--fe-threads', type=int, default=3, help='host front-end threads of the from-arguments pipeline')
     ap.add_argument('--runners', type=int, default=3,
                     help='host threads that run kernels in the end-to-end pipeline (plus one uploader, one fetcher)')
     ap.add_argument('--watchdog', type=int, default=1500, help='seconds after which a stuck run dumps its stacks and exits')
@@ -286,6 +287,8 @@ def main():
         run_reference(args, rank, world)
         return
 
+    # worker threads of the library's host stage: the ranks of one box share its cores
+    os.environ.setdefault('SGB_FRONTEND_THREADS', str(max(1, min(16, (os.cpu_count() or 16) // max(1, world)))))
     import __graft_entry__ as ge
     ge.build()
     import soundgen_beta_b200 as sg
@@ -392,6 +395,23 @@ def main():
     barrier()
     dt_wav = time.perf_counter() - t2
     d2h_i16 = sum(o.nbytes for o in pipe.outs)
+    pipe.close()
+    # the same again, but every step starts from the ARGUMENT LISTS (one sgb_soundgen_args struct per call, the
+    # form a binding such as r/src/rshim.c produces): `--fe-threads` threads run the library's host front-end
+    # (validation, R's RNG stream, contour set-up, description) for a sub-batch before it is uploaded
+    srcs = []
+    for i in range(npipe):
+        lo, hi = sharding.shard_range(len(calls), i, npipe)
+        srcs.append(sg.ArgArray(calls[lo:hi], np.float32))
+    pipe_a = sg.PipelinedBatches(sources=srcs, runners=args.runners, fe_threads=args.fe_threads)
+    pipe_a.run_steps(2, dtype=np.int16)
+    barrier()
+    t3 = time.perf_counter()
+    pipe_a.run_steps(args.steps, dtype=np.int16)
+    barrier()
+    dt_args = time.perf_counter() - t3
+    h2d_args = int(sum(fe.h2d_bytes() for fe in pipe_a.fes))
+    pipe_a.close()
     stuck.cancel()
     d2h_bytes = d2h_f32
     clocks = sampler.stop()
@@ -405,8 +425,9 @@ def main():
         outs_pick = {int(i): out[offs[i]:offs[i + 1]] for i in pick}
         parity = parity_sample(calls, outs_pick, [int(i) for i in pick])
 
-    dt, dt_e2e, audio_total, dt_wav = sharding.aggregate(dist, dt, dt_e2e, audio_s,
-                                                         device='cuda' if dist is not None else None, extra=(dt_wav,))
+    dt, dt_e2e, audio_total, dt_wav, dt_args = sharding.aggregate(dist, dt, dt_e2e, audio_s,
+                                                                  device='cuda' if dist is not None else None,
+                                                                  extra=(dt_wav, dt_args))
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -512,12 +533,19 @@ def main():
             # (R/soundgen.R:855-857 -> seewave::savewav), normalised and packed on the device; `e2e_f32` is the same
             # pipeline fetching FP32 samples (what soundgen() returns in memory): twice the bytes, and on an
             # 8-GPU box it runs at the bare pinned-copy ceiling of the host (profiles/r02_copy_ceiling_8gpu.json).
-            'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': int(bb.h2d_bytes()),
-                    'd2h_bytes_per_step': int(d2h_i16), 'ms_per_step': dt_wav / args.steps * 1e3,
+            'e2e': {'value': audio_total * args.steps / dt_args, 'unit': UNIT, 'h2d_bytes_per_step': h2d_args,
+                    'd2h_bytes_per_step': int(d2h_i16), 'ms_per_step': dt_args / args.steps * 1e3,
                     'result_format': 'int16 PCM (savePath / WAV sample format)', 'pipeline': npipe, 'runners': args.runners,
-                    'cpus_bound': len(numa_cpus), 'front_end_ms_per_step': fe_ms,
-                    'note': 'timed from prebuilt descriptions; front_end_ms_per_step = argument lists -> description '
-                            'through the library host front-end for the same batch, one thread (Python marshalling included)'},
+                    'fe_threads': args.fe_threads, 'cpus_bound': len(numa_cpus),
+                    'note': 'every step starts from the ARGUMENT LISTS (one sgb_soundgen_args struct per call, the form a '
+                            'binding such as r/src/rshim.c produces): library front-end (validation, R RNG stream, contour '
+                            'set-up, description) -> pinned H2D -> kernels -> PCM16 D2H, sub-batches pipelined'},
+            'e2e_prebuilt': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': int(bb.h2d_bytes()),
+                             'd2h_bytes_per_step': int(d2h_i16), 'ms_per_step': dt_wav / args.steps * 1e3,
+                             'front_end_ms_per_step': fe_ms,
+                             'note': 'the same pipeline timed from prebuilt batch descriptions (round-1 definition); '
+                                     'front_end_ms_per_step = argument lists -> description on ONE thread through the Python '
+                                     'mirror, per-call Python marshalling included'},
             'e2e_f32': {'value': e2e_f32, 'unit': UNIT, 'ms_per_step': dt_e2e / args.steps * 1e3,
                         'd2h_bytes_per_step': int(d2h_bytes),
                         'note': 'same pipeline, waveforms fetched as FP32 samples'},

@@ -311,6 +311,11 @@ void sgb_frontend_destroy(sgb_frontend *fe);
 int  sgb_frontend_add(sgb_frontend *fe, const sgb_soundgen_args *args);
 /* n calls that differ only in their seed (rng_mode 0): returns the index of the first. */
 int  sgb_frontend_add_seeded(sgb_frontend *fe, const sgb_soundgen_args *args, const uint32_t *seeds, int32_t n);
+/* `n` argument lists in one call (index of the first, or an error); the pointers inside every element must stay
+   valid until the last round of these calls has ended */
+int  sgb_frontend_add_many(sgb_frontend *fe, const sgb_soundgen_args *args, int32_t n);
+/* forget every registered call; the handle and its buffers are reused */
+int  sgb_frontend_clear(sgb_frontend *fe);
 /* Builds the description of the next round.  One round covers every call that still has bouts
  * to generate, up to and including the first bout whose main filter has to be drawn after the
  * device has run (stochastic moving formants): most batches need exactly one round.

@@ -118,6 +118,20 @@ _DEFAULT_FORMANT_ARGS = None
 _METHODS = {'loess': _abi.SGB_CONTOUR_LOESS, 'spline': _abi.SGB_CONTOUR_SPLINE}
 
 
+class ArgArray:
+    """soundgen() argument lists marshalled once into a contiguous array of `sgb_soundgen_args` -- the form in which
+    a binding hands its calls to the library (`sgb_frontend_add_many`)."""
+
+    def __init__(self, calls, u_dtype=np.float64):
+        fe = FrontEnd(u_dtype)
+        pairs = [fe.marshal(**dict(kw)) for kw in calls]
+        fe.close()
+        self.n = len(pairs)
+        self.u_dtype = np.dtype(u_dtype)
+        self.arr = (_abi.SoundgenArgs * max(1, self.n))(*[p[0] for p in pairs])
+        self.keep = [p[1] for p in pairs]
+
+
 class FrontEnd:
     """Handle of the library's host front-end: soundgen() argument lists in, batch descriptions out."""
 
@@ -140,10 +154,48 @@ class FrontEnd:
         except Exception:
             pass
 
-    def add(self, seed=None, z=None, u=None, contour_method='loess', warn=None, invalidArgAction='adjust',
-            formants='default', formantsNoise=None, tempEffects=None, device_pitch=True, rng_state=None,
-            sample_kind='Rounding', seeds=None, **kw):
+    def add(self, warn=None, seeds=None, **kw):
         """One soundgen() call; with `seeds` (a sequence) the same argument list once per seed."""
+        A, keep = self.marshal(**kw)
+        if seeds is not None:
+            sd = np.ascontiguousarray(np.asarray(seeds, dtype=np.int64) & 0xFFFFFFFF, dtype=np.uint32)
+            A.rng_mode = 0
+            rc = self.L.sgb_frontend_add_seeded(self.h, C.byref(A), sd.ctypes.data, sd.size)
+        else:
+            rc = self.L.sgb_frontend_add(self.h, C.byref(A))
+        self._raise(rc)
+        self.n_calls = rc + (1 if seeds is None else len(seeds))
+        if warn is not None:
+            w = self.L.sgb_frontend_warnings(self.h, rc).decode()
+            if w:
+                warn.extend(w.split('\n'))
+        return rc
+
+    def _raise(self, rc):
+        if rc < 0:
+            msg = self.L.sgb_last_error().decode()
+            if rc == _abi.SGB_ERR_INVALID and 'must be between' in msg:
+                raise ValueError(msg)
+            if rc == _abi.SGB_ERR_UNSUPPORTED:
+                raise NotImplementedError(msg)
+            raise SoundgenError(rc, msg)
+
+    def add_many(self, args):
+        """Every call of an `ArgArray` (argument lists already in the library's struct form) in one library call."""
+        rc = self.L.sgb_frontend_add_many(self.h, args.arr, args.n)
+        self._raise(rc)
+        self.n_calls = rc + args.n
+        return rc
+
+    def clear(self):
+        _check(self.L.sgb_frontend_clear(self.h))
+        self.n_calls = 0
+        self.n_sub = 0
+
+    def marshal(self, seed=None, z=None, u=None, contour_method='loess', invalidArgAction='adjust',
+                formants='default', formantsNoise=None, tempEffects=None, device_pitch=True, rng_state=None,
+                sample_kind='Rounding', **kw):
+        """A soundgen() argument list as the library's `sgb_soundgen_args` struct (+ the arrays it points to)."""
         keep = []
         A = _abi.SoundgenArgs()
         for k, d in SOUNDGEN_DEFAULTS.items():
@@ -205,25 +257,7 @@ class FrontEnd:
                 un = np.array([np.size(q) for q in ul], dtype=np.int64)
                 keep += [uc, un]
                 A.u, A.u_len, A.n_u = uc.ctypes.data, un.ctypes.data, len(ul)
-        if seeds is not None:
-            sd = np.ascontiguousarray(np.asarray(seeds, dtype=np.int64) & 0xFFFFFFFF, dtype=np.uint32)
-            A.rng_mode = 0
-            rc = self.L.sgb_frontend_add_seeded(self.h, C.byref(A), sd.ctypes.data, sd.size)
-        else:
-            rc = self.L.sgb_frontend_add(self.h, C.byref(A))
-        if rc < 0:
-            msg = self.L.sgb_last_error().decode()
-            if rc == _abi.SGB_ERR_INVALID and 'must be between' in msg:
-                raise ValueError(msg)
-            if rc == _abi.SGB_ERR_UNSUPPORTED:
-                raise NotImplementedError(msg)
-            raise SoundgenError(rc, msg)
-        self.n_calls = rc + (1 if seeds is None else len(seeds))
-        if warn is not None:
-            w = self.L.sgb_frontend_warnings(self.h, rc).decode()
-            if w:
-                warn.extend(w.split('\n'))
-        return rc
+        return A, keep
 
     def round_begin(self):
         d = BatchDesc()
@@ -708,7 +742,16 @@ class PipelinedBatches:
     engine).  ctypes releases the GIL during the library calls.  Independent sounds need no ordering,
     so no work is skipped and nothing is shared between the sub-batches."""
 
-    def __init__(self, descs, runners=2):
+    def __init__(self, descs=None, runners=2, sources=None, fe_threads=2):
+        """`descs`: prebuilt batch descriptions, one per sub-batch -- or `sources`: one `ArgArray` per sub-batch, in
+        which case every step starts from the argument lists: `fe_threads` threads run the library's host
+        front-end (`sgb_frontend_add_many` + `round_begin`) for a sub-batch before it is uploaded."""
+        self.sources = list(sources) if sources is not None else None
+        if self.sources is not None:
+            self.fes = [FrontEnd(src.u_dtype) for src in self.sources]
+            descs = [None] * len(self.sources)
+            self._pinned = [dict() for _ in self.sources]
+        self.fe_threads = max(1, int(fe_threads))
         self.descs = list(descs)
         self.batches = [Batch() for _ in self.descs]
         self.outs = [None] * len(self.descs)
@@ -765,13 +808,40 @@ class PipelinedBatches:
                     abort.set()
             return g
 
+        q_fe, q_up = queue.Queue(), queue.Queue()
+
+        def front_end():
+            while True:
+                i = q_get(q_fe)
+                if i is None:
+                    q_up.put(None)
+                    return
+                acquire(free[i])
+                fe = self.fes[i]
+                fe.clear()
+                fe.add_many(self.sources[i])
+                d, _ = fe.round_begin()
+                self._pin_pools(i, d)
+                self.descs[i] = d
+                q_up.put(i)
+
         def uploader():
-            for s in range(nsteps):
-                for i in range(n):
-                    acquire(free[i])
-                    if transfer or self.batches[i].desc is None:
-                        self.batches[i].upload(self.descs[i])
+            if self.sources is not None:
+                done = 0
+                while done < self.fe_threads:
+                    i = q_get(q_up)
+                    if i is None:
+                        done += 1
+                        continue
+                    self.batches[i].upload(self.descs[i])
                     q_run.put(i)
+            else:
+                for s in range(nsteps):
+                    for i in range(n):
+                        acquire(free[i])
+                        if transfer or self.batches[i].desc is None:
+                            self.batches[i].upload(self.descs[i])
+                        q_run.put(i)
             for _ in range(self.runners):
                 q_run.put(None)
 
@@ -798,12 +868,36 @@ class PipelinedBatches:
         th = [threading.Thread(target=guard(uploader))] + \
              [threading.Thread(target=guard(runner)) for _ in range(self.runners)] + \
              [threading.Thread(target=guard(fetcher))]
+        if self.sources is not None:
+            for s_ in range(nsteps):
+                for i in range(n):
+                    q_fe.put(i)
+            for _ in range(self.fe_threads):
+                q_fe.put(None)
+            th += [threading.Thread(target=guard(front_end)) for _ in range(self.fe_threads)]
         for t in th:
             t.start()
         for t in th:
             t.join()
         if err:
             raise err[0]
+
+    def _pin_pools(self, i, d):
+        """Page-locks the pools of a description the front-end just rebuilt, unless they sit where they sat last
+        time (cleared vectors keep their storage, so from the second step on this is a dictionary lookup)."""
+        L = _abi.load()
+        cur = {}
+        for k, a in d._keep.items():
+            if a.size:
+                cur[k] = (a.ctypes.data, a.nbytes)
+        old = self._pinned[i]
+        for k, v in old.items():
+            if cur.get(k) != v:
+                L.sgb_unpin(v[0])
+        for k, v in cur.items():
+            if old.get(k) != v:
+                _check(L.sgb_pin(v[0], v[1]))
+        self._pinned[i] = cur
 
     def step(self, dtype=np.float32):
         """upload + run + fetch of every sub-batch; returns the per-call waveforms in order."""
@@ -817,6 +911,13 @@ class PipelinedBatches:
             if o is not None:
                 _abi.load().sgb_unpin(o.ctypes.data)
         self.outs = [None] * len(self.descs)
+        if self.sources is not None:
+            for pm in self._pinned:
+                for v in pm.values():
+                    _abi.load().sgb_unpin(v[0])
+            self._pinned = [dict() for _ in self.sources]
+            for fe in self.fes:
+                fe.close()
 
 
 def pin_desc(desc, pin=True):

@@ -423,10 +423,8 @@ int sgb_frontend_create(sgb_frontend **out, int32_t u_is_float) {
 
 void sgb_frontend_destroy(sgb_frontend *fe) { delete fe; }
 
-int sgb_frontend_add(sgb_frontend *fe, const sgb_soundgen_args *args) {
-  if (!fe || !args) return ffail(SGB_ERR_INVALID, "null argument");
-  fe->calls.emplace_back();
-  CallState &C = fe->calls.back();
+// Parses one argument list into `C` (validation, defaults, copies of every table it points to); 0 or an error.
+static int build_call(const sgb_frontend *fe, const sgb_soundgen_args *args, CallState &C) {
   C.a = *args;
   sgb_soundgen_args &a = C.a;
   // ---- range check against permittedValues (soundgen.R:279-302) ----
@@ -439,7 +437,6 @@ int sgb_frontend_add(sgb_frontend *fe, const sgb_soundgen_args *args) {
     double v = *vals[i];
     if (std::isnan(v) || v < PERM[i].lo || v > PERM[i].hi) {
       if (a.invalidArgAction == 1) {
-        fe->calls.pop_back();
         return ffail(SGB_ERR_INVALID, "%s must be between %g and %g", PERM[i].name, PERM[i].lo, PERM[i].hi);
       } else if (a.invalidArgAction == 2) {
         warn(C, "%s outside its range in 'permittedValues'", PERM[i].name);
@@ -450,7 +447,6 @@ int sgb_frontend_add(sgb_frontend *fe, const sgb_soundgen_args *args) {
     }
   }
   if (!(a.samplingRate > 0) || !(a.pitchSamplingRate > 0) || !(a.pitchFloor > 0) || !(a.throwaway < 0)) {
-    fe->calls.pop_back();
     return ffail(SGB_ERR_INVALID, "samplingRate, pitchSamplingRate, pitchFloor must be positive and throwaway negative");
   }
   C.pitchAnchors = take_anchors(a.pitchAnchors, 1.0);
@@ -471,11 +467,10 @@ int sgb_frontend_add(sgb_frontend *fe, const sgb_soundgen_args *args) {
   C.rng.rejection_sampling = a.sample_rejection != 0;
   if (a.rng_mode == 0) C.rng.set_seed(a.seed);
   else if (a.rng_mode == 1) {
-    if (!a.rng_state) { fe->calls.pop_back(); return ffail(SGB_ERR_INVALID, "rng_mode 1 needs rng_state"); }
+    if (!a.rng_state) { return ffail(SGB_ERR_INVALID, "rng_mode 1 needs rng_state"); }
     C.rng.set_state(a.rng_state);
   } else {
     if (a.temperature > 0) {
-      fe->calls.pop_back();
       return ffail(SGB_ERR_UNSUPPORTED, "temperature > 0 draws from R's stream on the host: use rng_mode 0 / 1 (a seed), "
                                         "caller buffers only cover the device draws");
     }
@@ -521,7 +516,7 @@ int sgb_frontend_add(sgb_frontend *fe, const sgb_soundgen_args *args) {
     fl = std::floor(a.repeatBout);
     C.repeatBout = (int)(fl + (C.use_rng ? C.rng.rbinom(1, a.repeatBout - fl) : 0.0));
   }
-  if (C.nSyl < 1 || C.repeatBout < 1) { fe->calls.pop_back(); return ffail(SGB_ERR_INVALID, "nSyl and repeatBout must be at least 1"); }
+  if (C.nSyl < 1 || C.repeatBout < 1) { return ffail(SGB_ERR_INVALID, "nSyl and repeatBout must be at least 1"); }
   // ---- pitchDeltas (:448-462): getDiscreteContour(len = nSyl, method = 'spline') ----
   C.pitchDeltas.assign(C.nSyl, 1.0);
   {
@@ -532,7 +527,7 @@ int sgb_frontend_add(sgb_frontend *fe, const sgb_soundgen_args *args) {
       for (int i = 0; i < C.pitchAnchorsGlobal.n(); i++) { an.push_back(C.pitchAnchorsGlobal.t[i]); an.push_back(C.pitchAnchorsGlobal.v[i]); }
       ContourTab T;
       contour_prepare(&T, an.data(), C.pitchAnchorsGlobal.n(), C.nSyl, 16000.0, false, 0, false, 0, false, SGB_CONTOUR_SPLINE);
-      if (T.status != SGB_OK) { fe->calls.pop_back(); return ffail(T.status, "pitchAnchorsGlobal: too many anchors"); }
+      if (T.status != SGB_OK) { return ffail(T.status, "pitchAnchorsGlobal: too many anchors"); }
       for (int s = 0; s < C.nSyl; s++) C.pitchDeltas[s] = std::pow(2.0, contour_eval(&T, C.nSyl, s) / 12);
     }
   }
@@ -553,6 +548,14 @@ int sgb_frontend_add(sgb_frontend *fe, const sgb_soundgen_args *args) {
     for (double v : C.amplAnchors.v) if (v < -a.throwaway) cnt++;
     C.wiggleAmpl = a.temperature > 0 && !C.amplAnchors.na() && cnt > 0;
   }
+  return SGB_OK;
+}
+
+int sgb_frontend_add(sgb_frontend *fe, const sgb_soundgen_args *args) {
+  if (!fe || !args) return ffail(SGB_ERR_INVALID, "null argument");
+  fe->calls.emplace_back();
+  int rc = build_call(fe, args, fe->calls.back());
+  if (rc < 0) { fe->calls.pop_back(); return rc; }
   return (int)fe->calls.size() - 1;
 }
 
@@ -570,6 +573,31 @@ int sgb_frontend_add_seeded(sgb_frontend *fe, const sgb_soundgen_args *args, con
     if (i == 0) first = rc;
   }
   return first;
+}
+
+// n argument lists at once (one library call instead of n: a binding marshals its calls into an array once).
+int sgb_frontend_add_many(sgb_frontend *fe, const sgb_soundgen_args *args, int32_t n) {
+  if (!fe || !args || n < 1) return ffail(SGB_ERR_INVALID, "bad argument");
+  const size_t base = fe->calls.size();
+  fe->calls.resize(base + (size_t)n);
+  std::vector<int> rcs((size_t)n, 0);
+  parallel_for(n, [&](int i) { rcs[i] = build_call(fe, &args[i], fe->calls[base + i]); });
+  for (int i = 0; i < n; i++)
+    if (rcs[i] < 0) {                       // the message belongs to a worker thread: produce it again on this one
+      CallState tmp;
+      int rc = build_call(fe, &args[i], tmp);
+      fe->calls.resize(base);
+      return rc < 0 ? rc : rcs[i];
+    }
+  return (int)base;
+}
+
+// Forget every registered call (the handle and its buffers are reused for the next batch).
+int sgb_frontend_clear(sgb_frontend *fe) {
+  if (!fe) return ffail(SGB_ERR_INVALID, "null argument");
+  fe->calls.clear();
+  fe->R.clear();
+  return SGB_OK;
 }
 
 }  // extern "C"
