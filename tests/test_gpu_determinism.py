@@ -21,10 +21,8 @@ def test_pipelined_runs_are_bit_reproducible(cfg, n, npipe, reps):
     for i in range(npipe):
         lo, hi = sharding.shard_range(n, i, npipe)
         bb = sg.BatchBuilder(u_dtype=np.float32)
-        for kw in calls[lo:hi]:
-            if 'seed' in kw:      # cfg4: temperature 0 keeps every draw inside the description, so that
-                kw = dict(kw, temperature=0)   # re-running the same description repeats the same draws
-            bb.add_soundgen(**kw)
+        for kw in calls[lo:hi]:   # cfg4 keeps its temperature: the draws that wait for device results (formant
+            bb.add_soundgen(**kw)  # tracks, sgb_frontend_resolve) restart from the same stream position on every run
         descs.append(bb.build())
     batches = [sg.Batch() for _ in descs]
     sums = [[] for _ in descs]
@@ -58,3 +56,29 @@ def test_pipelined_runs_are_bit_reproducible(cfg, n, npipe, reps):
             assert not diff, 'sub-batch %d, repetition %d: %s differ' % (i, r, diff)
     for b in batches:
         b.close()
+
+
+@pytest.mark.parametrize('cfg,n', [(3, 96), (4, 66)])
+def test_pipeline_from_argument_lists_equals_prebuilt(cfg, n):
+    """Every step of PipelinedBatches(sources=...) runs the library front-end on the argument structs
+    (sgb_frontend_add_many on worker threads): same waveforms as the prebuilt descriptions, step after step."""
+    calls = workloads.CONFIGS[cfg](n=n)
+    npipe = 3
+    descs, srcs = [], []
+    for i in range(npipe):
+        lo, hi = sharding.shard_range(n, i, npipe)
+        bb = sg.BatchBuilder(u_dtype=np.float32)
+        for kw in calls[lo:hi]:
+            bb.add_soundgen(**kw)
+        descs.append(bb.build())
+        srcs.append(sg.ArgArray(calls[lo:hi], np.float32))
+    ref = sg.PipelinedBatches(descs, runners=2)
+    want = [np.array(w, copy=True) for w in ref.step(np.float32)]
+    ref.close()
+    pipe = sg.PipelinedBatches(sources=srcs, runners=2, fe_threads=2)
+    for _ in range(3):
+        got = pipe.step(np.float32)
+        assert len(got) == len(want) == n
+        for a, b in zip(got, want):
+            assert np.array_equal(a, b)
+    pipe.close()

@@ -69,3 +69,36 @@ def test_workloads_are_seeded():
     assert workloads.config0() == [dict(sylLen=1000, seed=1)]           # the literal reference call
     c4 = workloads.config4(n=34)
     assert c4[33]['seed'] == 33 and sorted(c4[0]) == sorted(c4[33])
+
+
+def _pool_bytes(d):
+    esz = 4 if d.u_is_float else 8
+    out = []
+    for ptr, n in ((d.pitch, 8 * d.n_pitch), (d.anchors, 16 * d.n_anchors), (d.formants, 32 * d.n_formants),
+                   (d.z, 8 * d.n_z), (d.u, esz * d.n_u), (d.pre, 8 * d.n_pre),
+                   (d.syllables, C.sizeof(_abi.Syllable) * d.n_syllables), (d.noises, C.sizeof(_abi.Noise) * d.n_noises),
+                   (d.bouts, C.sizeof(_abi.Bout) * d.n_bouts), (d.envelopes, C.sizeof(_abi.Envelope) * d.n_envelopes)):
+        out.append(C.string_at(ptr, n) if ptr and n else b'')
+    return out
+
+
+def test_add_many_equals_per_call_add():
+    """sgb_frontend_add_many (worker threads) + clear + re-use yield the description the per-call path builds."""
+    calls = workloads.config3(n=40) + workloads.config0(n=6, seed=3) + workloads.config2(n=5)
+    fe1 = sg.FrontEnd(np.float32)
+    for kw in calls:
+        fe1.add(**dict(kw))
+    d1, n1 = fe1.round_begin()
+    aa = sg.ArgArray(calls, np.float32)
+    fe2 = sg.FrontEnd(np.float32)
+    for _ in range(2):                       # second pass: the cleared handle is reused
+        fe2.clear()
+        assert fe2.add_many(aa) == 0
+        d2, n2 = fe2.round_begin()
+        assert n1 == n2 == len(calls)
+        assert _pool_bytes(d1) == _pool_bytes(d2)
+    bad = sg.ArgArray([dict(sylLen=300, temperature=0), dict(sylLen=-5, temperature=0, invalidArgAction='abort')], np.float32)
+    fe2.clear()
+    with pytest.raises(ValueError):
+        fe2.add_many(bad)
+    assert fe2.round_begin()[1] == 0         # nothing of a failed add_many stays registered
