@@ -191,6 +191,8 @@ struct sgb_batch {
   DBuf d_trk, d_mouth, d_formants_late, d_tiles_tc, d_ntabs;
   struct RunState *rs = nullptr;     // state carried from run_begin to run_finish
   std::vector<double> late_rows;     // host-drawn formant tracks set between begin and finish
+  std::vector<int> late_envs;        // the envelopes they belong to (deferred again at the next run_begin)
+  size_t n_frefs_uploaded = 0;
   bool envs_dirty = false;
   DBuf d_bl, d_place, d_nl, d_envinst, d_plans, d_tw, d_win, d_fjobs, d_njobs, d_fsegs, d_nsegs, d_max;
   Pools pools;
@@ -558,7 +560,8 @@ int sgb_batch_upload(sgb_batch *b, const sgb_batch_desc *D) {
   CK(b->d_totals.ensure(64));
   CK(b->d_summary.ensure(sizeof(SylSummary) * (size_t)S));
   CK(b->d_epmax.ensure(4 * (size_t)S * SGB_MAX_EPOCHS));
-  b->late_rows.clear(); b->envs_dirty = false;
+  b->late_rows.clear(); b->late_envs.clear(); b->envs_dirty = false;
+  b->n_frefs_uploaded = b->frefs.size();
   b->have_desc = true;
   b->have_run = false;
   b->keep_voiced = (D->n_calls <= 64);
@@ -707,6 +710,9 @@ int sgb_batch_run_begin(sgb_batch *b) {
   R.begun = false;
   CK(cudaSetDevice(b->device));
   b->have_run = false;           // a failed run must not leave the previous run's results fetchable
+  // tracks that arrived during the previous run of this upload: their envelopes wait for new ones again
+  for (int e : b->late_envs) b->envs[e].tracks_given = 3;
+  b->late_envs.clear(); b->late_rows.clear(); b->frefs.resize(b->n_frefs_uploaded);
   cudaStream_t st = b->st;
   const int S = (int)b->syls.size(), NB = (int)b->bouts.size(), NN = (int)b->noises.size(), NC = (int)b->calls.size();
   sgb_run_info &info = b->info;
@@ -1212,6 +1218,7 @@ int sgb_batch_set_tracks(sgb_batch *b, int32_t env, const double *rows, int32_t 
     b->frefs.push_back(R);
   }
   b->late_rows.insert(b->late_rows.end(), rows, rows + (size_t)4 * n_formants * nc);
+  b->late_envs.push_back(env);
   b->envs_dirty = true;
   return SGB_OK;
 }

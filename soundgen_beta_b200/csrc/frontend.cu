@@ -16,6 +16,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <chrono>
 
 #include "ctrl.cuh"
 #include "rrng.h"
@@ -232,13 +233,20 @@ struct Round {
   }
 };
 
+// round_begin emits the calls on worker threads: every thread fills its own shard of the round (contiguous calls),
+// the shards are concatenated in call order afterwards.  While a thread emits, this points at its shard.
+static thread_local Round *tl_round = nullptr;
+
 }  // namespace
 
 struct sgb_frontend {
   int u_is_float = 0;
   std::vector<CallState> calls;
   Round R;
+  std::vector<Round> shards;       // kept between rounds: their vectors keep their storage
+  Round &round() { return tl_round ? *tl_round : R; }
   int64_t add_anchors(const Anchors &a, int32_t *n) {
+    Round &R = round();
     int64_t off = (int64_t)(R.anchors.size() / 2);
     for (int i = 0; i < a.n(); i++) { R.anchors.push_back(a.t[i]); R.anchors.push_back(a.v[i]); }
     *n = a.n();
@@ -608,7 +616,7 @@ namespace {
 // tracks: host-drawn formants_upsampled (stochastic) or nullptr; deferred: tracks come after run_begin.
 int add_envelope(sgb_frontend *fe, CallState &C, const std::vector<Formant> *fl, bool has_f, int nc_fixed,
                  const std::vector<std::vector<double>> *tracks, int tracks_nc, bool deferred) {
-  Round &R = fe->R;
+  Round &R = fe->round();
   const sgb_soundgen_args &a = C.a;
   sgb_envelope e;
   memset(&e, 0, sizeof e);
@@ -661,7 +669,7 @@ bool formants_moving(const std::vector<Formant> &fl) {
 // (its main filter is deferred and later bouts draw after it).
 bool emit_bout(sgb_frontend *fe, int ci, int b) {
   CallState &C = fe->calls[ci];
-  Round &R = fe->R;
+  Round &R = fe->round();
   const sgb_soundgen_args &a = C.a;
   RRng &g = C.rng;
   const double T = a.temperature, sr = a.samplingRate;
@@ -748,6 +756,7 @@ bool emit_bout(sgb_frontend *fe, int ci, int b) {
       y.ampl_method = a.contour_method;
       int32_t npa = 0;
       y.pitch_anchor_off = fe->add_anchors(pitchA, &npa);
+      y.reserved0 = 1;                    // pitch_anchor_off is set (merge_shard rebases it)
       if (!amplA.na()) y.ampl_off = fe->add_anchors(amplA, &y.ampl_n);
       y.attackLen = ps.attackLen; y.nonlinBalance = C.nonlinBalance; y.jitterDep = ps.jitterDep; y.jitterLen = a.jitterLen;
       y.vibratoFreq = a.vibratoFreq; y.vibratoDep = a.vibratoDep; y.shimmerDep = ps.shimmerDep; y.rolloff = ps.rolloff;
@@ -906,29 +915,101 @@ bool emit_bout(sgb_frontend *fe, int ci, int b) {
   return !(deferred && b < C.repeatBout - 1);
 }
 
+// One call's share of a round: its next bouts into the current round (fe->round()).
+static void emit_call(sgb_frontend *fe, int ci) {
+  Round &R = fe->round();
+  CallState &C = fe->calls[ci];
+  C.deferred = false;
+  C.resolved = false;
+  if (C.next_bout >= C.repeatBout || C.status != SGB_OK) return;
+  sgb_call cl;
+  cl.bout_begin = (int)R.bouts.size();
+  while (C.next_bout < C.repeatBout) {
+    bool go_on = emit_bout(fe, ci, C.next_bout);
+    C.next_bout++;
+    if (!go_on) break;
+  }
+  cl.bout_end = (int)R.bouts.size();
+  R.calls.push_back(cl);
+  R.sub_call.push_back(ci);
+}
+
+template <typename T>
+static void append(std::vector<T> &dst, const std::vector<T> &src) { dst.insert(dst.end(), src.begin(), src.end()); }
+
+// Appends shard S to R: every index and pool offset of S is relative to S and is rebased.
+static void merge_shard(sgb_frontend *fe, Round &R, const Round &S) {
+  const int b_bout = (int)R.bouts.size(), b_syl = (int)R.syls.size(), b_noise = (int)R.noises.size(), b_env = (int)R.envs.size();
+  const int64_t b_fref = (int64_t)R.frefs.size(), b_pitch = (int64_t)R.pitch.size(), b_anchor = (int64_t)(R.anchors.size() / 2);
+  const int64_t b_formant = (int64_t)(R.formants.size() / 4), b_z = (int64_t)R.z.size(), b_pre = (int64_t)R.pre.size();
+  const int64_t b_u = fe->u_is_float ? (int64_t)R.u32.size() : (int64_t)R.u64.size(), b_virt = R.virt_pitch;
+  for (sgb_call c : S.calls) { c.bout_begin += b_bout; c.bout_end += b_bout; R.calls.push_back(c); }
+  for (sgb_bout b : S.bouts) {
+    b.syl_begin += b_syl; b.syl_end += b_syl; b.noise_begin += b_noise; b.noise_end += b_noise;
+    if (b.env_id >= 0) b.env_id += b_env;
+    if (b.aglobal_n > 0) b.aglobal_off += b_anchor;     // unused offsets stay what the serial loop writes (0)
+    R.bouts.push_back(b);
+  }
+  for (sgb_syllable y : S.syls) {
+    if (y.pitch_off < 0) y.pitch_off -= b_virt;                    // virtual: -1 - offset
+    else if (y.pitch_len > 0) y.pitch_off += b_pitch;
+    if (y.z_cap > 0) y.z_off += b_z;
+    if (y.ampl_n > 0) y.ampl_off += b_anchor;
+    if (y.reserved0 & 1) y.pitch_anchor_off += b_anchor;
+    R.syls.push_back(y);
+  }
+  for (sgb_noise n : S.noises) {
+    n.u_off += b_u;
+    if (n.anchor_n > 0) n.anchor_off += b_anchor;
+    if (n.env_id >= 0) n.env_id += b_env;
+    if (n.strength_pre_off >= 0) n.strength_pre_off += b_pre;
+    R.noises.push_back(n);
+  }
+  for (sgb_envelope e : S.envs) {
+    e.formant_off += (e.tracks_given == 2) ? b_pre : b_fref;
+    if (e.mouth_n > 0) e.mouth_off += b_anchor;
+    R.envs.push_back(e);
+  }
+  for (sgb_formant_ref r : S.frefs) { r.off += b_formant; R.frefs.push_back(r); }
+  for (int ci : S.sub_call) {
+    CallState &C = fe->calls[ci];
+    if (C.deferred) { C.deferred_env += b_env; C.deferred_bout += b_bout; }
+  }
+  append(R.pitch, S.pitch); append(R.anchors, S.anchors); append(R.formants, S.formants); append(R.z, S.z);
+  append(R.pre, S.pre); append(R.u64, S.u64); append(R.u32, S.u32);
+  append(R.sub_call, S.sub_call); append(R.syl_z_drawn, S.syl_z_drawn); append(R.syl_call, S.syl_call);
+  R.virt_pitch += S.virt_pitch;
+}
+
 }  // namespace
 
 extern "C" {
+
+// test hook: worker threads of the host stage (0 = SGB_FRONTEND_THREADS / the default)
+int sgb_host_set_threads(int32_t n) { sgb_host_threads_override().store(n > 0 ? n : 0); return SGB_OK; }
 
 int sgb_frontend_round_begin(sgb_frontend *fe, sgb_batch_desc *D, int32_t *n_subcalls) {
   if (!fe || !D || !n_subcalls) return ffail(SGB_ERR_INVALID, "null argument");
   Round &R = fe->R;
   R.clear();
-  for (int ci = 0; ci < (int)fe->calls.size(); ci++) {
-    CallState &C = fe->calls[ci];
-    C.deferred = false;
-    C.resolved = false;
-    if (C.next_bout >= C.repeatBout || C.status != SGB_OK) continue;
-    sgb_call cl;
-    cl.bout_begin = (int)R.bouts.size();
-    while (C.next_bout < C.repeatBout) {
-      bool go_on = emit_bout(fe, ci, C.next_bout);
-      C.next_bout++;
-      if (!go_on) break;
-    }
-    cl.bout_end = (int)R.bouts.size();
-    R.calls.push_back(cl);
-    R.sub_call.push_back(ci);
+  const int ncall = (int)fe->calls.size();
+  const int ov = sgb_host_threads_override().load();
+  const int T = std::min(ov > 0 ? ov : sgb_host_threads(), ncall / 16);
+  if (T <= 1) {
+    for (int ci = 0; ci < ncall; ci++) emit_call(fe, ci);
+  } else {
+    // contiguous shards of calls, one thread each, concatenated in call order: the description is the one the
+    // serial loop builds, byte for byte (tests/test_host_api.py)
+    if ((int)fe->shards.size() < T) fe->shards.resize(T);
+    parallel_for(T, [&](int t) {
+      Round &S = fe->shards[t];
+      S.clear();
+      tl_round = &S;
+      const int lo = (int)((int64_t)ncall * t / T), hi = (int)((int64_t)ncall * (t + 1) / T);
+      for (int ci = lo; ci < hi; ci++) emit_call(fe, ci);
+      tl_round = nullptr;
+    }, 1);
+    for (int t = 0; t < T; t++) merge_shard(fe, R, fe->shards[t]);
   }
   for (auto &y : R.syls)
     if (y.kind == 1 && y.pitch_off < 0) y.pitch_off = (int64_t)R.pitch.size() + (-1 - y.pitch_off);
@@ -966,6 +1047,8 @@ int sgb_frontend_resolve(sgb_frontend *fe, sgb_batch *b) {
     j.ncol = std::max(1, nint);        // a bypassed bout has no filter: draw as for one column
     jobs.push_back(std::move(j));
   }
+  const bool trace = getenv("SGB_TRACE_HOST") != nullptr;
+  auto t0 = std::chrono::steady_clock::now();
   parallel_for((int)jobs.size(), [&](int i) {
     Job &J = jobs[i];
     CallState &C = *J.C;
@@ -985,16 +1068,25 @@ int sgb_frontend_resolve(sgb_frontend *fe, sgb_batch *b) {
     for (auto &t : up) J.rows.insert(J.rows.end(), t.begin(), t.end());
     J.nf = (int)up.size();
   });
+  auto t1 = std::chrono::steady_clock::now();
   for (auto &J : jobs) {
     int rc = sgb_batch_set_tracks(b, J.C->deferred_env, J.rows.data(), J.nf, J.ncol);
     if (rc != SGB_OK) return rc;
+  }
+  if (trace) {
+    auto t2 = std::chrono::steady_clock::now();
+    size_t bytes = 0;
+    for (auto &J : jobs) bytes += J.rows.size() * 8;
+    fprintf(stderr, "resolve: %zu calls, draw %.1f ms (parallel), set_tracks %.1f ms, %.1f MB of tracks\n", jobs.size(),
+            std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(t2 - t1).count(),
+            bytes / 1e6);
   }
   return SGB_OK;
 }
 
 int sgb_frontend_round_end(sgb_frontend *fe, sgb_batch *b) {
   if (!fe || !b) return ffail(SGB_ERR_INVALID, "null argument");
-  Round &R = fe->R;
+  Round &R = fe->round();
   std::vector<int32_t> st(R.calls.size()), zu(R.syls.size());
   int rc = sgb_batch_status(b, st.data());
   if (rc != SGB_OK) return rc;

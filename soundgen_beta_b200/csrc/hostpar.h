@@ -16,13 +16,15 @@ inline int sgb_host_threads() {
   }();
   return n;
 }
+inline std::atomic<int> &sgb_host_threads_override() { static std::atomic<int> v(0); return v; }
 template <typename F>
-inline void parallel_for(int n, F f) {
-  const int T = std::min(sgb_host_threads(), n);
+inline void parallel_for(int n, F f, int grain = 8) {
+  const int ov = sgb_host_threads_override().load();
+  const int T = std::min(ov > 0 ? ov : sgb_host_threads(), (n + grain - 1) / grain);
   if (T <= 1) { for (int i = 0; i < n; i++) f(i); return; }
   std::atomic<int> next(0);
   std::vector<std::thread> th;
-  auto work = [&] { for (int i = next.fetch_add(8); i < n; i = next.fetch_add(8)) for (int j = i; j < std::min(n, i + 8); j++) f(j); };
+  auto work = [&] { for (int i = next.fetch_add(grain); i < n; i = next.fetch_add(grain)) for (int j = i; j < std::min(n, i + grain); j++) f(j); };
   for (int t = 1; t < T; t++) th.emplace_back(work);
   work();
   for (auto &t : th) t.join();

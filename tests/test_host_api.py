@@ -77,7 +77,8 @@ def _pool_bytes(d):
     for ptr, n in ((d.pitch, 8 * d.n_pitch), (d.anchors, 16 * d.n_anchors), (d.formants, 32 * d.n_formants),
                    (d.z, 8 * d.n_z), (d.u, esz * d.n_u), (d.pre, 8 * d.n_pre),
                    (d.syllables, C.sizeof(_abi.Syllable) * d.n_syllables), (d.noises, C.sizeof(_abi.Noise) * d.n_noises),
-                   (d.bouts, C.sizeof(_abi.Bout) * d.n_bouts), (d.envelopes, C.sizeof(_abi.Envelope) * d.n_envelopes)):
+                   (d.bouts, C.sizeof(_abi.Bout) * d.n_bouts), (d.envelopes, C.sizeof(_abi.Envelope) * d.n_envelopes),
+                   (d.calls, C.sizeof(_abi.Call) * d.n_calls), (d.formant_index, C.sizeof(_abi.FormantRef) * d.n_formant_refs)):
         out.append(C.string_at(ptr, n) if ptr and n else b'')
     return out
 
@@ -102,3 +103,27 @@ def test_add_many_equals_per_call_add():
     with pytest.raises(ValueError):
         fe2.add_many(bad)
     assert fe2.round_begin()[1] == 0         # nothing of a failed add_many stays registered
+
+
+def test_parallel_round_begin_equals_serial():
+    """round_begin on worker threads (contiguous shards of calls, merged in order) builds the serial description,
+    byte for byte -- stochastic presets (R's stream per call), noise, several bouts included."""
+    L = _abi.load()
+    L.sgb_host_set_threads.argtypes = [C.c_int32]
+    calls = workloads.config4(n=132) + workloads.config3(n=40) + workloads.config2(n=12) + \
+        [dict(sylLen=150, nSyl=2, repeatBout=3, seed=5), dict(sylLen=200, temperature=0, pitchAnchors=[100, 150, 120])]
+    aa = sg.ArgArray(calls, np.float32)
+    out = []
+    try:
+        for threads in (1, 5):
+            L.sgb_host_set_threads(threads)
+            fe = sg.FrontEnd(np.float32)
+            fe.add_many(aa)
+            d, n = fe.round_begin()
+            out.append((n, _pool_bytes(d), fe))
+    finally:
+        L.sgb_host_set_threads(0)
+    assert out[0][0] == out[1][0] == len(calls)
+    names = ['pitch', 'anchors', 'formants', 'z', 'u', 'pre', 'syllables', 'noises', 'bouts', 'envelopes', 'calls', 'formant_index']
+    diff = [nm for nm, a, b in zip(names, out[0][1], out[1][1]) if a != b]
+    assert not diff, diff
