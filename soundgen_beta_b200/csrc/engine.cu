@@ -18,7 +18,7 @@
 #include <cstdlib>
 
 // ---- kernel launchers defined in the other translation units ----
-void launch_control(const sgb_syllable *, int, const double *, const double *, const double *, const Pools &,
+void launch_control(const sgb_syllable *, int, const int32_t *, const double *, const double *, const double *, const Pools &,
                     SylCtrl *, SylLayout *, int64_t *, cudaStream_t);
 void launch_tiles_amp(const sgb_syllable *, int, const SylCtrl *, const SylLayout *, const Pools &, SynthTile *,
                       int64_t *, double *, float4 *, cudaStream_t);
@@ -188,9 +188,10 @@ struct sgb_batch {
   HBuf h_calltab;
   DBuf d_pcm, d_calltab;
   DBuf d_amp, d_amp32, d_wave, d_raw, d_sound, d_voiced, d_filt, d_noise_raw, d_noise_fin, d_env, d_out, d_out64;
-  DBuf d_trk, d_mouth, d_formants_late, d_tiles_tc, d_ntabs;
+  DBuf d_trk, d_mouth, d_formants_late, d_tiles_tc, d_ntabs, d_order;
   struct RunState *rs = nullptr;     // state carried from run_begin to run_finish
   std::vector<double> late_rows;     // host-drawn formant tracks set between begin and finish
+  std::vector<int32_t> h_order;
   std::vector<int> late_envs;        // the envelopes they belong to (deferred again at the next run_begin)
   size_t n_frefs_uploaded = 0;
   bool envs_dirty = false;
@@ -378,7 +379,7 @@ void sgb_batch_destroy(sgb_batch *b) {
                  &b->d_totals, &b->d_summary, &b->d_tiles, &b->d_epmax, &b->p_pitch_w, &b->d_amp, &b->d_amp32, &b->d_wave, &b->d_raw,
                  &b->d_sound, &b->d_voiced, &b->d_filt, &b->d_noise_raw, &b->d_noise_fin, &b->d_env, &b->d_out,
                  &b->d_out64, &b->d_bl, &b->d_place, &b->d_nl, &b->d_envinst, &b->d_plans, &b->d_tw, &b->d_win,
-                 &b->d_fjobs, &b->d_njobs, &b->d_fsegs, &b->d_nsegs, &b->d_max, &b->d_trk, &b->d_mouth, &b->d_formants_late, &b->d_tiles_tc, &b->d_ntabs};
+                 &b->d_fjobs, &b->d_njobs, &b->d_fsegs, &b->d_nsegs, &b->d_max, &b->d_trk, &b->d_mouth, &b->d_formants_late, &b->d_tiles_tc, &b->d_ntabs, &b->d_order};
   for (auto d : all) d->release();
   for (auto &d : b->p_i32) d.release();
   for (auto &d : b->p_f64) d.release();
@@ -504,6 +505,17 @@ int sgb_batch_upload(sgb_batch *b, const sgb_batch_desc *D) {
   int rc;
   if ((rc = upload_array(b, b->d_bouts, D->bouts, sizeof(sgb_bout) * D->n_bouts))) return rc;
   if ((rc = upload_array(b, b->d_syls, D->syllables, sizeof(sgb_syllable) * S))) return rc;
+  {   // K0 runs one warp per syllable and its time grows with the pitch contour: longest first, so that a long
+      // syllable scheduled last does not become the kernel's tail (a preset sweep mixes 50 ms and 3 s syllables)
+    std::vector<int32_t> &order = b->h_order;     // a member: the copy below is asynchronous
+    order.resize((size_t)S);
+    for (int s = 0; s < S; s++) order[s] = s;
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t c) {
+      const int la = b->syls[a].kind == 1 ? b->syls[a].pitch_len : 0, lc = b->syls[c].kind == 1 ? b->syls[c].pitch_len : 0;
+      return la > lc;
+    });
+    if ((rc = upload_array(b, b->d_order, order.data(), sizeof(int32_t) * (size_t)S))) return rc;
+  }
   if ((rc = upload_array(b, b->d_noises, D->noises, sizeof(sgb_noise) * D->n_noises))) return rc;
   if ((rc = upload_array(b, b->d_envs, D->envelopes, sizeof(sgb_envelope) * D->n_envelopes))) return rc;
   if ((rc = upload_array(b, b->d_frefs, D->formant_index, sizeof(sgb_formant_ref) * D->n_formant_refs))) return rc;
@@ -740,7 +752,7 @@ int sgb_batch_run_begin(sgb_batch *b) {
     return m ? atoi(m) : 224;
   }();
   synth_min_rows_set(tc_min_rows);
-  launch_control(d_syl, S, b->d_pitch.as<double>(), b->d_anchors.as<double>(), b->d_z.as<double>(), P, d_ctrl, d_lay,
+  launch_control(d_syl, S, b->d_order.as<int32_t>(), b->d_pitch.as<double>(), b->d_anchors.as<double>(), b->d_z.as<double>(), P, d_ctrl, d_lay,
                  d_tot, st);
   CKL("launch_control");
   launches += 2;

@@ -7,10 +7,10 @@
 #define CTRL_THREADS 32   // one warp per syllable: the stage is bound by the latency of its sequential
                           // part, so what matters is how many syllables are resident per SM
 __global__ void __launch_bounds__(CTRL_THREADS, 16)
-k_control(const sgb_syllable *syl, int S, const double *pitch, const double *anchors, const double *z,
-          Pools P, SylCtrl *ctrl, int tc_min_rows) {
-  int s = blockIdx.x;
-  if (s >= S) return;
+k_control(const sgb_syllable *syl, int S, const int32_t *__restrict__ order, const double *pitch, const double *anchors,
+          const double *z, Pools P, SylCtrl *ctrl, int tc_min_rows) {
+  if ((int)blockIdx.x >= S) return;
+  const int s = order[blockIdx.x];        // longest pitch contours first
   const sgb_syllable sp = syl[s];
   SylCtrl &C = ctrl[s];
   __shared__ int sh_status;
@@ -426,9 +426,9 @@ k_rolloff_api(const double *p, int G, int nH, const double *ro, int n_ro, const 
 static int g_tc_min_rows = 1 << 30;      // K1 dispatch (engine.cu): epochs with >= this many rows go to k_synth_tc
 void synth_min_rows_set(int v) { g_tc_min_rows = v; }
 int synth_min_rows() { return g_tc_min_rows; }
-void launch_control(const sgb_syllable *syl, int S, const double *pitch, const double *anchors, const double *z,
+void launch_control(const sgb_syllable *syl, int S, const int32_t *order, const double *pitch, const double *anchors, const double *z,
                     const Pools &P, SylCtrl *ctrl, SylLayout *lay, int64_t *totals, cudaStream_t st) {
-  k_control<<<S, CTRL_THREADS, 0, st>>>(syl, S, pitch, anchors, z, P, ctrl, g_tc_min_rows);
+  k_control<<<S, CTRL_THREADS, 0, st>>>(syl, S, order, pitch, anchors, z, P, ctrl, g_tc_min_rows);
   k_scan_sizes<<<1, 1024, 0, st>>>(ctrl, S, lay, totals);
 }
 void launch_tiles_amp(const sgb_syllable *syl, int S, const SylCtrl *ctrl, const SylLayout *lay, const Pools &P,
