@@ -7,58 +7,30 @@
 // and a_j(u) = Y_j + w(u) dY_j inside one interval of approx() (source.R:403-405), so for the samples of one
 // interval C and S are small GEMMs  [128 samples x KR] . [KR x 2 blocks]  of a trig matrix (KR values per sample,
 // one complex rotation each) against the interval's amplitude column -- instead of one recurrence step per
-// (row, sample) on the FMA pipe.  A CTA (128 threads) takes one interval of approx() (one glottal cycle of one
-// epoch, a "unit") at a time:
-//   * it stages the amplitude operand of the interval ONCE: Y | dY of up to 1024 rows, split hi + lo in TF32,
-//     from K3's FP32 table into shared memory in the canonical K-major core-matrix layout;
+// (row, sample) on the FMA pipe.  A CTA (128 threads, four per SM, persistent) takes one interval of approx() (one
+// glottal cycle of one epoch, a "unit") at a time:
+//   * it stages the amplitude operand of the interval ONCE: Y | dY of up to 1152 rows from K3's FP32 table, scaled by
+//     a power of two and split hi + lo in FP16 (22 significant bits), in shared memory in the canonical K-major
+//     core-matrix layout, one image per pass of 384 rows;
 //   * per tile of 128 samples (thread = sample = TMEM lane) every thread writes its trig row cos / sin(m theta'),
-//     m < KR, hi + lo; one thread issues 12 tcgen05.mma kind::tf32 (M 128, N = 2 x blocks <= 64, K 8) per pass of
-//     512 rows: 2 k-steps x 3xTF32 terms (hi hi + lo hi + hi lo: FP32-grade products) x (cos, sin), accumulators
-//     in TMEM (128 columns per CTA, four CTAs per SM);
+//     m < KR, hi + lo in FP16, into TMEM with tcgen05.st: the A operand of the MMAs never touches shared memory;
+//   * per pass two threads issue three tcgen05.mma kind::f16 each (M 128, N = 2 x blocks <= 48, K 16: hi hi + lo hi +
+//     hi lo, one chain for C and one for S), FP32 accumulators in TMEM (128 columns per CTA: 32 of A, 96 of C | S);
 //   * tcgen05.ld hands every thread its own lane: C_b, S_b (Y and dY parts) of the pass for ITS sample, reduced
-//     in registers by a complex Horner recurrence in e^{i KR theta'}; the pass offset e^{i 512 p theta'} comes
-//     from the FP64 phase.
+//     in registers by a complex Horner recurrence in e^{2 i KR theta'} on packed FP32 pairs (even | odd blocks); the
+//     pass offset e^{i 384 p theta'} is a rotation seeded from the FP64 phase.
 // Phase: as in the FMA kernel, FP64 closed form per spline piece (K0's quartic), re-anchored at every knot.
-// Numerics: scripts/micro/k1_umma.cu; the GPU parity tests run through this kernel.
+// Why it looks like this (operands in TMEM, FP16, two issuers, pass size): scripts/micro/mma_rate.cu and
+// profiles/README.md.  Epochs with few rows are left to the FP32-pipe kernel (kernels_synth.cu; engine.cu decides).
 #include "engine.cuh"
 #include <cuda_fp16.h>
 #include <cstdlib>
 #include <cstdio>
 
 #define TC_KR 16                         // rows per block = K of the contraction
-#define TC_NB 32                         // blocks per chunk
-#define TC_NCOL (2 * TC_NB)              // N of one MMA: Y and dY of every block
-#define TC_CHUNK (TC_KR * TC_NB)         // 512 rows per chunk
-#define TC_A_BYTES (128 * TC_KR * 4)     // one trig operand: 8 KB
-#define TC_B_BYTES (TC_NCOL * TC_KR * 4) // one amplitude operand: 4 KB
-#define TC_TILE 128
+#define TC_TILE 128                      // samples per tile = M of the MMAs = TMEM lanes
 
 __device__ __forceinline__ uint32_t tc_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint32_t tc_tf32(float x) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
-// K-major, no swizzle, in 16-byte units ((8, n), 2) : ((1, SBO), LBO): a core matrix is 8 rows x 16 bytes;
-// the next 16 bytes of K are LBO = 128 B further, the next 8 rows SBO = (KR / 4) * 128 B further
-__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)(128 >> 4) << 16;
-  d |= (uint64_t)(((TC_KR / 4) * 128) >> 4) << 32;
-  d |= (uint64_t)1 << 46;                 // descriptor version of sm_100
-  return d;
-}
-__device__ __forceinline__ int tc_off(int r, int k) { return (r >> 3) * ((TC_KR / 4) * 128) + (k >> 2) * 128 + (r & 7) * 16 + (k & 3) * 4; }
-__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-               "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}\n"
-               :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0) : "memory");
-}
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, float *v) {
-  uint32_t *r = reinterpret_cast<uint32_t *>(v);
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-                 "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
-                 "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
-                 "=r"(r[30]), "=r"(r[31]) : "r"(taddr));
-}
 
 // -DTC_PROF: wall-clock shares of the kernel's phases as one worker warp sees them (printed per launch)
 #ifdef TC_PROF
@@ -80,12 +52,6 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float *v) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
                  "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(taddr));
-}
-// x = hi + lo with hi on the TF32 grid (round to nearest, ties away) and lo exact in FP32; the tensor core reads
-// the top 19 bits of lo, i.e. 2^-22 of x is kept -- three full-rate integer / FP32 operations instead of two cvt
-__device__ __forceinline__ void tc_split(float x, uint32_t &hi, uint32_t &lo) {
-  hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
-  lo = __float_as_uint(x - __uint_as_float(hi));
 }
 
 // Work list: one unit per interval of approx() of every epoch.  One thread per syllable; intervals without
