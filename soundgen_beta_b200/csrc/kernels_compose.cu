@@ -322,6 +322,8 @@ k_place_voiced(const sgb_syllable *__restrict__ syl, int S, const SylCtrl *__res
     return;
   }
   const double inv_max = C.raw_max;
+  const double rcp_max = 1.0 / inv_max;     // one division per syllable: x * (1 / max) is within an ulp of x / max in
+                                            // double, far below the FP32 the sample is stored in
   int lf = 0;
   if (sp.attackLen > 0.0) {
     lf = (int)floor(sp.attackLen * sp.samplingRate / 1000.0);
@@ -335,7 +337,7 @@ k_place_voiced(const sgb_syllable *__restrict__ syl, int S, const SylCtrl *__res
   const int G = C.nGC;
 #pragma unroll 4
   for (int k = blockIdx.y * blockDim.x + threadIdx.x; k < L; k += gridDim.y * blockDim.x) {
-    double v = (double)src[k] / inv_max;
+    double v = (double)src[k] * rcp_max;
     if (lf > 0) {
       if (k < lf) v = v * r_seq_at(0.0, 1.0, lf, k);                        // fade-in
       if (k >= L - lf) v = v * r_seq_at(0.0, 1.0, lf, (L - 1) - k);         // fade-out = rev(fadeIn)

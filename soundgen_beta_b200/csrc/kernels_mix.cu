@@ -28,6 +28,7 @@ k_noise_final(const sgb_noise *__restrict__ noises, const NoiseLayout *__restric
   const sgb_noise N = noises[n];
   const int L = N.len;
   const float mx = ordered_to_float(maxpool[max_base + n]);
+  const double rcp_mx = 1.0 / (double)mx;     // x * (1 / max): within an ulp of x / max in double, stored as FP32
   const float *src = raw + nl[n].raw_off;
   float *dst = fin + nl[n].raw_off;
   int lf = (int)floor(N.attackLen * N.samplingRate / 1000.0);
@@ -43,7 +44,7 @@ k_noise_final(const sgb_noise *__restrict__ noises, const NoiseLayout *__restric
   }
   for (int k = blockIdx.y * blockDim.x + threadIdx.x; k < L; k += gridDim.y * blockDim.x) {
     double c = (N.strength_pre_off >= 0) ? pre[N.strength_pre_off + k] : contour_eval(&T, L, k);
-    double v = (double)src[k] / (double)mx * exp2(c / 10.0);
+    double v = (double)src[k] * rcp_mx * exp2(c / 10.0);
     if (lf > 0) {
       if (k < lf) v = v * r_seq_at(0.0, 1.0, lf, k);
       if (k >= L - lf) v = v * r_seq_at(0.0, 1.0, lf, (L - 1) - k);
@@ -107,6 +108,7 @@ k_finalize(const sgb_bout *__restrict__ bouts, const BoutLayout *__restrict__ bl
   const BoutLayout L = bl[b];
   const float *src = L.bypass ? (sound + L.sound_off) : (filt + L.filt_off);
   const double mx = L.bypass ? 1.0 : (double)ordered_to_float(maxpool[b]);
+  const double rcp_mx = 1.0 / mx;
   OutT *dst = out + L.out_off;
   // AM pattern
   const bool am = B.amDep > 0.0;
@@ -125,7 +127,7 @@ k_finalize(const sgb_bout *__restrict__ bouts, const BoutLayout *__restrict__ bl
   for (int k = blockIdx.y * blockDim.x + threadIdx.x; k < L.final_len; k += gridDim.y * blockDim.x) {
     double v = 0.0;
     int rel = k - L.final_shift;
-    if (rel >= 0 && rel < L.filt_len) v = (double)src[rel] / mx;
+    if (rel >= 0 && rel < L.filt_len) v = (double)src[rel] * rcp_mx;
     for (int n = B.noise_begin; n < B.noise_end; n++) {
       if (noises[n].mix != 1) continue;
       int64_t r2 = (L.out_off + k) - nl[n].dst_off;
