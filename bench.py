@@ -277,8 +277,9 @@ def main():
     ap.add_argument('--pipeline', type=int, default=8,
                     help='sub-batches (handles / CUDA streams) of the end-to-end measurement')
     ap.add_argument('--fe-threads', type=int, default=3, help='host front-end threads of the from-arguments pipeline')
-    ap.add_argument('--runners', type=int, default=3,
-                    help='host threads that run kernels in the end-to-end pipeline (plus one uploader, one fetcher)')
+    ap.add_argument('--runners', type=int, default=0,
+                    help='host threads that run kernels in the end-to-end pipeline (plus one uploader, one fetcher); '
+                         '0 = 4 when the rank has at least 8 host cores to itself, else 3')
     ap.add_argument('--watchdog', type=int, default=1500, help='seconds after which a stuck run dumps its stacks and exits')
     args = ap.parse_args()
     faulthandler.dump_traceback_later(args.watchdog, exit=True)   # a stuck run reports where, instead of hanging the box
@@ -287,6 +288,8 @@ def main():
         run_reference(args, rank, world)
         return
 
+    if args.runners <= 0:
+        args.runners = 4 if (os.cpu_count() or 8) // max(1, world) >= 8 else 3
     # worker threads of the library's host stage: the ranks of one box share its cores
     os.environ.setdefault('SGB_FRONTEND_THREADS', str(max(1, min(16, (os.cpu_count() or 16) // max(1, world)))))
     import __graft_entry__ as ge
