@@ -306,7 +306,8 @@ typedef struct sgb_soundgen_args {   /* arguments of soundgen(), R/soundgen.R:20
 typedef struct sgb_frontend sgb_frontend;   /* opaque */
 int  sgb_frontend_create(sgb_frontend **out, int32_t u_is_float);
 void sgb_frontend_destroy(sgb_frontend *fe);
-/* Registers one soundgen() call (copies its arguments); returns the call index or an error.
+/* Registers one soundgen() call; returns the call index or an error.  Scalars and tables are copied; the
+ * caller-drawn buffers `z` and `u` (rng_mode 2) are referenced and must stay valid until the call's last round ended.
  * The host stage up to the bout loop (validation, hyper-parameters, rbinom draws) runs here. */
 int  sgb_frontend_add(sgb_frontend *fe, const sgb_soundgen_args *args);
 /* n calls that differ only in their seed (rng_mode 0): returns the index of the first. */

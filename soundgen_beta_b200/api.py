@@ -142,11 +142,13 @@ class FrontEnd:
         _check(self.L.sgb_frontend_create(C.byref(self.h), 1 if self.u_dtype == np.float32 else 0))
         self.n_calls = 0
         self.n_sub = 0
+        self._keep_alive = []
 
     def close(self):
         if self.h:
             self.L.sgb_frontend_destroy(self.h)
             self.h = C.c_void_p()
+        self._keep_alive = []
 
     def __del__(self):
         try:
@@ -157,6 +159,7 @@ class FrontEnd:
     def add(self, warn=None, seeds=None, **kw):
         """One soundgen() call; with `seeds` (a sequence) the same argument list once per seed."""
         A, keep = self.marshal(**kw)
+        self._keep_alive.append(keep)      # the library references the caller-drawn z / u buffers until the rounds end
         if seeds is not None:
             sd = np.ascontiguousarray(np.asarray(seeds, dtype=np.int64) & 0xFFFFFFFF, dtype=np.uint32)
             A.rng_mode = 0
@@ -183,12 +186,14 @@ class FrontEnd:
     def add_many(self, args):
         """Every call of an `ArgArray` (argument lists already in the library's struct form) in one library call."""
         rc = self.L.sgb_frontend_add_many(self.h, args.arr, args.n)
+        self._keep_alive.append(args)
         self._raise(rc)
         self.n_calls = rc + args.n
         return rc
 
     def clear(self):
         _check(self.L.sgb_frontend_clear(self.h))
+        self._keep_alive = []
         self.n_calls = 0
         self.n_sub = 0
 

@@ -190,9 +190,10 @@ struct CallState {
   bool has_formants = false, has_formantsNoise = false;
   RRng rng;
   bool use_rng = true;
-  std::vector<std::vector<double>> zbuf;   // rng_mode 2
-  std::vector<std::vector<double>> ubuf;
-  std::vector<std::vector<float>> ubuf32;
+  // rng_mode 2: the caller's buffers, by reference (they stay valid until the calls' last round has ended)
+  struct Span { const void *p; int64_t n; };
+  std::vector<Span> zbuf;                  // one stream of normals per voiced syllable
+  std::vector<Span> ubuf;                  // one buffer of uniforms per noise (float or double: the handle's u type)
   size_t zi = 0, ui = 0;
   // derived by the host stage before the bout loop
   int nSyl = 1, repeatBout = 1, wl_points = 0;
@@ -483,13 +484,13 @@ static int build_call(const sgb_frontend *fe, const sgb_soundgen_args *args, Cal
                                         "caller buffers only cover the device draws");
     }
     const double *zp = a.z;
-    for (int i = 0; i < a.n_z; i++) { C.zbuf.emplace_back(zp, zp + a.z_len[i]); zp += a.z_len[i]; }
+    for (int i = 0; i < a.n_z; i++) { C.zbuf.push_back(CallState::Span{zp, a.z_len[i]}); zp += a.z_len[i]; }
     if (fe->u_is_float) {
       const float *up = (const float *)a.u;
-      for (int i = 0; i < a.n_u; i++) { C.ubuf32.emplace_back(up, up + a.u_len[i]); up += a.u_len[i]; }
+      for (int i = 0; i < a.n_u; i++) { C.ubuf.push_back(CallState::Span{up, a.u_len[i]}); up += a.u_len[i]; }
     } else {
       const double *up = (const double *)a.u;
-      for (int i = 0; i < a.n_u; i++) { C.ubuf.emplace_back(up, up + a.u_len[i]); up += a.u_len[i]; }
+      for (int i = 0; i < a.n_u; i++) { C.ubuf.push_back(CallState::Span{up, a.u_len[i]}); up += a.u_len[i]; }
     }
   }
   C.wl_points = (int)(std::floor(a.windowLength / 1000 * a.samplingRate / 2) * 2);      // :317
@@ -796,8 +797,9 @@ bool emit_bout(sgb_frontend *fe, int ci, int b) {
       }
       if (!C.use_rng) {
         if (C.zi < C.zbuf.size()) {
-          y.z_off = (int64_t)R.z.size(); y.z_cap = (int)C.zbuf[C.zi].size();
-          R.z.insert(R.z.end(), C.zbuf[C.zi].begin(), C.zbuf[C.zi].end());
+          const double *zp = (const double *)C.zbuf[C.zi].p;
+          y.z_off = (int64_t)R.z.size(); y.z_cap = (int)C.zbuf[C.zi].n;
+          R.z.insert(R.z.end(), zp, zp + C.zbuf[C.zi].n);
         }
         C.zi++;
         zdrawn = -1;
@@ -853,11 +855,10 @@ bool emit_bout(sgb_frontend *fe, int ci, int b) {
           for (int64_t i = 0; i < nu; i++) dst[i] = g.unif_rand();
         }
       } else {
-        bool ok = fe->u_is_float ? (C.ui < C.ubuf32.size() && (int64_t)C.ubuf32[C.ui].size() >= nu)
-                                 : (C.ui < C.ubuf.size() && (int64_t)C.ubuf[C.ui].size() >= nu);
+        bool ok = C.ui < C.ubuf.size() && C.ubuf[C.ui].n >= nu;
         if (!ok) { C.status = SGB_ERR_STREAM; C.ui++; continue; }
-        if (fe->u_is_float) R.u32.insert(R.u32.end(), C.ubuf32[C.ui].begin(), C.ubuf32[C.ui].begin() + nu);
-        else R.u64.insert(R.u64.end(), C.ubuf[C.ui].begin(), C.ubuf[C.ui].begin() + nu);
+        if (fe->u_is_float) { const float *up = (const float *)C.ubuf[C.ui].p; R.u32.insert(R.u32.end(), up, up + nu); }
+        else { const double *up = (const double *)C.ubuf[C.ui].p; R.u64.insert(R.u64.end(), up, up + nu); }
         C.ui++;
       }
       R.noises.push_back(N);
