@@ -254,6 +254,13 @@ int sgb_batch_z_used(sgb_batch *b, int32_t *out);
 /* sizeof() of the ABI structs, for bindings to verify their mirrors:
  * syllable, envelope, noise, bout, call, formant_ref, batch_desc, run_info, soundgen_args. */
 int sgb_abi_sizes(int32_t *out, int32_t cap);
+/* The additive synthesis has two kernels: epochs with at least `rows` rows run on the tensor cores, the others on the
+   FP32 pipe (default 224, or SGB_SYNTH / SGB_SYNTH_MIN_ROWS from the environment).  0 = tensor cores only, a huge value =
+   FP32 pipe only, -1 = back to the default.  Applies to batches that run after the call; meant for tests and A/B runs. */
+int sgb_synth_min_rows_set(int32_t rows);
+/* Worker threads of the library's host stage (front-end registration, round_begin, resolve, layout checks):
+   0 = SGB_FRONTEND_THREADS from the environment, else the hardware's, at most 16. */
+int sgb_host_set_threads(int32_t n);
 
 /* ------------------------------------------------------------------------- */
 /* Host front-end: the host stage of soundgen() (R/soundgen.R:279-733)         */

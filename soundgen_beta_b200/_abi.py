@@ -128,7 +128,7 @@ EXPORTS = ['sgb_version', 'sgb_last_error', 'sgb_device_count', 'sgb_set_device'
            'sgb_batch_artefacts', 'sgb_batch_artefact_ints', 'sgb_batch_pitch_per_gc', 'sgb_batch_checksums', 'sgb_batch_debug_state',
            'sgb_get_rolloff', 'sgb_get_spectral_envelope', 'sgb_filter_len', 'sgb_filter',
            'sgb_batch_run_begin', 'sgb_batch_run_finish', 'sgb_batch_bout_geometry', 'sgb_batch_set_tracks',
-           'sgb_batch_z_used', 'sgb_abi_sizes', 'sgb_frontend_create', 'sgb_frontend_destroy', 'sgb_frontend_add', 'sgb_frontend_add_seeded', 'sgb_frontend_add_many', 'sgb_frontend_clear',
+           'sgb_batch_z_used', 'sgb_abi_sizes', 'sgb_synth_min_rows_set', 'sgb_host_set_threads', 'sgb_frontend_create', 'sgb_frontend_destroy', 'sgb_frontend_add', 'sgb_frontend_add_seeded', 'sgb_frontend_add_many', 'sgb_frontend_clear',
            'sgb_frontend_round_begin', 'sgb_frontend_resolve', 'sgb_frontend_round_end', 'sgb_frontend_round_calls',
            'sgb_frontend_status', 'sgb_frontend_warnings', 'sgb_frontend_rng_state', 'sgb_frontend_h2d_bytes',
            'sgb_rng_draw', 'sgb_smooth_contour']
@@ -199,6 +199,8 @@ def load():
     L.sgb_frontend_add_seeded.argtypes = [vp, C.POINTER(SoundgenArgs), vp, i32]
     L.sgb_frontend_add_many.argtypes = [vp, vp, i32]
     L.sgb_frontend_clear.argtypes = [vp]
+    L.sgb_synth_min_rows_set.argtypes = [i32]
+    L.sgb_host_set_threads.argtypes = [i32]
     L.sgb_frontend_round_begin.argtypes = [vp, C.POINTER(BatchDesc), C.POINTER(i32)]
     L.sgb_frontend_resolve.argtypes = [vp, vp]
     L.sgb_frontend_round_end.argtypes = [vp, vp]

@@ -60,6 +60,7 @@ int stft_timeout_flag();
 int *compose_debug_buffer();
 // ------------------------------------------------------------------ errors ---
 static thread_local std::string g_err;
+static int g_synth_min_rows_override = -1;      // sgb_synth_min_rows_set
 static int fail(int code, const char *fmt, ...) {
   char buf[512];
   va_list ap;
@@ -744,13 +745,14 @@ int sgb_batch_run_begin(sgb_batch *b) {
 
   // ---- K0 control + size scan ----
   CK(cudaMemsetAsync(d_tot, 0, 64, st));
-  static const int tc_min_rows = [] {
+  static const int tc_min_rows_env = [] {
     const char *e = getenv("SGB_SYNTH");
     if (e && !strcmp(e, "ffma")) return 1 << 30;
     if (e && !strcmp(e, "tc")) return 0;
     const char *m = getenv("SGB_SYNTH_MIN_ROWS");
     return m ? atoi(m) : 224;
   }();
+  const int tc_min_rows = g_synth_min_rows_override >= 0 ? g_synth_min_rows_override : tc_min_rows_env;
   synth_min_rows_set(tc_min_rows);
   launch_control(d_syl, S, b->d_order.as<int32_t>(), b->d_pitch.as<double>(), b->d_anchors.as<double>(), b->d_z.as<double>(), P, d_ctrl, d_lay,
                  d_tot, st);
@@ -1241,6 +1243,9 @@ int sgb_batch_z_used(sgb_batch *b, int32_t *out) {
   for (size_t s = 0; s < b->summary.size(); s++) out[s] = b->summary[s].z_used;
   return SGB_OK;
 }
+
+// K1 dispatch threshold for the batches that run after this call (tests; -1 = environment / default 224 rows)
+int sgb_synth_min_rows_set(int32_t rows) { g_synth_min_rows_override = rows < 0 ? -1 : rows; return SGB_OK; }
 
 int sgb_abi_sizes(int32_t *out, int32_t cap) {
   const int32_t v[] = {(int32_t)sizeof(sgb_syllable), (int32_t)sizeof(sgb_envelope), (int32_t)sizeof(sgb_noise),

@@ -196,3 +196,36 @@ def test_linearity_property_full_size():
     a = sg.filter_sound(x, np.full(1200, 1.0), 2400)
     b = sg.filter_sound(x, np.full(1200, 7.5), 2400)
     assert a.size == 47400 and np.max(np.abs(a - b)) < 1e-5
+
+
+def test_both_synthesis_kernels_agree():
+    """K1 has two kernels (tcgen05 contraction for epochs with many rows, packed-FP32 Clenshaw for the others): the
+    same batch through either gives the same integer artefacts and waveforms within 2e-5 of peak, and each agrees
+    with the oracle (the dispatch threshold is moved with sgb_synth_min_rows_set)."""
+    from soundgen_beta_b200 import _abi
+    L = _abi.load()
+    calls = workloads.config3(n=24) + workloads.config1(n=8)
+    outs = {}
+    try:
+        for mode, rows in (('tc', 0), ('ffma', 1 << 30), ('default', -1)):
+            assert L.sgb_synth_min_rows_set(rows) == 0
+            bb = sg.BatchBuilder(u_dtype=np.float32)
+            for kw in calls:
+                bb.add_soundgen(**dict(kw))
+            bt = sg.Batch()
+            bt.upload(bb.build())
+            bt.run()
+            outs[mode] = [np.array(w, copy=True) for w in bt.fetch(np.float64)]
+            bt.close()
+    finally:
+        L.sgb_synth_min_rows_set(-1)
+    for a, b, c in zip(outs['tc'], outs['ffma'], outs['default']):
+        assert a.shape == b.shape == c.shape        # zero-crossing trims agree: same lengths
+        pk = np.max(np.abs(b))
+        assert np.max(np.abs(a - b)) <= 2e-5 * pk and np.max(np.abs(c - b)) <= 2e-5 * pk
+    for i in (0, 5, 23, 27):
+        ref = _oracle_call(calls[i])
+        for mode in ('tc', 'ffma'):
+            y = outs[mode][i]
+            assert y.shape == ref.shape
+            assert np.max(np.abs(y - ref)) <= 1e-4 * np.max(np.abs(ref)), (mode, i)

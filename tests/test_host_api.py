@@ -109,7 +109,6 @@ def test_parallel_round_begin_equals_serial():
     """round_begin on worker threads (contiguous shards of calls, merged in order) builds the serial description,
     byte for byte -- stochastic presets (R's stream per call), noise, several bouts included."""
     L = _abi.load()
-    L.sgb_host_set_threads.argtypes = [C.c_int32]
     calls = workloads.config4(n=132) + workloads.config3(n=40) + workloads.config2(n=12) + \
         [dict(sylLen=150, nSyl=2, repeatBout=3, seed=5), dict(sylLen=200, temperature=0, pitchAnchors=[100, 150, 120])]
     aa = sg.ArgArray(calls, np.float32)
