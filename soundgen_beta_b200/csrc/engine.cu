@@ -37,7 +37,7 @@ void launch_compose(const sgb_syllable *, int, SylCtrl *, const SylLayout *, con
 void launch_place_voiced(const sgb_syllable *, int, const SylCtrl *, const SylLayout *, const SylPlace *,
                          const Pools &, const float *, float *, int, cudaStream_t);
 void launch_env_tracks(const EnvInst *, int, const sgb_envelope *, const sgb_formant_ref *, const double *,
-                       const double *, double *, double *, cudaStream_t);
+                       const double *, double *, double *, void *, cudaStream_t);
 void launch_envelope_f32(const EnvInst *, int, int, const sgb_envelope *, const sgb_formant_ref *, const double *,
                          const double *, const double *, const double *, const double *, float *, cudaStream_t);
 void launch_envelope_f64(const EnvInst *, int, int, const sgb_envelope *, const sgb_formant_ref *, const double *,
@@ -189,7 +189,7 @@ struct sgb_batch {
   HBuf h_calltab;
   DBuf d_pcm, d_calltab;
   DBuf d_amp, d_amp32, d_wave, d_raw, d_sound, d_voiced, d_filt, d_noise_raw, d_noise_fin, d_env, d_out, d_out64;
-  DBuf d_trk, d_mouth, d_formants_late, d_tiles_tc, d_ntabs, d_order;
+  DBuf d_trk, d_mouth, d_formants_late, d_tiles_tc, d_ntabs, d_order, d_mtabs;
   struct RunState *rs = nullptr;     // state carried from run_begin to run_finish
   std::vector<double> late_rows;     // host-drawn formant tracks set between begin and finish
   std::vector<int32_t> h_order;
@@ -380,7 +380,7 @@ void sgb_batch_destroy(sgb_batch *b) {
                  &b->d_totals, &b->d_summary, &b->d_tiles, &b->d_epmax, &b->p_pitch_w, &b->d_amp, &b->d_amp32, &b->d_wave, &b->d_raw,
                  &b->d_sound, &b->d_voiced, &b->d_filt, &b->d_noise_raw, &b->d_noise_fin, &b->d_env, &b->d_out,
                  &b->d_out64, &b->d_bl, &b->d_place, &b->d_nl, &b->d_envinst, &b->d_plans, &b->d_tw, &b->d_win,
-                 &b->d_fjobs, &b->d_njobs, &b->d_fsegs, &b->d_nsegs, &b->d_max, &b->d_trk, &b->d_mouth, &b->d_formants_late, &b->d_tiles_tc, &b->d_ntabs, &b->d_order};
+                 &b->d_fjobs, &b->d_njobs, &b->d_fsegs, &b->d_nsegs, &b->d_max, &b->d_trk, &b->d_mouth, &b->d_formants_late, &b->d_tiles_tc, &b->d_ntabs, &b->d_order, &b->d_mtabs};
   for (auto d : all) d->release();
   for (auto &d : b->p_i32) d.release();
   for (auto &d : b->p_f64) d.release();
@@ -1128,9 +1128,10 @@ int sgb_batch_run_finish(sgb_batch *b, sgb_run_info *info_out) {
   }
   CK(cudaEventRecord(ev[5], st)); trace_mark(b, 5);   // assemble (part 1)
   // ---- K4 envelopes (bouts + noises) ----
+  CK(b->d_mtabs.ensure(contour_tab_bytes() * std::max<size_t>(envinst.size(), 1)));
   launch_env_tracks(b->d_envinst.as<EnvInst>(), (int)envinst.size(), b->d_envs.as<sgb_envelope>(),
                     b->d_frefs.as<sgb_formant_ref>(), b->d_formants.as<double>(), b->d_anchors.as<double>(),
-                    b->d_trk.as<double>(), b->d_mouth.as<double>(), st);
+                    b->d_trk.as<double>(), b->d_mouth.as<double>(), b->d_mtabs.p, st);
   CKL("launch_env_tracks");
   launch_envelope_f32(b->d_envinst.as<EnvInst>(), (int)envinst.size(), max_nc, b->d_envs.as<sgb_envelope>(),
                       b->d_frefs.as<sgb_formant_ref>(), b->d_formants.as<double>(), b->d_formants_late.as<double>(), b->d_trk.as<double>(),
@@ -1543,8 +1544,10 @@ int sgb_get_spectral_envelope(int32_t nr, int32_t nc, const sgb_envelope *env, c
     if (E.mouth_n) CK(cudaMemcpy(dA.p, mouth_anchors, 16 * (size_t)E.mouth_n, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dI.p, &I, sizeof I, cudaMemcpyHostToDevice));
     CK(dT.ensure(8 * (size_t)std::max(1, nc * E.n_formants * 3))); CK(dM.ensure(8 * (size_t)nc));
+    DBuf dTab;
+    CK(dTab.ensure(contour_tab_bytes()));
     launch_env_tracks(dI.as<EnvInst>(), 1, dE.as<sgb_envelope>(), dR.as<sgb_formant_ref>(), dF.as<double>(),
-                      dA.as<double>(), dT.as<double>(), dM.as<double>(), 0);
+                      dA.as<double>(), dT.as<double>(), dM.as<double>(), dTab.p, 0);
     CKL("launch_env_tracks");
     launch_envelope_f64(dI.as<EnvInst>(), 1, nc, dE.as<sgb_envelope>(), dR.as<sgb_formant_ref>(), dF.as<double>(),
                         nullptr, dT.as<double>(), dM.as<double>(), nullptr, dO.as<double>(), 0);

@@ -158,20 +158,36 @@ k_envelope(const EnvInst *__restrict__ inst, const sgb_envelope *__restrict__ en
 // spline(approx(y, n = nPoints + 2^smoothLinearFactor, x = time)$y, n = nc)) and the mouth-opening
 // contour (:436-443) depend on the column only through the evaluation point, so their coefficients
 // are solved once per instance here and k_envelope just reads the per-column values.
+// The mouth-opening contour's fit (a loess fit is a millisecond of FP64 on one thread): one thread per instance
+// here, instead of thread 0 of every 128-thread CTA of k_env_tracks while the other 127 wait.
+__global__ void k_mouth_tabs(const EnvInst *__restrict__ inst, int n_inst, const sgb_envelope *__restrict__ envs,
+                             const double *__restrict__ anchors, ContourTab *__restrict__ tabs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_inst) return;
+  const EnvInst I = inst[i];
+  const sgb_envelope E = envs[I.env_id];
+  if (E.mouth_n > 0 && E.n_formants > 0 && E.tracks_given != 2) {
+    // getSmoothContour(len = nc, mouthAnchors, valueFloor = 0, valueCeiling = 1): samplingRate is
+    // not passed, so the span heuristic sees getSmoothContour's own default of 16000
+    contour_prepare(&tabs[i], anchors + 2 * E.mouth_off, E.mouth_n, I.nc, 16000.0, true, 0.0, true, 1.0, false,
+                    E.mouth_method);       // a failing fit is reported by the host (contour_fits)
+  }
+}
+
 __global__ void __launch_bounds__(ENV_THREADS)
 k_env_tracks(const EnvInst *__restrict__ inst, const sgb_envelope *__restrict__ envs,
              const sgb_formant_ref *__restrict__ fidx, const double *__restrict__ formants,
-             const double *__restrict__ anchors, double *__restrict__ trk, double *__restrict__ mouth) {
+             const ContourTab *__restrict__ tabs, double *__restrict__ trk, double *__restrict__ mouth) {
   const EnvInst I = inst[blockIdx.x];
   const sgb_envelope E = envs[I.env_id];
   const int nc = I.nc, F = E.n_formants;
   __shared__ ContourTab T;
   if (E.mouth_n > 0 && F > 0 && E.tracks_given != 2) {
-    if (threadIdx.x == 0) {
-      // getSmoothContour(len = nc, mouthAnchors, valueFloor = 0, valueCeiling = 1): samplingRate is
-      // not passed, so the span heuristic sees getSmoothContour's own default of 16000
-      contour_prepare(&T, anchors + 2 * E.mouth_off, E.mouth_n, nc, 16000.0, true, 0.0, true, 1.0, false,
-                      E.mouth_method);     // a failing fit is reported by the host (contour_fits)
+    {
+      static_assert(sizeof(ContourTab) % 8 == 0, "ContourTab is copied as doubles");
+      const double *g = reinterpret_cast<const double *>(&tabs[blockIdx.x]);
+      double *d = reinterpret_cast<double *>(&T);
+      for (int i = threadIdx.x; i < (int)(sizeof(ContourTab) / 8); i += blockDim.x) d[i] = g[i];
     }
     __syncthreads();
     for (int c = threadIdx.x; c < nc; c += blockDim.x) mouth[I.col0 + c] = (T.status == SGB_OK) ? contour_eval(&T, nc, c) : 0.5;
@@ -199,10 +215,11 @@ k_env_tracks(const EnvInst *__restrict__ inst, const sgb_envelope *__restrict__ 
 }
 
 void launch_env_tracks(const EnvInst *inst, int n_inst, const sgb_envelope *envs, const sgb_formant_ref *fidx,
-                       const double *formants, const double *anchors, double *trk, double *mouth,
+                       const double *formants, const double *anchors, double *trk, double *mouth, void *tabs,
                        cudaStream_t st) {
   if (n_inst <= 0) return;
-  k_env_tracks<<<n_inst, ENV_THREADS, 0, st>>>(inst, envs, fidx, formants, anchors, trk, mouth);
+  k_mouth_tabs<<<(n_inst + 31) / 32, 32, 0, st>>>(inst, n_inst, envs, anchors, (ContourTab *)tabs);
+  k_env_tracks<<<n_inst, ENV_THREADS, 0, st>>>(inst, envs, fidx, formants, (const ContourTab *)tabs, trk, mouth);
 }
 
 void launch_envelope_f32(const EnvInst *inst, int n_inst, int max_nc, const sgb_envelope *envs,
