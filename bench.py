@@ -508,6 +508,15 @@ def main():
                        'frac': ach / hbm, 'traffic': traffic_f,
                        'peak_source': 'MEASURED_PEAKS.json' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s',
                        'algorithmic': '8 B per output sample x %d samples per launch' % info.filter_samples,
+                       # the roofline that actually binds it: shared-memory traffic of the FFT passes.  Tuned plans
+                       # (800 / 1200 / 2400 / 160 points): 3 forward + 3 inverse passes with the middle two fused = 5
+                       # read + write sweeps of 8 B per complex point; a complex FFT carries two real frames and the
+                       # hop is a quarter window: 5 x 16 B x wl / (2 x wl / 4) = 160 B per output sample
+                       'smem': {'algorithmic_bytes_per_sample': 160,
+                                'achieved': 160.0 * info.filter_samples / (ms_filter * 1e-3) / 1e9,
+                                'peak': 148 * 128 * 1.965, 'unit': 'GB/s',
+                                'frac': 160.0 * info.filter_samples / (ms_filter * 1e-3) / 1e9 / (148 * 128 * 1.965),
+                                'peak_source': 'nominal: 148 SMs x 128 B per clock x 1965 MHz'},
                        'note': 'the kernel is bound by its shared-memory FFT passes, not by HBM: see '
                                'profiles/r02_ncu_k_stft_summary.txt (shared-memory wavefronts, issue slots)'}
     if roofline is None:
