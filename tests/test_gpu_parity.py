@@ -229,3 +229,24 @@ def test_both_synthesis_kernels_agree():
             y = outs[mode][i]
             assert y.shape == ref.shape
             assert np.max(np.abs(y - ref)) <= 1e-4 * np.max(np.abs(ref)), (mode, i)
+
+
+@pytest.mark.parametrize('rows', [7, 16, 17, 127, 128, 129, 383, 384, 385, 767, 769, 1151, 1152, 1153, 1300])
+def test_tensor_core_kernel_at_pass_boundaries(rows):
+    """k_synth_tc works in blocks of 16 rows, passes of 384 and resident groups of 1152: epochs whose row count sits
+    on either side of each boundary (flat pitch at 48 kHz, every harmonic below Nyquist kept) against the oracle,
+    with the dispatch forced to the tensor-core kernel."""
+    from soundgen_beta_b200 import _abi
+    L = _abi.load()
+    f0 = 24000.0 / (rows + 0.5)                       # harmonics 1..rows lie below Nyquist
+    kw = dict(sylLen=max(300, int(6000.0 / f0)), samplingRate=48000, invalidArgAction='ignore', temperature=0,
+              pitchAnchors=[f0, f0 * 1.0001], pitchFloor=1, rolloff=-1, rolloffOct=0, rolloffKHz=0, nonlinBalance=0,
+              attackLen=10, addSilence=0)
+    ref = _oracle_call(kw)
+    try:
+        assert L.sgb_synth_min_rows_set(0) == 0
+        y = sg.soundgen(**kw)
+    finally:
+        L.sgb_synth_min_rows_set(-1)
+    assert y.shape == ref.shape
+    assert np.max(np.abs(y - ref)) <= 1e-4 * np.max(np.abs(ref))
