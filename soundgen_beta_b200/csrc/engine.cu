@@ -772,7 +772,12 @@ int sgb_batch_run_begin(sgb_batch *b) {
   b->last_amp = amp_total; b->last_wave = wave_total; b->last_raw = raw_total; b->last_tiles = n_tiles;
   if (n_tiles > 2000000000LL) return fail(SGB_ERR_UNSUPPORTED, "batch too large: %lld synthesis tiles", (long long)n_tiles);
   CK(b->d_amp.ensure(8 * (size_t)std::max<int64_t>(amp_total, 1)));
-  CK(b->d_amp32.ensure(16 * (size_t)std::max<int64_t>(amp_total, 1)));
+  {   // epochs of the tensor-core kernel use the first half of their region ({Y, dY} pairs): a fresh buffer is cleared
+      // once so that the unused halves are zeros, not allocator leftovers (sgb_batch_checksums covers the buffer)
+    const size_t cap0 = b->d_amp32.cap;
+    CK(b->d_amp32.ensure(16 * (size_t)std::max<int64_t>(amp_total, 1)));
+    if (b->d_amp32.cap != cap0) CK(cudaMemsetAsync(b->d_amp32.p, 0, b->d_amp32.cap, st));
+  }
   CK(b->d_wave.ensure(4 * (size_t)std::max<int64_t>(wave_total, 4)));
   CK(b->d_raw.ensure(4 * (size_t)std::max<int64_t>(raw_total, 4)));
   CK(b->d_tiles.ensure(sizeof(SynthTile) * (size_t)std::max<int64_t>(n_tiles, 1)));

@@ -51,7 +51,7 @@ struct SynthTile { int32_t syl; int32_t epoch; int32_t k0; int32_t gi_lo; int32_
 // One unit of the tensor-core K1: the samples [kbeg, kend) of one epoch that lie in ONE interval of approx()
 // (one amplitude column), with everything the kernel needs so that it never touches SylCtrl.
 struct TcUnit {
-  int64_t col_off;      // first float4 of the interval's column in the amplitude table (row j - 1)
+  int64_t col_off;      // first {Y, dY} pair (float2) of the interval's column in the amplitude table (row j - 1)
   int64_t wave_off;     // sample 0 of the epoch in the wave buffer
   int64_t pc_off;       // the syllable's first spline piece
   double x_first, by, x_last, inv_sr_np1;

@@ -217,7 +217,7 @@ __global__ void k_build_tiles(const SylCtrl *ctrl, int S, const SylLayout *lay, 
 #define AMP_DR 10        // rows per thread of the dense variant (rows <= 2560)
 __global__ void __launch_bounds__(256, 3)
 k_amp(const sgb_syllable *syl, int S, const SylCtrl *ctrl, const SylLayout *lay, Pools P, double *amp,
-      float4 *amp32) {
+      float4 *amp32, int tc_min_rows) {
   int s = blockIdx.x;
   if (s >= S) return;
   const SylCtrl &C = ctrl[s];
@@ -242,6 +242,9 @@ k_amp(const sgb_syllable *syl, int S, const SylCtrl *ctrl, const SylLayout *lay,
       const int g0 = C.ep_start[e] - 1;
       double *oe = out + C.ep_amp_off[e];
       float4 *oe32 = out32 + C.ep_amp_off[e];
+      // the tensor-core kernel reads {Y, dY} pairs (8 B per element, packed at the start of the epoch's region); the
+      // FP32-pipe kernel wants {Y, Y, dY, dY} (one broadcast LDS.128 feeds both packed lanes)
+      const bool tc_ep = rows >= tc_min_rows;
       const bool tabled = (n == 0) || (Hk <= AMP_MAXH && n <= AMP_MAXS);
       __syncthreads();
       if (tabled && n > 0) {
@@ -315,7 +318,8 @@ k_amp(const sgb_syllable *syl, int S, const SylCtrl *ctrl, const SylLayout *lay,
             if (g < gb) oc[j - 1] = v;
             if (g > ga) {   // {Y, Y, dY, dY}: one 16-byte load gives K1 both packed FFMA2 operands
               const float y = (float)prev[i], dy = (float)(v - prev[i]);
-              oc32[j - 1] = make_float4(y, y, dy, dy);
+              if (tc_ep) reinterpret_cast<float2 *>(oe32)[(int64_t)(g - 1 - g0) * rows + (j - 1)] = make_float2(y, dy);
+              else oc32[j - 1] = make_float4(y, y, dy, dy);
             }
             prev[i] = v;
           }
@@ -364,7 +368,8 @@ k_amp(const sgb_syllable *syl, int S, const SylCtrl *ctrl, const SylLayout *lay,
             if (g < gb) oc[j - 1] = v;
             if (g > ga) {   // {Y, Y, dY, dY}: one 16-byte load gives K1 both packed FFMA2 operands
               const float y = (float)prev[i], dy = (float)(v - prev[i]);
-              oc32[j - 1] = make_float4(y, y, dy, dy);
+              if (tc_ep) reinterpret_cast<float2 *>(oe32)[(int64_t)(g - 1 - g0) * rows + (j - 1)] = make_float2(y, dy);
+              else oc32[j - 1] = make_float4(y, y, dy, dy);
             }
             prev[i] = v;
           }
@@ -435,7 +440,7 @@ void launch_tiles_amp(const sgb_syllable *syl, int S, const SylCtrl *ctrl, const
                       SynthTile *tiles, int64_t *totals, double *amp, float4 *amp32, cudaStream_t st) {
   k_build_tiles<<<(S + 127) / 128, 128, 0, st>>>(ctrl, S, lay, P, tiles, totals, g_tc_min_rows);
   dim3 g(S, S >= 2048 ? 1 : (S >= 256 ? 4 : 16));
-  k_amp<<<g, 256, 0, st>>>(syl, S, ctrl, lay, P, amp, amp32);
+  k_amp<<<g, 256, 0, st>>>(syl, S, ctrl, lay, P, amp, amp32, g_tc_min_rows);
 }
 void launch_rolloff_api(const double *p, int G, int nH, const double *ro, int n_ro, const double *roct, int n_roct,
                         const double *rk, int n_rk, double rolloffParab, double rolloffParabHarm,

@@ -97,7 +97,7 @@ __global__ void k_build_units_tc(const sgb_syllable *syl, const SylCtrl *ctrl, i
       const double u = (double)(x_first_i + kcur);
       while (a < G - 1 && u >= kt[a + 1]) a++;
       TcUnit U;
-      U.col_off = lay[s].amp_off + C.ep_amp_off[e] + (int64_t)i * J;
+      U.col_off = 2 * (lay[s].amp_off + C.ep_amp_off[e]) + (int64_t)i * J;      // in {Y, dY} pairs (8 B)
       U.wave_off = lay[s].wave_off + C.ep_wave_off[e];
       U.pc_off = o;
       U.x_first = x_first; U.by = by; U.x_last = x_last;
@@ -208,7 +208,7 @@ k_synth_tc(const TcUnit *__restrict__ units, int nunits, const double *__restric
     if (U.kend <= U.kbeg) continue;
     TP(0)
     const int J = U.J;
-    const float4 *__restrict__ col = amp + U.col_off;               // {Y, Y, dY, dY} of the interval, row j - 1
+    const float2 *__restrict__ col = reinterpret_cast<const float2 *>(amp) + U.col_off;   // {Y, dY} of the interval, row j - 1
     const double *__restrict__ pcs = pc + SYNTH_PC * U.pc_off;
     const int x_first_i = (int)U.x_first;
     const float inv_dx = __frcp_rn((float)(U.xn - U.xg));
@@ -231,7 +231,7 @@ k_synth_tc(const TcUnit *__restrict__ units, int nunits, const double *__restric
       for (int i = 0; i < TC_MAX_ROWS / 128; i++) {
         const int j = row0 + tid + 128 * i;
         yv[i] = 0.f; dv[i] = 0.f;
-        if (tid + 128 * i < blocks_here * TC_KR && j >= 1 && j <= J) { const float4 q = __ldg(&col[j - 1]); yv[i] = q.x; dv[i] = q.z; }
+        if (tid + 128 * i < blocks_here * TC_KR && j >= 1 && j <= J) { const float2 q = __ldg(&col[j - 1]); yv[i] = q.x; dv[i] = q.y; }
         mx = fmaxf(mx, fmaxf(fabsf(yv[i]), fabsf(dv[i])));
       }
 #pragma unroll
