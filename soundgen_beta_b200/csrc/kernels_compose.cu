@@ -104,7 +104,10 @@ __device__ __forceinline__ int sign3(float v, float tol) {
   return (fabsf(v) >= tol) ? (v > 0.0f ? 1 : -1) : 0;
 }
 
-__global__ void __launch_bounds__(COMPOSE_THREADS)
+#ifndef COMPOSE_MIN_CTAS
+#define COMPOSE_MIN_CTAS 4     // one CTA per syllable, bound by memory latency: four resident CTAs (64 registers, some spills) beat two (cfg3: 2.9 -> 2.0 ms)
+#endif
+__global__ void __launch_bounds__(COMPOSE_THREADS, COMPOSE_MIN_CTAS)
 k_compose(const sgb_syllable *__restrict__ syl, int S, SylCtrl *__restrict__ ctrl,
           const SylLayout *__restrict__ lay, Pools P, const double *__restrict__ amp,
           const float *__restrict__ wave, float *__restrict__ raw, const double *__restrict__ anchors,
