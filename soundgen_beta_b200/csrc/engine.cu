@@ -18,7 +18,7 @@
 #include <cstdlib>
 
 // ---- kernel launchers defined in the other translation units ----
-void launch_control(const sgb_syllable *, int, const int32_t *, const double *, const double *, const double *, const Pools &,
+void launch_control(const sgb_syllable *, int, bool, const int32_t *, const double *, const double *, const double *, const Pools &,
                     SylCtrl *, SylLayout *, int64_t *, cudaStream_t);
 void launch_tiles_amp(const sgb_syllable *, int, const SylCtrl *, const SylLayout *, const Pools &, SynthTile *,
                       int64_t *, double *, float4 *, cudaStream_t);
@@ -193,6 +193,7 @@ struct sgb_batch {
   struct RunState *rs = nullptr;     // state carried from run_begin to run_finish
   std::vector<double> late_rows;     // host-drawn formant tracks set between begin and finish
   std::vector<int32_t> h_order;
+  bool ctrl_dense = false;
   std::vector<int> late_envs;        // the envelopes they belong to (deferred again at the next run_begin)
   size_t n_frefs_uploaded = 0;
   bool envs_dirty = false;
@@ -516,6 +517,11 @@ int sgb_batch_upload(sgb_batch *b, const sgb_batch_desc *D) {
       return la > lc;
     });
     if ((rc = upload_array(b, b->d_order, order.data(), sizeof(int32_t) * (size_t)S))) return rc;
+    // K0 variant: with no syllable longer than twice the mean, more resident syllables beat fewer registers
+    int64_t sum_len = 0; int max_len = 0, nv = 0;
+    for (int s = 0; s < S; s++)
+      if (b->syls[s].kind == 1) { sum_len += b->syls[s].pitch_len; max_len = std::max(max_len, (int)b->syls[s].pitch_len); nv++; }
+    b->ctrl_dense = nv >= 2048 && (int64_t)max_len * nv <= 2 * sum_len;
   }
   if ((rc = upload_array(b, b->d_noises, D->noises, sizeof(sgb_noise) * D->n_noises))) return rc;
   if ((rc = upload_array(b, b->d_envs, D->envelopes, sizeof(sgb_envelope) * D->n_envelopes))) return rc;
@@ -754,7 +760,7 @@ int sgb_batch_run_begin(sgb_batch *b) {
   }();
   const int tc_min_rows = g_synth_min_rows_override >= 0 ? g_synth_min_rows_override : tc_min_rows_env;
   synth_min_rows_set(tc_min_rows);
-  launch_control(d_syl, S, b->d_order.as<int32_t>(), b->d_pitch.as<double>(), b->d_anchors.as<double>(), b->d_z.as<double>(), P, d_ctrl, d_lay,
+  launch_control(d_syl, S, b->ctrl_dense, b->d_order.as<int32_t>(), b->d_pitch.as<double>(), b->d_anchors.as<double>(), b->d_z.as<double>(), P, d_ctrl, d_lay,
                  d_tot, st);
   CKL("launch_control");
   launches += 2;

@@ -6,7 +6,11 @@
 // upsampling knots -- R/source.R:206-385.
 #define CTRL_THREADS 32   // one warp per syllable: the stage is bound by the latency of its sequential
                           // part, so what matters is how many syllables are resident per SM
-__global__ void __launch_bounds__(CTRL_THREADS, 16)
+// MINB: resident syllables per SM.  16 (128 registers) when the batch has long outliers -- the kernel then ends with its
+// longest lane-0 chain, which spills would stretch; 32 (64 registers, some spills) when the syllables are alike and
+// the stage is a matter of how many of them are in flight (cfg3: 4.4 -> 3.7 ms).  launch_control() picks.
+template <int MINB>
+__global__ void __launch_bounds__(CTRL_THREADS, MINB)
 k_control(const sgb_syllable *syl, int S, const int32_t *__restrict__ order, const double *pitch, const double *anchors,
           const double *z, Pools P, SylCtrl *ctrl, int tc_min_rows) {
   if ((int)blockIdx.x >= S) return;
@@ -67,9 +71,8 @@ k_control(const sgb_syllable *syl, int S, const int32_t *__restrict__ order, con
       pc[SYNTH_PC * g + 5] = d / 4.0;
     }
   }
-  __shared__ double lgt[1024];
-  const bool use_tab = nH <= 1024;
-  if (use_tab) for (int h = 1 + threadIdx.x; h <= nH; h += blockDim.x) lgt[h - 1] = log2((double)h);
+  const bool use_tab = nH <= 1024;       // (the name is historical: log2(h) used to sit in a shared table, whose 8 KB
+                                         // would cap the resident CTAs per SM; it is recomputed where needed)
   __syncthreads();
   const bool ao = C.any_oct != 0;
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
@@ -82,7 +85,7 @@ k_control(const sgb_syllable *syl, int S, const int32_t *__restrict__ order, con
     const double pg = A.ppg[g], rog = A.ro[g], roctg = A.roct[g], rkg = A.rk[g];
     auto probe = [&](int h) {
       if (h < 1 || h > nH) return;
-      double r = rolloff_db_l(h, lgt[h - 1], pg, rog, roctg, rkg, ao, sp.rolloffParab, C.parab_harm, C.parab_a,
+      double r = rolloff_db_l(h, log2((double)h), pg, rog, roctg, rkg, ao, sp.rolloffParab, C.parab_harm, C.parab_a,
                               C.parab_b, C.parab_c, 200.0, sp.throwaway, sp.samplingRate);
       if (r > m) m = r;
     };
@@ -104,7 +107,7 @@ k_control(const sgb_syllable *syl, int S, const int32_t *__restrict__ order, con
   for (int h = 1 + threadIdx.x; h <= nH; h += blockDim.x) {
     if (!use_tab) { A.rowmap[h - 1] = ctrl_rowkept(sp, A, C, h) ? 1 : 0; continue; }
     int kept = 0;
-    const double lh = lgt[h - 1];
+    const double lh = log2((double)h);
     for (int g = 0; g < G && !kept; g++) {
       double r = rolloff_db_l(h, lh, A.ppg[g], A.ro[g], A.roct[g], A.rk[g], ao, sp.rolloffParab, C.parab_harm,
                               C.parab_a, C.parab_b, C.parab_c, 200.0, sp.throwaway, sp.samplingRate);
@@ -431,9 +434,10 @@ k_rolloff_api(const double *p, int G, int nH, const double *ro, int n_ro, const 
 static int g_tc_min_rows = 1 << 30;      // K1 dispatch (engine.cu): epochs with >= this many rows go to k_synth_tc
 void synth_min_rows_set(int v) { g_tc_min_rows = v; }
 int synth_min_rows() { return g_tc_min_rows; }
-void launch_control(const sgb_syllable *syl, int S, const int32_t *order, const double *pitch, const double *anchors, const double *z,
+void launch_control(const sgb_syllable *syl, int S, bool dense, const int32_t *order, const double *pitch, const double *anchors, const double *z,
                     const Pools &P, SylCtrl *ctrl, SylLayout *lay, int64_t *totals, cudaStream_t st) {
-  k_control<<<S, CTRL_THREADS, 0, st>>>(syl, S, order, pitch, anchors, z, P, ctrl, g_tc_min_rows);
+  if (dense) k_control<32><<<S, CTRL_THREADS, 0, st>>>(syl, S, order, pitch, anchors, z, P, ctrl, g_tc_min_rows);
+  else k_control<16><<<S, CTRL_THREADS, 0, st>>>(syl, S, order, pitch, anchors, z, P, ctrl, g_tc_min_rows);
   k_scan_sizes<<<1, 1024, 0, st>>>(ctrl, S, lay, totals);
 }
 void launch_tiles_amp(const sgb_syllable *syl, int S, const SylCtrl *ctrl, const SylLayout *lay, const Pools &P,
