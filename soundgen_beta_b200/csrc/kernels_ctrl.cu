@@ -215,10 +215,13 @@ __global__ void k_build_tiles(const SylCtrl *ctrl, int S, const SylLayout *lay, 
 #define AMP_MAXH 1024
 #define AMP_MAXS 16
 #define AMP_CG 32
+#ifndef AMP_MIN_CTAS
+#define AMP_MIN_CTAS 4      // resident CTAs per SM (64 registers): measured 2 / 3 / 4 / 5 / 6 -> cfg3 6.0 / 5.8 / 5.9 / 6.7 / 7.0 ms, preset sweep 17.7 / 15.3 / 14.3 / 14.7 / 16.9 ms
+#endif
 #define AMP_RPT 4
 #define AMP_VF 1024      // f-harmonics per column the dense variant keeps in shared memory
 #define AMP_DR 10        // rows per thread of the dense variant (rows <= 2560)
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, AMP_MIN_CTAS)
 k_amp(const sgb_syllable *syl, int S, const SylCtrl *ctrl, const SylLayout *lay, Pools P, double *amp,
       float4 *amp32, int tc_min_rows) {
   int s = blockIdx.x;
